@@ -1,0 +1,90 @@
+/* lesvgpu.h -- C ABI of liblesvgpu.so, the B200 (sm_100a) implementation of lesv's mapping /
+ * SV-signature hot path.  Plain pointers and sizes only; every entry point names the reference
+ * interface it stands in for (paths relative to the reference's src/).
+ *
+ * Conventions kept from the reference:
+ *   - the caller owns all input buffers and all FILE*s; results the library allocates stay valid
+ *     until the next call on the same context (or lesvgpu_ctx_destroy);
+ *   - "no alignment" is a normal outcome (ok = 0), not an error; fatal conditions return a
+ *     non-zero status and the driver decides (the reference's drivers HBN_ERR -> abort());
+ *   - one feeder thread per context; a context is bound to one GPU.  There is NO CPU fallback:
+ *     without a usable GPU lesvgpu_ctx_create fails.
+ */
+#ifndef LESVGPU_H
+#define LESVGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lesvgpu_ctx lesvgpu_ctx;
+
+enum {
+    LESVGPU_OK = 0,
+    LESVGPU_E_CUDA = 1,      /* CUDA runtime error, see lesvgpu_last_error */
+    LESVGPU_E_ARG = 2,       /* invalid argument */
+    LESVGPU_E_NOMEM = 3,     /* a single alignment does not fit the traceback arena */
+    LESVGPU_E_NOGPU = 4      /* no CUDA device / wrong architecture */
+};
+
+/* ---- context -------------------------------------------------------------------------------- */
+
+int lesvgpu_device_count(void);
+/* arena_bytes = HBM reserved for traceback matrices (0 = 80 % of the free memory, grown lazily). */
+int lesvgpu_ctx_create(int device, size_t arena_bytes, lesvgpu_ctx** ctx);
+void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx);
+const char* lesvgpu_last_error(const lesvgpu_ctx* ctx);
+
+/* Device-side timings of the last batch call, CUDA events on the launching stream. */
+typedef struct {
+    float h2d_ms;            /* host -> device copies of the inputs                    */
+    float pack_ms;           /* 2-bit packing / extraction kernels                      */
+    float dp_ms;             /* ksw_dp_kernel launches (DP + traceback walk)            */
+    float scan_ms;           /* alignment-scan kernels (trim, identity, gap runs)       */
+    float d2h_ms;            /* device -> host copies of the results                    */
+    int   dp_launches;       /* ksw_dp_kernel launches inside dp_ms                     */
+    int   kernel_launches;   /* all kernels launched by the call                        */
+    size_t h2d_bytes, d2h_bytes;
+} lesvgpu_timing;
+void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t);
+
+/* ---- pairwise dual-affine banded global alignment ------------------------------------------
+ * Stands in for
+ *   int nw_ksw2_extd2(Ksw2Data*, int qid, const u8* query, int qfrom, int qto, int qsize,
+ *                     int sid, const u8* subject, int sfrom, int sto, int ssize,
+ *                     int min_align_size, double min_ident_perc, int max_distance,
+ *                     int* qoff, int* qend, int* soff, int* send, double* ident_perc,
+ *                     kstring_t* qaln, kstring_t* saln)           algo/ksw2_wrapper.h:65-85
+ * (algo/ksw2_wrapper.c:97-211 -> ksw_extd2_sse, algo/ksw2_extd2_sse.c:26-393, + ksw_backtrack,
+ * algo/ksw2.h:121-153) in batch form, with the scoring of ksw2_extd2_set_params
+ * (algo/ksw2_wrapper.c:72-95).  query/target point at the already sliced sub-ranges
+ * (query + qfrom, qto - qfrom, ...), residues coded 0..3.
+ */
+typedef struct {
+    const uint8_t* query;  int qlen;
+    const uint8_t* target; int tlen;
+    int max_distance;        /* band; 0 -> (int)(max(qlen,tlen) * 0.1) as ksw2_wrapper.c:121 */
+} lesvgpu_ksw_pair;
+
+typedef struct {
+    int ok;                  /* what nw_ksw2_extd2 returns with min_ident_perc = 0           */
+    int n_cigar;             /* BAM-coded ops (len<<4 | op; 0 = M, 1 = I, 2 = D), first op first */
+    size_t cigar_off;        /* offset (in uint32) of this pair's ops in *cigar_pool          */
+    int aln_size;            /* alignment columns = strlen(qaln)                             */
+    int n_match;             /* identical columns; ident_perc = 100.0 * n_match / aln_size   */
+} lesvgpu_ksw_result;
+
+int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs, int n,
+                      lesvgpu_ksw_result* results, const uint32_t** cigar_pool);
+
+/* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
+ * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */
+int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

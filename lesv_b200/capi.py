@@ -1,0 +1,129 @@
+"""ctypes binding of liblesvgpu.so (include/lesvgpu.h) -- the same C ABI a lesv driver links.
+
+No torch types cross this boundary: numpy arrays are passed as plain pointers.  Importing this
+module never falls back to a CPU path: if the shared library is missing, `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblesvgpu.so")
+
+OK, E_CUDA, E_ARG, E_NOMEM, E_NOGPU = 0, 1, 2, 3, 4
+
+
+class KswPair(C.Structure):
+    _fields_ = [("query", C.c_void_p), ("qlen", C.c_int), ("target", C.c_void_p), ("tlen", C.c_int),
+                ("max_distance", C.c_int)]
+
+
+class KswResult(C.Structure):
+    _fields_ = [("ok", C.c_int), ("n_cigar", C.c_int), ("cigar_off", C.c_size_t),
+                ("aln_size", C.c_int), ("n_match", C.c_int)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("dp_ms", C.c_float),
+                ("scan_ms", C.c_float), ("d2h_ms", C.c_float), ("dp_launches", C.c_int),
+                ("kernel_launches", C.c_int), ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen liblesvgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    lib.lesvgpu_device_count.restype = C.c_int
+    lib.lesvgpu_ctx_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.lesvgpu_ctx_destroy.argtypes = [C.c_void_p]
+    lib.lesvgpu_last_error.argtypes = [C.c_void_p]
+    lib.lesvgpu_last_error.restype = C.c_char_p
+    lib.lesvgpu_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    lib.lesvgpu_ksw_batch.argtypes = [C.c_void_p, C.POINTER(KswPair), C.c_int, C.POINTER(KswResult),
+                                      C.POINTER(C.POINTER(C.c_uint32))]
+    lib.lesvgpu_ksw_cells.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.lesvgpu_ksw_cells.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One GPU, one feeder thread (lesvgpu_ctx)."""
+
+    def __init__(self, device: int = 0, arena_bytes: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.lesvgpu_ctx_create(device, arena_bytes, C.byref(h))
+        if rc != OK:
+            raise RuntimeError(f"lesvgpu_ctx_create(device={device}) failed with status {rc} "
+                               "(no B200 / sm_100 GPU visible?)")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.lesvgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def error(self) -> str:
+        return self.lib.lesvgpu_last_error(self.h).decode()
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self.lib.lesvgpu_last_timing(self.h, C.byref(t))
+        return t
+
+    def ksw_batch(self, queries, targets, max_distances, want_cigars: bool = True):
+        """Batch form of nw_ksw2_extd2. queries/targets: lists of uint8 code arrays.
+
+        Returns (results, cigars): results is a ctypes array of KswResult, cigars a list of numpy
+        uint32 arrays (BAM-coded, first op first) or None per pair.
+        """
+        n = len(queries)
+        pairs = (KswPair * n)()
+        keep = []
+        for i in range(n):
+            q = np.ascontiguousarray(queries[i], dtype=np.uint8)
+            t = np.ascontiguousarray(targets[i], dtype=np.uint8)
+            keep.append((q, t))
+            pairs[i].query = q.ctypes.data
+            pairs[i].qlen = len(q)
+            pairs[i].target = t.ctypes.data
+            pairs[i].tlen = len(t)
+            pairs[i].max_distance = int(max_distances[i])
+        res = (KswResult * n)()
+        pool = C.POINTER(C.c_uint32)()
+        rc = self.lib.lesvgpu_ksw_batch(self.h, pairs, n, res, C.byref(pool))
+        if rc != OK:
+            raise RuntimeError(f"lesvgpu_ksw_batch failed ({rc}): {self.error()}")
+        cigars = None
+        if want_cigars:
+            cigars = []
+            for i in range(n):
+                if res[i].ok:
+                    a = np.ctypeslib.as_array(pool, shape=(res[i].cigar_off + res[i].n_cigar,))
+                    cigars.append(a[res[i].cigar_off:].copy())
+                else:
+                    cigars.append(None)
+        return res, cigars
+
+
+def ksw_cells(qlen: int, tlen: int, max_distance: int):
+    ok = C.c_int()
+    c = load().lesvgpu_ksw_cells(qlen, tlen, max_distance, C.byref(ok))
+    return int(c), bool(ok.value)

@@ -1,0 +1,379 @@
+// ksw_core.cuh -- per-thread arithmetic core of the banded dual-affine DP kernel (K-ksw).
+//
+// Replaces: ksw_extd2_sse (reference src/algo/ksw2_extd2_sse.c:26-393, flag = 0, zdrop = -1)
+// with the scoring fixed by ksw2_extd2_set_params (src/algo/ksw2_wrapper.c:72-95):
+// match +2, mismatch -5, gap = min(5 + 4l, 56 + 1l).
+//
+// The file is written once for device and host: on the device the packed helpers map to the
+// sm_100a SIMD-in-register instructions (VIADD.16x2, VIMNMX3.S16x2, VIADDMNMX.S16x2, PRMT,
+// SHF); on the host they are scalar restatements so that tests/emul can run the *same* update
+// code single-threaded on a CPU and compare it with the oracle.  The host build is a test
+// vehicle only -- the product never executes it.
+//
+// ---------------------------------------------------------------------------------------------
+// Formulation.  The reference keeps, per target column t, the int8 differences u,v,x,y,x2,y2
+// and per anti-diagonal r computes for every column of the 16-aligned band
+//     z = max(s, a = x[t-1]+v[t-1], b = y[t]+u[t], a2 = x2[t-1]+v[t-1], b2 = y2[t]+u[t])
+// (first maximum wins, order s,a,b,a2,b2), clamps z to +2, and updates
+//     u' = z - v[t-1]   v' = z - u[t]
+//     x' = max(a - z + q, 0) - (q+e)     (likewise y', and x2'/y2' with q2,e2)
+// storing one traceback byte: winner index | 4 "gap is being extended" flags.  All of it is
+// 8-bit two's-complement arithmetic WITH wrap-around, and the wrap-around is observable: columns
+// of the 16-aligned band that lie outside the band proper are computed from band-edge garbage,
+// overflow int8 (measured on the oracle, tests/test_oracle_ksw.py), and feed back into the
+// band-edge cells of later rows.
+//
+// Here one 32-bit register holds TWO columns in signed 16-bit lanes, each lane = 256*value + tag:
+// the int8 value sits in the HIGH byte, so VIADD.16x2's mod-2^16 wrap IS the int8 wrap and
+// VIMNMX's signed 16-bit compare IS the int8 compare with the low byte breaking ties.  Pair j of a
+// 16-column block holds columns (j, j+8), so "one column to the left" of pair j is pair j-1 (one
+// PRMT per block fixes up pair 0).  State per column (lane):
+//     U = 256u + 127      V = 256v + 127
+//     AX = 256*max(a',0)  with x = AX/256 - (q+e);  AY, AX2, AY2 likewise (low byte 0)
+//     S = 256s + 4                                    (tag = 4 - winner index)
+// Row update of a pair:
+//     Va = V[t-1] + (256*-(q+e)   + 3 - 127)    ka  = AX[t-1]  + Va = 256a  + 3
+//     Vb = V[t-1] + (256*-(q2+e2) + 1 - 127)    ka2 = AX2[t-1] + Vb = 256a2 + 1
+//     Ua = U + (256*-(q+e) + 2 - 127)           kb  = AY  + Ua = 256b  + 2
+//     Ub = U + (256*-(q2+e2) + 0 - 127)         kb2 = AY2 + Ub = 256b2 + 0
+//     k  = max(S, ka, kb, ka2, kb2)             tag = k & 7
+//     Zc = min(k | 0xFF, 0x02FF) = 256z + 255   (clamp z <= 2)
+//     U' = Zc + ~V[t-1]    V' = Zc + ~U         (~w = -w-1 per lane; 255 - 127 - 1 = 127)
+//     AX'  = relu(ka  + (~Zc + 256(q+1)  - 3))  = 256*max(a - z + q, 0)
+//     AY'  = relu(kb  + (~Zc + 256(q+1)  - 2))
+//     AX2' = relu(ka2 + (~Zc + 256(q2+1) - 1))   AY2' = relu(kb2 + (~Zc + 256(q2+1)))
+// and the flag "x' > -(q+e)" is "high byte of AX' != 0", tested 4 columns at a time after a byte
+// permute ((bytes + 0x7f) & 0x80).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KSW_HD __host__ __device__ __forceinline__
+#define KSW_HDC __host__ __device__ constexpr
+#else
+#define KSW_HD inline
+#define KSW_HDC constexpr
+#endif
+
+namespace lesvksw {
+
+// ---- scoring in force (ksw2_wrapper.c:83-94) and what ksw_extd2_sse derives from it ----------
+constexpr int kMatch = 2, kMismatch = -5;
+constexpr int kQ = 5, kE = 4, kQ2 = 56, kE2 = 1;           // q+e <= q2+e2, no swap (:70)
+constexpr int kLongThres = 16;                              // (q2-q)/(e-e2)-1, not bumped (:94-96)
+constexpr int kLongDiff = kLongThres * (kE - kE2) - (kQ2 - kQ) - kE2;   // -4 (:97)
+static_assert(kLongDiff == -4, "long_diff");
+static_assert(!(kQ2 + kE2 + kLongThres * kE2 > kQ + kE + kLongThres * kE), "long_thres bump");
+
+// ---- lane representation: 256*value + tag ---------------------------------------------------
+constexpr int kLUV = 127;                                   // low byte of U and V
+constexpr int kTagS = 4, kTagA = 3, kTagB = 2, kTagA2 = 1, kTagB2 = 0;
+KSW_HDC uint32_t dup(int v) { return (uint32_t)(v & 0xFFFF) | ((uint32_t)(v & 0xFFFF) << 16); }
+constexpr uint32_t kVa = dup(256 * -(kQ + kE) + kTagA - kLUV);
+constexpr uint32_t kVb = dup(256 * -(kQ2 + kE2) + kTagA2 - kLUV);
+constexpr uint32_t kUa = dup(256 * -(kQ + kE) + kTagB - kLUV);
+constexpr uint32_t kUb = dup(256 * -(kQ2 + kE2) + kTagB2 - kLUV);
+constexpr uint32_t kClampZ = dup(256 * kMatch + 255);
+constexpr uint32_t kNZa = dup(256 * (kQ + 1) - kTagA), kNZb = dup(256 * (kQ + 1) - kTagB);
+constexpr uint32_t kNZa2 = dup(256 * (kQ2 + 1) - kTagA2), kNZb2 = dup(256 * (kQ2 + 1) - kTagB2);
+constexpr uint32_t kInitU = dup(256 * -(kQ + kE) + kLUV);   // u = v = -(q+e)
+constexpr uint32_t kInitS = dup(256 * 0 + kTagS);           // calloc()ed s[] = 0
+constexpr uint32_t kSMatch = dup(256 * kMatch + kTagS);
+constexpr uint32_t kSStep = (uint32_t)((256 * (kMismatch - kMatch)) & 0xFFFF);   // 0xF900, no carry out of a lane
+static_assert(256 * kMatch + kTagS + (int)kSStep < 65536, "score select stays inside its lane");
+
+// value the reference writes into u[r] (top row) and uses as v1 at column 0 (:150, :154)
+KSW_HD int first_gap_diff(int r)
+{
+    return r == 0 ? -(kQ + kE) : r < kLongThres ? -kE : r == kLongThres ? kLongDiff : -kE2;
+}
+
+// ---- packed 16x2 helpers -----------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+KSW_HD uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+KSW_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+KSW_HD uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+KSW_HD uint32_t vaddrelu(uint32_t a, uint32_t b) { return __viaddmax_s16x2_relu(a, b, 0u); }
+KSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t r;                              // PTX prmt: selector bit 3 = replicate the byte's sign
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
+KSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+#else
+KSW_HD int16_t lo16(uint32_t a) { return (int16_t)(a & 0xFFFF); }
+KSW_HD int16_t hi16(uint32_t a) { return (int16_t)(a >> 16); }
+KSW_HD uint32_t mk2(int lo, int hi) { return (uint32_t)(lo & 0xFFFF) | ((uint32_t)(hi & 0xFFFF) << 16); }
+KSW_HD uint32_t vadd2(uint32_t a, uint32_t b) { return mk2(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+KSW_HD int max_i(int a, int b) { return a > b ? a : b; }
+KSW_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c)
+{
+    return mk2(max_i(max_i(lo16(a), lo16(b)), lo16(c)), max_i(max_i(hi16(a), hi16(b)), hi16(c)));
+}
+KSW_HD uint32_t vmin2(uint32_t a, uint32_t b)
+{
+    return mk2(lo16(a) < lo16(b) ? lo16(a) : lo16(b), hi16(a) < hi16(b) ? hi16(a) : hi16(b));
+}
+KSW_HD uint32_t vaddrelu(uint32_t a, uint32_t b)
+{
+    return mk2(max_i((int16_t)(lo16(a) + lo16(b)), 0), max_i((int16_t)(hi16(a) + hi16(b)), 0));
+}
+KSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint64_t ab = (uint64_t)b << 32 | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)((ab >> (8 * (sel & 7))) & 0xFF);
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+KSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+    s &= 31;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
+#endif
+
+// ---- internal traceback byte -------------------------------------------------------------------
+// bits 0-2: 4 - winner (winner 0 H, 1 E, 2 F, 3 E~, 4 F~); bit 7: E continues; bit 6: F continues;
+// bit 5: E~ continues; bit 4: F~ continues; bit 3: 0.  (The reference's own layout, ksw2.h:117-120,
+// is winner | flags at bits 3..6; only our backtrack kernel reads this one.)
+KSW_HD int tb_cont_bit(int state) { return 8 - state; }
+KSW_HD int tb_winner(uint32_t byte) { return 4 - (int)(byte & 7); }
+// byte position of column c (0..15) inside the 16-byte block written per thread per row
+KSW_HD int tb_byte_pos(int c) { return 4 * ((c & 7) >> 1) + 2 * (c & 1) + (c >> 3); }
+
+// ---- per-block register state -----------------------------------------------------------------
+struct BlockState {
+    uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8];    // X.. = AX.. of the header comment
+    KSW_HD void init()
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            U[j] = kInitU; V[j] = kInitU; X[j] = 0u; Y[j] = 0u;
+            X2[j] = 0u; Y2[j] = 0u; S[j] = kInitS;
+        }
+    }
+};
+
+// Left-neighbour values entering a block at column -1: X^, V^ (low/high lane of xv) and X2^.
+struct Carry {
+    uint32_t xv;    // lo = X^[-1], hi = V^[-1]
+    uint32_t x2;    // lo = X2^[-1]
+};
+KSW_HD Carry carry_init()
+{
+    Carry c; c.xv = kInitU & 0xFFFF0000u; c.x2 = 0u; return c;
+}
+KSW_HD Carry carry_left_boundary(int r)     // column 0, :148-151
+{
+    Carry c;
+    c.xv = (uint32_t)((256 * first_gap_diff(r) + kLUV) & 0xFFFF) << 16;
+    c.x2 = 0u;
+    return c;
+}
+
+// expand bit (7-sh) .. of a 16-bit column mask to a lane mask for pair j (columns j, j+8)
+KSW_HD uint32_t lane_mask(uint32_t m16, int j)
+{
+    // bit j -> low lane, bit j+8 -> high lane
+    uint32_t t = m16 << (7 - j);             // bit j at bit 7, bit j+8 at bit 15
+    return prmt(t, 0, 0x9988);               // replicate the sign of byte 0 / byte 1
+}
+
+// mismatch bits of a block: bit 2c set iff target column c differs from the query base under it
+KSW_HD uint32_t mismatch_bits(uint32_t tword, uint32_t qword)
+{
+    uint32_t x = tword ^ qword;
+    return (x | (x >> 1)) & 0x55555555u;
+}
+
+// Refresh S^ for the columns in fresh16 (bit c = column c gets a new score this row).
+template <bool kAllFresh>
+KSW_HD void update_scores(BlockState& b, uint32_t mis, uint32_t fresh16)
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t e = (mis >> (2 * j)) & 0x00010001u;
+        uint32_t s = e * kSStep + kSMatch;                    // per lane: match or mismatch
+        if (kAllFresh) b.S[j] = s;
+        else {
+            uint32_t m = lane_mask(fresh16, j);
+            b.S[j] = (s & m) | (b.S[j] & ~m);
+        }
+    }
+}
+
+// One anti-diagonal step of a 16-column block.  `cin` holds the previous-row values of the column
+// left of the block; on return `cout` holds this row's values of column 15 and tb[0..3] the 16
+// traceback bytes (column order given by tb_byte_pos).
+KSW_HD void block_row(BlockState& b, const Carry cin, Carry& cout, uint32_t tb[4])
+{
+    // previous-row left neighbours of pair 0 = (column -1, column 7)
+    const uint32_t xl0 = prmt(cin.xv, b.X[7], 0x5410);     // lo = cin X, hi = X[7].lo
+    const uint32_t vl0 = prmt(cin.xv, b.V[7], 0x5432);     // lo = cin V, hi = V[7].lo
+    const uint32_t x2l0 = prmt(cin.x2, b.X2[7], 0x5410);
+    uint32_t kk[8];
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {          // descending: pair j-1 still holds the previous row
+        const uint32_t x1 = j ? b.X[j - 1] : xl0;
+        const uint32_t v1 = j ? b.V[j - 1] : vl0;
+        const uint32_t x21 = j ? b.X2[j - 1] : x2l0;
+        const uint32_t u0 = b.U[j];
+        const uint32_t ka = vadd2(x1, vadd2(v1, kVa)), kb = vadd2(b.Y[j], vadd2(u0, kUa));
+        const uint32_t ka2 = vadd2(x21, vadd2(v1, kVb)), kb2 = vadd2(b.Y2[j], vadd2(u0, kUb));
+        uint32_t k = vmax3(b.S[j], ka, kb);
+        k = vmax3(k, ka2, kb2);
+        kk[j] = k;
+        const uint32_t zc = vmin2(k | 0x00FF00FFu, kClampZ);
+        const uint32_t nz = ~zc;
+        b.U[j] = vadd2(zc, ~v1);
+        b.V[j] = vadd2(zc, ~u0);
+        b.X[j] = vaddrelu(ka, vadd2(nz, kNZa));
+        b.Y[j] = vaddrelu(kb, vadd2(nz, kNZb));
+        b.X2[j] = vaddrelu(ka2, vadd2(nz, kNZa2));
+        b.Y2[j] = vaddrelu(kb2, vadd2(nz, kNZb2));
+    }
+    cout.xv = prmt(b.X[7], b.V[7], 0x7632);      // lo = X[7].hi, hi = V[7].hi  (column 15)
+    cout.x2 = b.X2[7] >> 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {           // 4 columns per instruction from here on
+        const int j = 2 * i;
+        const uint32_t pk = prmt(kk[j], kk[j + 1], 0x6420);              // tags, 0..4
+        const uint32_t fx = prmt(b.X[j], b.X[j + 1], 0x7531) + 0x7F7F7F7Fu;   // bit 7 of a byte = value != 0
+        const uint32_t fy = (prmt(b.Y[j], b.Y[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 1;
+        const uint32_t fx2 = (prmt(b.X2[j], b.X2[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 2;
+        const uint32_t fy2 = (prmt(b.Y2[j], b.Y2[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 3;
+        uint32_t m = pk | (fx & 0x80808080u);
+        m |= fy & 0x40404040u;
+        m |= fx2 & 0x20202020u;
+        m |= fy2 & 0x10101010u;
+        tb[i] = m;
+    }
+}
+
+// Backtrack state machine, one step (ksw_backtrack, ksw2.h:121-153, is_rot = 1, min_intron_len = 0).
+// `byte` is the internal traceback byte (ignored when force >= 0).  Returns the new state:
+// 0 = diagonal move, 1/3 = deletion (consume target), 2/4 = insertion (consume query).
+KSW_HD int tb_next_state(int state, uint32_t byte, int force)
+{
+    if (force >= 0) return force;
+    if (state != 0 && !((byte >> tb_cont_bit(state)) & 1)) state = 0;
+    if (state == 0) state = tb_winner(byte);
+    return state;
+}
+
+// ---- band geometry (ksw2_extd2_sse.c:124-139) -------------------------------------------------
+struct RowGeom {
+    int st0, en0;      // band proper
+    int wr;            // last column whose score byte is rewritten this row (:158)
+    KSW_HD bool empty() const { return st0 > en0; }
+};
+KSW_HD RowGeom row_geom(int r, int qlen, int tlen, int w)
+{
+    RowGeom g;
+    int st = 0, en = tlen - 1;
+    if (st < r - qlen + 1) st = r - qlen + 1;
+    if (en > r) en = r;
+    if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+    if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+    g.st0 = st; g.en0 = en;
+    g.wr = st + (((en - st) >> 4) + 1) * 16 - 1;
+    return g;
+}
+// blocks per traceback row = n_col_ of the reference (:85-86)
+KSW_HD int tb_row_blocks(int qlen, int tlen, int w)
+{
+    int n = qlen < tlen ? qlen : tlen;
+    n = n < w + 1 ? n : w + 1;
+    return (n + 15) / 16 + 1;
+}
+
+// ---- the per-thread row step shared by the kernel and the host emulation ----------------------
+// A thread owns, at any row, the unique block B = bst + ((tid - bst) mod NT) of the live window.
+struct ThreadCtx {
+    BlockState b;
+    int myB;               // block currently held (-1 = none)
+    uint32_t tword;        // 16 target bases of block myB, 2 bits each, column c at bits 2c
+    uint32_t qlo, qhi;     // window into the packed reversed query: words qwi, qwi+1 of qrp
+    int qwi;
+};
+
+KSW_HD int owned_block(int tid, int nt, int bst)
+{
+    int d = (tid - bst) % nt;
+    if (d < 0) d += nt;
+    return bst + d;
+}
+
+// tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by
+// +1 (qrp[0] is a zero pad word so that index -1..-16 reads zeros).
+// Returns true if the thread computed DP cells this row (then cout/tb are valid).
+KSW_HD bool thread_row_step(ThreadCtx& c, int tid, int nt, int r, int qlen, int tlen, int w,
+                            const uint32_t* tp, const uint32_t* qrp,
+                            const Carry cin_from_left, Carry& cout, uint32_t tb[4], int& tb_block)
+{
+    const RowGeom g = row_geom(r, qlen, tlen, w);
+    const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
+    const int B = owned_block(tid, nt, bst);
+    if (B > bwr) return false;
+    if (B != c.myB) {                       // take ownership of a new block
+        c.myB = B;
+        c.b.init();
+        c.tword = tp[B];
+        c.qwi = -0x7fffffff;
+    }
+    // reversed-query index under column 0 of the block; it slides down by one per row
+    const int qbase = qlen - 1 - r + 16 * B;
+    const int wi = (qbase >> 4) + 1;        // arithmetic shift = floor; +1 skips the pad word
+    if (wi != c.qwi) {
+        if (wi == c.qwi - 1) { c.qhi = c.qlo; c.qlo = qrp[wi]; }
+        else { c.qlo = qrp[wi]; c.qhi = qrp[wi + 1]; }
+        c.qwi = wi;
+    }
+    const uint32_t qword = funnel_r(c.qlo, c.qhi, 2 * (qbase & 15));
+    const uint32_t mis = mismatch_bits(c.tword, qword);
+    const int c0 = 16 * B;
+    const bool interior = c0 >= g.st0 && c0 + 15 <= g.en0;
+    if (interior) update_scores<true>(c.b, mis, 0xFFFF);
+    else {
+        // fresh columns: st0 <= c0 + col <= wr
+        int lo = g.st0 - c0, hi = g.wr - c0;
+        lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
+        uint32_t fresh = lo <= hi ? ((0xFFFFu >> (15 - hi)) & (0xFFFFu << lo)) & 0xFFFFu : 0u;
+        update_scores<false>(c.b, mis, fresh);
+    }
+    if (B > ben) return false;              // pre-block: only its score bytes exist so far
+    if ((r >> 4) == B) {                    // top row of the matrix reaches column r: :152-155
+        const int col = r & 15, j = col & 7;
+        const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
+        const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            if (jj == j) {
+                c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
+                c.b.Y[jj] &= ~m;            // y = -(q+e), y2 = -(q2+e2)
+                c.b.Y2[jj] &= ~m;
+            }
+    }
+    Carry cin;
+    if (B == 0) cin = carry_left_boundary(r);
+    else {
+        // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
+        bool left_live = false;
+        if (r > 0) {
+            const RowGeom gp = row_geom(r - 1, qlen, tlen, w);
+            left_live = B - 1 >= (gp.st0 >> 4);
+        }
+        cin = left_live ? cin_from_left : carry_init();
+    }
+    block_row(c.b, cin, cout, tb);
+    tb_block = B - bst;
+    return true;
+}
+
+}  // namespace lesvksw

@@ -72,9 +72,30 @@ static uint32_t* push_cigar(int* n, int* m, uint32_t* cigar, uint32_t op, int le
     return cigar;
 }
 
+static int ksw_extd2_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                          const lesv_oracle_ksw_params* prm, int w,
+                          uint32_t** cigar_out, int* score_out, uint8_t** tb_out, int* tb_row_bytes);
+
 int lesv_oracle_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                           const lesv_oracle_ksw_params* prm, int w,
                           uint32_t** cigar_out, int* score_out)
+{
+    return ksw_extd2_impl(qlen, query, tlen, target, prm, w, cigar_out, score_out, NULL, NULL);
+}
+
+/* Same, but also hands back the whole traceback matrix p[] (reference byte layout, ksw2.h:117-120;
+ * row r starts at r * *tb_row_bytes and covers columns off[r] = st0/16*16 onward). Used by the
+ * tests to compare every in-matrix cell of the aligned band, not just the cells on the path. */
+int lesv_oracle_ksw_extd2_tb(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                             const lesv_oracle_ksw_params* prm, int w,
+                             uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes)
+{
+    return ksw_extd2_impl(qlen, query, tlen, target, prm, w, cigar_out, NULL, tb_out, tb_row_bytes);
+}
+
+static int ksw_extd2_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                          const lesv_oracle_ksw_params* prm, int w,
+                          uint32_t** cigar_out, int* score_out, uint8_t** tb_out, int* tb_row_bytes)
 {
     int8_t q = prm->q, e = prm->e, q2 = prm->q2, e2 = prm->e2;
     const int8_t sc_mch = prm->match, sc_mis = prm->mismatch;
@@ -82,6 +103,7 @@ int lesv_oracle_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_
     /* sc_N_: mat[m*m-1] is sc_ambi (!= 0) -> that value (:79) */
     const int8_t sc_N = prm->ambi == 0 ? (int8_t)-e2 : (int8_t)(prm->ambi > 0 ? -prm->ambi : prm->ambi);
     *cigar_out = NULL;
+    if (tb_out) *tb_out = NULL;
     if (score_out) *score_out = NEG_INF;
     if (qlen <= 0 || tlen <= 0) return 0;
     if (q2 + e2 < q + e) { int8_t t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }   /* :70 */
@@ -112,7 +134,7 @@ int lesv_oracle_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_
     for (size_t t = 0; t < A; ++t) H[t] = NEG_INF;
     const size_t nrow = (size_t)qlen + tlen - 1;
     const size_t prow = (size_t)n_col_ * 16;
-    uint8_t* p = (uint8_t*)malloc(nrow * prow + 16);
+    uint8_t* p = (uint8_t*)calloc(nrow * prow + 16, 1);
     int* off = (int*)malloc(nrow * sizeof(int) * 2);
     int* off_end = off + nrow;
     for (int t = 0; t < qlen; ++t) qr[t] = query[qlen - 1 - t];
@@ -235,7 +257,8 @@ int lesv_oracle_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_
             uint32_t t = cigar[i]; cigar[i] = cigar[n_cigar - 1 - i]; cigar[n_cigar - 1 - i] = t;
         }
     }
-    free(mem); free(H); free(p); free(off);
+    free(mem); free(H); free(off);
+    if (tb_out) { *tb_out = p; *tb_row_bytes = (int)prow; } else free(p);
     *cigar_out = cigar;
     return n_cigar;
 }

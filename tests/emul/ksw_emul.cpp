@@ -1,0 +1,114 @@
+// ksw_emul.cpp -- single-threaded CPU run of the K-ksw kernel's per-thread update code.
+// TEST VEHICLE ONLY: compiles lesv_b200/csrc/ksw_core.cuh in host mode and steps NT emulated
+// threads row by row exactly as ksw_dp_kernel schedules them (block ownership, carries, pre-block
+// score tracking), then backtracks over the internal traceback bytes.  tests/test_ksw_emul.py
+// compares the CIGARs with the oracle so that kernel logic errors are caught without a GPU.
+#include "../../lesv_b200/csrc/ksw_core.cuh"
+#include <vector>
+#include <cstdlib>
+#include <cstring>
+
+using namespace lesvksw;
+
+// pack 16 bases per word, base k at bits 2(k&15)
+static void pack_words(const uint8_t* s, int n, int reversed, std::vector<uint32_t>& out, int pad_front, int nwords)
+{
+    out.assign(nwords + pad_front, 0u);
+    for (int k = 0; k < n; ++k) {
+        uint32_t c = reversed ? s[n - 1 - k] : s[k];
+        out[pad_front + (k >> 4)] |= (c & 3u) << (2 * (k & 15));
+    }
+}
+
+static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes);
+
+extern "C" int lesv_emul_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                   int w, int nt, uint32_t** cigar_out)
+{
+    return emul_impl(qlen, query, tlen, target, w, nt, cigar_out, nullptr, nullptr);
+}
+// also returns the traceback matrix translated to the reference byte layout (natural column order,
+// flags at bits 3..6, bit 7 clear) so tests can compare it cell by cell with the oracle's
+extern "C" int lesv_emul_ksw_extd2_tb(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                      int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes)
+{
+    return emul_impl(qlen, query, tlen, target, w, nt, cigar_out, tb_out, tb_row_bytes);
+}
+
+static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes)
+{
+    *cigar_out = nullptr;
+    if (qlen <= 0 || tlen <= 0) return 0;
+    if (w < 0) w = tlen > qlen ? tlen : qlen;
+    // band must not be cut (the host library rejects those jobs before launch)
+    for (int r = 0; r < qlen + tlen - 1; ++r) if (row_geom(r, qlen, tlen, w).empty()) return 0;
+    const int prow_blocks = tb_row_blocks(qlen, tlen, w);
+    const size_t prow = (size_t)prow_blocks * 16;
+    const size_t nrow = (size_t)qlen + tlen - 1;
+    std::vector<uint8_t> p(nrow * prow + 16, 0xAA);
+    std::vector<uint32_t> tp, qrp;
+    pack_words(target, tlen, 0, tp, 0, (tlen >> 4) + 4);
+    pack_words(query, qlen, 1, qrp, 1, (qlen >> 4) + 6);
+    std::vector<ThreadCtx> th(nt);
+    for (auto& t : th) { t.myB = -1; t.qwi = -0x7fffffff; }
+    std::vector<Carry> pub(nt), pub_next(nt);
+    for (auto& c : pub) c = carry_init();
+    for (int r = 0; r < (int)nrow; ++r) {
+        const RowGeom g = row_geom(r, qlen, tlen, w);
+        if ((g.wr >> 4) - (g.st0 >> 4) + 1 > nt) return -1;      // window does not fit NT threads
+        for (int tid = 0; tid < nt; ++tid) {
+            Carry cout; uint32_t tb[4]; int tbb = 0;
+            const Carry cin = pub[(tid + nt - 1) % nt];
+            if (thread_row_step(th[tid], tid, nt, r, qlen, tlen, w, tp.data(), qrp.data(), cin, cout, tb, tbb)) {
+                if (tbb < 0 || tbb >= prow_blocks) return -2;
+                memcpy(&p[(size_t)r * prow + (size_t)tbb * 16], tb, 16);
+                pub_next[tid] = cout;
+            } else pub_next[tid] = carry_init();
+        }
+        pub.swap(pub_next);
+    }
+    // backtrack (ksw2.h:121-153) over the internal byte format
+    std::vector<uint32_t> cig;
+    auto push = [&](uint32_t op, int len) {
+        if (cig.empty() || (cig.back() & 0xf) != op) cig.push_back((uint32_t)len << 4 | op);
+        else cig.back() += (uint32_t)len << 4;
+    };
+    int i = tlen - 1, j = qlen - 1, state = 0;
+    while (i >= 0 && j >= 0) {
+        const int r = i + j;
+        const RowGeom g = row_geom(r, qlen, tlen, w);
+        const int off = (g.st0 >> 4) << 4, off_end = ((g.en0 >> 4) << 4) + 15;
+        int force = -1;
+        if (i < off) force = 2;
+        if (i > off_end) force = 1;
+        uint32_t byte = 0;
+        if (force < 0) byte = p[(size_t)r * prow + (size_t)((i >> 4) - (off >> 4)) * 16 + tb_byte_pos(i & 15)];
+        state = tb_next_state(state, byte, force);
+        if (state == 0) { push(0, 1); --i; --j; }
+        else if (state == 1 || state == 3) { push(2, 1); --i; }
+        else { push(1, 1); --j; }
+    }
+    if (i >= 0) push(2, i + 1);
+    if (j >= 0) push(1, j + 1);
+    const int n = (int)cig.size();
+    uint32_t* out = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+    for (int k = 0; k < n; ++k) out[k] = cig[n - 1 - k];
+    *cigar_out = out;
+    if (tb_out) {
+        uint8_t* t = (uint8_t*)calloc(nrow * prow + 16, 1);
+        for (size_t r = 0; r < nrow; ++r) {
+            const RowGeom g = row_geom((int)r, qlen, tlen, w);
+            const int nb = (g.en0 >> 4) - (g.st0 >> 4) + 1;
+            for (int b = 0; b < nb; ++b)
+                for (int c = 0; c < 16; ++c) {
+                    const uint8_t x = p[r * prow + (size_t)b * 16 + tb_byte_pos(c)];
+                    t[r * prow + (size_t)b * 16 + c] = (uint8_t)((4 - (x & 7)) | ((x >> 7) & 1) << 3 | ((x >> 6) & 1) << 4 |
+                                                             ((x >> 5) & 1) << 5 | ((x >> 4) & 1) << 6);
+                }
+        }
+        *tb_out = t; *tb_row_bytes = (int)prow;
+    }
+    return n;
+}

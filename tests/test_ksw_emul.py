@@ -1,0 +1,44 @@
+"""The K-ksw per-thread code (lesv_b200/csrc/ksw_core.cuh), run on the CPU by tests/emul, against
+the oracle: CIGARs for random thread counts, and every in-matrix traceback byte."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_emulated_kernel_cigar_equals_oracle(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = 0
+    for it in range(1500):
+        q, t, w = H.random_pair(rng, it)
+        if not H.oracle_cells(len(q), len(t), w)[1]:
+            continue  # band cut: the library answers ok = 0 without launching
+        need = H.min_threads(len(q), len(t), w)
+        nt = max(need, int(rng.choice([need, need + 1, 64, 128])))
+        a, _ = H.oracle_ksw(q, t, w)
+        b = H.emul_ksw(q, t, w, nt)
+        assert a == b, (it, len(q), len(t), w, nt)
+        n += 1
+    assert n > 800
+
+
+def test_emulated_kernel_traceback_bytes_equal_oracle():
+    rng = np.random.default_rng(7)
+    cells = 0
+    for it in range(400):
+        q, t, w = H.random_pair(rng, it, max_len=400)
+        ql, tl = len(q), len(t)
+        if not H.oracle_cells(ql, tl, w)[1]:
+            continue
+        ww = w if w >= 0 else max(ql, tl)
+        A = H.oracle_tb(q, t, w)
+        B = H.emul_tb(q, t, w, H.min_threads(ql, tl, w))
+        for r in range(ql + tl - 1):
+            st0 = max(0, r - ql + 1, (r - ww + 1) >> 1)
+            en0 = min(tl - 1, r, (r + ww) >> 1)
+            st, en = st0 // 16 * 16, en0 // 16 * 16 + 15
+            lo, hi = max(st, r - ql + 1), min(en, r, tl - 1)   # aligned band ∩ DP matrix
+            assert np.array_equal(A[r, lo - st:hi - st + 1], B[r, lo - st:hi - st + 1]), (it, ql, tl, w, r)
+            cells += hi - lo + 1
+    assert cells > 5_000_000

@@ -1,0 +1,74 @@
+"""K-ksw on the GPU through the C ABI (lesvgpu_ksw_batch) against the oracle: bit-exact CIGARs."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from lesv_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _check(ctx, cases):
+    res, cigs = ctx.ksw_batch([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases])
+    for i, (q, t, w) in enumerate(cases):
+        exp, _ = H.oracle_ksw(q, t, w if w != 0 else int(max(len(q), len(t)) * 0.1))
+        ok = H.oracle_cells(len(q), len(t), w if w != 0 else int(max(len(q), len(t)) * 0.1))[1]
+        if not ok:
+            assert not res[i].ok, i
+            continue
+        assert res[i].ok, (i, len(q), len(t), w)
+        got = [int(x) for x in cigs[i]]
+        assert got == exp, (i, len(q), len(t), w, H.cigar_str(exp)[:80], H.cigar_str(got)[:80])
+        aln = sum(x >> 4 for x in exp)
+        assert res[i].aln_size == aln
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_pairs_bit_exact(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    cases = [H.random_pair(rng, it) for it in range(600)]
+    _check(ctx, cases)
+
+
+def test_noisy_reads_svsig_shape(ctx):
+    """10-12 kb reads at 12 % error with planted indels, band = 1.2 * dist as qx2svsig uses."""
+    from lesv_b200.synth import mutate
+    rng = np.random.default_rng(3)
+    cases = []
+    for it in range(12):
+        q = rng.integers(0, 4, int(rng.integers(3000, 12000)), dtype=np.uint8)
+        t = q.copy()
+        if it % 3 == 1:
+            k = int(rng.integers(500, len(t) - 500)); t = np.concatenate([t[:k], t[k + 300:]])
+        if it % 3 == 2:
+            k = int(rng.integers(500, len(t) - 500)); t = np.concatenate([t[:k], rng.integers(0, 4, 400, dtype=np.uint8), t[k:]])
+        q = mutate(q, 0.12, rng)
+        w = int(int((len(q) + len(t)) * 12.0 / 200) * 1.2) + 400
+        cases.append((np.ascontiguousarray(q), np.ascontiguousarray(t), w))
+    _check(ctx, cases)
+
+
+def test_identity_counts(ctx):
+    rng = np.random.default_rng(9)
+    from lesv_b200.synth import mutate
+    q = rng.integers(0, 4, 2000, dtype=np.uint8)
+    t = mutate(q, 0.1, rng)
+    res, cigs = ctx.ksw_batch([q], [t], [300])
+    qi = si = m = 0
+    for x in cigs[0]:
+        n, op = int(x) >> 4, int(x) & 15
+        if op == 0:
+            m += int((q[qi:qi + n] == t[si:si + n]).sum()); qi += n; si += n
+        elif op == 1:
+            qi += n
+        else:
+            si += n
+    assert (qi, si) == (len(q), len(t))
+    assert res[0].n_match == m
