@@ -80,6 +80,54 @@ typedef struct {
 int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs, int n,
                       lesvgpu_ksw_result* results, const uint32_t** cigar_pool);
 
+/* ---- qx2svsig: per-read SV-signature extraction ---------------------------------------------
+ * Stands in for the body of discover_func (app/necat2sv/find_sv_signature.c:234-380) over one
+ * contig's SvRead array: extract read[qoff,qend) on its strand and contig[soff,send)
+ * (RawReadReader_ExtractSubRead, corelib/raw_reads_reader.c:83-124), nw_ksw2_extd2 with band
+ * (int)(dist*1.2) and, if that band cannot reach the last cell, max(qlen,slen) (:272-316),
+ * truncate_align_bad_ends (algo/hbn_traceback.c:547-606), the optional TRF filter
+ * (trf_array.cpp:74-83), calc_effective_ident_perc >= 70 (algo/hbn_traceback_aux.c:22-95) and
+ * find_sv_signature (find_sv_signature.c:126-220).  The caller keeps the file formats, the read
+ * names and the final sort_svsig_sfrom_lt / INS-then-DEL dump (:222-232, :406-407).
+ */
+typedef struct {            /* SvRead, app/necat2sv/sv_reads.h:11-20 (fields discover_func reads) */
+    int query_id, subject_id;
+    int qdir, qoff, qend, qsize;
+    int soff, send;
+    int dist;
+} lesvgpu_svread;
+
+typedef struct {            /* SvSignature, app/necat2sv/sv_signature.h:11-21 */
+    int qid, qdir;
+    int qfrom, qto, fqfrom, fqto, qsize;
+    int sfrom, sto, fsfrom, fsto, ssize;
+    int type;               /* 0 = DEL (eGapAlignDel), 6 = INS (eGapAlignIns), gapinfo.h:47-53 */
+} lesvgpu_svsig;
+
+typedef struct {
+    int status;             /* 1 signatures scanned; 0 ksw fail; -1 truncate fail; -2 TRF; -3 eff. identity < 70 */
+    int n_sig;              /* signatures this read contributed */
+    int qb, qe, sb, se;     /* trimmed alignment range inside the aligned sub-sequences */
+    int eff_mat, eff_len;   /* calc_effective_ident_perc = 100.0 * eff_mat / eff_len */
+    int band;               /* band the alignment ran with */
+} lesvgpu_svsig_read;
+
+/* The subject volume's 2-bit .pac (CSeqDB.packed_seq / RawReadReader.packed_raw_seq_array) stays
+ * resident in HBM; load it once per context.  A 3.1 Gbp genome is 0.78 GB. */
+int lesvgpu_subject_load(lesvgpu_ctx* ctx, const uint8_t* subject_pac, size_t pac_bytes);
+
+/* query_pac / query_read_offset are RawReadReader.packed_raw_seq_array / .raw_read_offset_array
+ * (residue offset of the read + 1, raw_reads_reader.c:25,160); subject_seq_offset / subject_size
+ * are CSeqInfo.seq_offset / .seq_size of the contig (corelib/seqdb.h:20-27).  trf_mask may be NULL
+ * (TrfArray.trf_array, one byte per subject residue).  *sigs is library-owned (valid until the
+ * next call), grouped by read in input order, each read's records in alignment order. */
+int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
+                        const uint8_t* query_pac, const size_t* query_read_offset,
+                        size_t subject_seq_offset, int subject_size,
+                        const lesvgpu_svread* reads, int n, int min_indel_size,
+                        const char* trf_mask,
+                        lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs);
+
 /* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
  * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */
 int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* ok);

@@ -127,3 +127,59 @@ def ksw_cells(qlen: int, tlen: int, max_distance: int):
     ok = C.c_int()
     c = load().lesvgpu_ksw_cells(qlen, tlen, max_distance, C.byref(ok))
     return int(c), bool(ok.value)
+
+
+class SvRead(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("query_id", "subject_id", "qdir", "qoff", "qend", "qsize", "soff", "send", "dist")]
+
+
+class SvSig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("qid", "qdir", "qfrom", "qto", "fqfrom", "fqto", "qsize", "sfrom", "sto",
+                                       "fsfrom", "fsto", "ssize", "type")]
+
+    def astuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
+class SvSigRead(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("status", "n_sig", "qb", "qe", "sb", "se", "eff_mat", "eff_len", "band")]
+
+
+def _bind_svsig(lib):
+    lib.lesvgpu_subject_load.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.lesvgpu_svsig_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                        C.POINTER(SvRead), C.c_int, C.c_int, C.c_void_p,
+                                        C.POINTER(SvSigRead), C.POINTER(C.POINTER(SvSig)), C.POINTER(C.c_int)]
+
+
+def subject_load(ctx: "Context", pac: np.ndarray):
+    _bind_svsig(ctx.lib)
+    pac = np.ascontiguousarray(pac, dtype=np.uint8)
+    rc = ctx.lib.lesvgpu_subject_load(ctx.h, pac.ctypes.data, pac.size)
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_subject_load failed ({rc}): {ctx.error()}")
+
+
+def svsig_batch(ctx: "Context", query_pac: np.ndarray, query_read_offset: np.ndarray, subject_seq_offset: int,
+                subject_size: int, reads, min_indel: int, trf_mask=None):
+    """discover_func over a list of SvRead tuples
+    (query_id, subject_id, qdir, qoff, qend, qsize, soff, send, dist).
+    Returns (per_read ctypes array, list of signature tuples)."""
+    _bind_svsig(ctx.lib)
+    n = len(reads)
+    arr = (SvRead * n)()
+    for i, r in enumerate(reads):
+        for (name, _), v in zip(SvRead._fields_, r):
+            setattr(arr[i], name, int(v))
+    per = (SvSigRead * max(1, n))()
+    sigs = C.POINTER(SvSig)()
+    n_sigs = C.c_int()
+    query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
+    offs = np.ascontiguousarray(query_read_offset, dtype=np.uint64)
+    trf = None if trf_mask is None else np.ascontiguousarray(trf_mask, dtype=np.uint8)
+    rc = ctx.lib.lesvgpu_svsig_batch(ctx.h, query_pac.ctypes.data, offs.ctypes.data, subject_seq_offset, subject_size,
+                                     arr, n, min_indel, None if trf is None else trf.ctypes.data,
+                                     per, C.byref(sigs), C.byref(n_sigs))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_svsig_batch failed ({rc}): {ctx.error()}")
+    return per, [sigs[i].astuple() for i in range(n_sigs.value)]

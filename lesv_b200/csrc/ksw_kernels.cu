@@ -23,20 +23,32 @@ namespace lesvksw {
 // ---------------------------------------------------------------------------------------------
 // packing: byte codes -> 2-bit words
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pac_base(const uint8_t* __restrict__ pac, uint64_t l)
+{
+    return (pac[l >> 2] >> ((~l & 3) << 1)) & 3u;             // _get_pac, hbn_aux.h:126
+}
+
+// One CTA per alignment.  Writes the packed target (column c of block B at bits 2c of word B) and
+// the packed REVERSED query behind one zero pad word.  For .pac sources this is also where the read
+// range is reverse-complemented (RawReadReader_ExtractSubRead, raw_reads_reader.c:83-124): the
+// reversed query of a REV read is simply the complement of the forward range.
 __global__ void pack_kernel(const KswJob* __restrict__ jobs, const uint8_t* __restrict__ raw,
-                            uint32_t* __restrict__ pool)
+                            const uint8_t* __restrict__ subject_pac, uint32_t* __restrict__ pool)
 {
     const KswJob job = jobs[blockIdx.x];
-    const uint8_t* t = raw + job.seq_off_t;
-    const uint8_t* q = raw + job.seq_off_q;
     const int ntw = (int)tp_words(job.tlen), nqw = (int)qrp_words(job.qlen);
+    const bool pac = job.src == 1;
     for (int wi = threadIdx.x; wi < ntw; wi += blockDim.x) {
         uint32_t w = 0;
         const int base = wi * 16;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int idx = base + k;
-            if (idx < job.tlen) w |= (uint32_t)(t[idx] & 3) << (2 * k);
+            if (idx < job.tlen) {
+                const uint32_t c = pac ? pac_base(subject_pac, job.seq_off_t + (uint64_t)idx)
+                                       : (uint32_t)(raw[job.seq_off_t + idx] & 3);
+                w |= c << (2 * k);
+            }
         }
         pool[job.tp_off + wi] = w;
     }
@@ -47,16 +59,23 @@ __global__ void pack_kernel(const KswJob* __restrict__ jobs, const uint8_t* __re
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int idx = base + k;               // index into the reversed query
-                if (idx < job.qlen) w |= (uint32_t)(q[job.qlen - 1 - idx] & 3) << (2 * k);
+                if (idx < job.qlen) {
+                    uint32_t c;
+                    if (!pac) c = (uint32_t)(raw[job.seq_off_q + (job.qlen - 1 - idx)] & 3);
+                    else if (job.qdir) c = 3u - pac_base(raw, job.seq_off_q + (uint64_t)idx);
+                    else c = pac_base(raw, job.seq_off_q + (uint64_t)(job.qlen - 1 - idx));
+                    w |= c << (2 * k);
+                }
             }
         }
         pool[job.qrp_off + wi] = w;
     }
 }
 
-void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, uint32_t* d_pool, cudaStream_t s)
+void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const uint8_t* d_subject_pac,
+                 uint32_t* d_pool, cudaStream_t s)
 {
-    if (njobs > 0) pack_kernel<<<njobs, 256, 0, s>>>(d_jobs, d_raw, d_pool);
+    if (njobs > 0) pack_kernel<<<njobs, 256, 0, s>>>(d_jobs, d_raw, d_subject_pac, d_pool);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -70,22 +89,99 @@ struct BtShared {
 };
 
 __device__ __forceinline__ void bt_emit(uint32_t op, uint32_t len, uint32_t& cur_op, uint32_t& cur_len,
-                                        uint32_t* cigar, int& n, int lane)
+                                        uint32_t* cigar, int& n, bool write)
 {
     if (op == cur_op) { cur_len += len; return; }
-    if (cur_len && lane == 0) cigar[n] = cur_len << 4 | cur_op;
+    if (cur_len && write) cigar[n] = cur_len << 4 | cur_op;
     if (cur_len) ++n;
     cur_op = op; cur_len = len;
 }
 
-// All 32 lanes run the same walk out of the shared-memory row cache; lane 0 writes the CIGAR.
+// Alignment scan folded into the traceback walk.  The walk visits the alignment columns from the
+// LAST to the first, so the three forward scans of the reference are restated right-to-left:
+//   truncate_align_bad_ends (hbn_traceback.c:547-606): the kept range ends with the right-most
+//     window of 8 identical columns and starts with the left-most one; walking leftwards, the first
+//     time the run of identical columns reaches 8 fixes the right end, and every later column at
+//     which the run is >= 8 is a new candidate for the left end (the last candidate wins);
+//   calc_effective_ident_perc (hbn_traceback_aux.c:22-95): counters restart at the right end and are
+//     snapshotted at every left-end candidate; gap runs >= 20 columns do not count;
+//   find_sv_signature (find_sv_signature.c:126-220): gap runs >= min_indel are recorded when the run
+//     closes; records right of the right end are dropped, the snapshot bounds them on the left.
+struct ScanState {
+    int m;                 // identical columns in a row, ending at the current column
+    int gap_op, gap_len;   // open gap run (0 = none; 1 = I, 2 = D) and its length
+    int gap_i, gap_j;      // cell of its right-most column
+    int have_right, right_fail;
+    int qe, se;
+    int eff_mat, eff_len, mat, len, n_runs;
+    // snapshot at the current left-end candidate
+    int s_valid, s_at_end, qb, sb, s_eff_mat, s_eff_len, s_mat, s_len, s_runs;
+};
+
+__device__ __forceinline__ void scan_close_gap(ScanState& z, int min_indel, KswGapRun* runs, bool write)
+{
+    if (!z.gap_op) return;
+    const int n = z.gap_len;
+    if (z.have_right) {
+        z.len += n;
+        if (n < 20) z.eff_len += n;
+        if (min_indel > 0 && n >= min_indel) {
+            if (write && z.n_runs < kSigCap) {
+                KswGapRun g;
+                if (z.gap_op == 2) {            // deletion: target columns gap_i-n+1 .. gap_i, read stays at gap_j+1
+                    g.type = 0; g.qfrom = z.gap_j + 1; g.qto = z.gap_j + 2;
+                    g.sfrom = z.gap_i - n + 1; g.sto = z.gap_i + 1;
+                } else {                        // insertion: read bases gap_j-n+1 .. gap_j, target stays at gap_i+1
+                    g.type = 6; g.qfrom = z.gap_j - n + 1; g.qto = z.gap_j + 1;
+                    g.sfrom = z.gap_i + 1; g.sto = z.gap_i + 2;
+                }
+                runs[z.n_runs] = g;
+            }
+            ++z.n_runs;
+        }
+    }
+    z.gap_op = 0; z.gap_len = 0;
+}
+
+__device__ __forceinline__ void scan_column(ScanState& z, uint32_t op, bool ident, int i, int j, int qlen, int tlen,
+                                            int min_indel, KswGapRun* runs, bool write)
+{
+    if (op == 0) {
+        scan_close_gap(z, min_indel, runs, write);
+        z.m = ident ? z.m + 1 : 0;
+        z.eff_len += 1; z.eff_mat += ident; z.len += 1; z.mat += ident;
+        if (z.m >= 8) {
+            if (!z.have_right) {
+                z.have_right = 1; z.qe = j + 8; z.se = i + 8;
+                z.right_fail = (i == 0 && j == 0);
+                z.eff_len = z.eff_mat = z.len = z.mat = 8; z.n_runs = 0;
+            }
+            z.s_valid = 1; z.qb = j; z.sb = i;
+            z.s_at_end = (i + 8 == tlen && j + 8 == qlen);
+            z.s_eff_mat = z.eff_mat; z.s_eff_len = z.eff_len; z.s_mat = z.mat; z.s_len = z.len; z.s_runs = z.n_runs;
+        }
+    } else {
+        z.m = 0;
+        if ((int)op != z.gap_op) {
+            scan_close_gap(z, min_indel, runs, write);
+            z.gap_op = (int)op; z.gap_len = 0; z.gap_i = i; z.gap_j = j;
+        }
+        ++z.gap_len;
+    }
+}
+
+// All 32 lanes run the same walk out of the shared-memory row cache; lane 0 writes results.
 __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ arena, size_t prow,
                                const uint32_t* tp_s, const uint32_t* qrp_s,
-                               uint32_t* __restrict__ cigar, KswOut* out, BtShared& sh, int lane)
+                               uint32_t* __restrict__ cigar, KswGapRun* __restrict__ runs, KswOut* out,
+                               BtShared& sh, int lane)
 {
-    const int qlen = job.qlen, tlen = job.tlen, w = job.w;
+    const int qlen = job.qlen, tlen = job.tlen, w = job.w, min_indel = job.min_indel;
+    const bool wr_cigar = job.cigar_cap != 0 && lane == 0, wr_runs = lane == 0;
     int i = tlen - 1, j = qlen - 1, state = 0, n = 0, n_match = 0;
     uint32_t cur_op = 0xFFFFFFFFu, cur_len = 0, aln = 0;
+    ScanState z;
+    memset(&z, 0, sizeof z);
     while (i >= 0 && j >= 0) {
         const int r0 = i + j;
         // ---- refill: rows r0 .. r0-63, two 16-byte blocks around the predicted column -------
@@ -127,28 +223,41 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
             }
             state = tb_next_state(state, byte, force);
             const uint32_t op = state == 0 ? 0u : (state == 1 || state == 3) ? 2u : 1u;
-            bt_emit(op, 1, cur_op, cur_len, cigar, n, lane);
+            bt_emit(op, 1, cur_op, cur_len, cigar, n, wr_cigar);
             ++aln;
-            if (op == 0) {                       // calc_ident_perc numerator (hbn_traceback_aux.c:4-19)
+            bool ident = false;
+            if (op == 0) {                       // identical column? (calc_ident_perc, hbn_traceback_aux.c:4-19)
                 const int qi = qlen - 1 - j;     // index into the reversed query
                 const uint32_t tb = (tp_s[i >> 4] >> (2 * (i & 15))) & 3u;
                 const uint32_t qb = (qrp_s[1 + (qi >> 4)] >> (2 * (qi & 15))) & 3u;
-                n_match += tb == qb;
-                --i; --j;
-            } else if (op == 2) --i; else --j;
+                ident = tb == qb;
+                n_match += ident;
+            }
+            scan_column(z, op, ident, i, j, qlen, tlen, min_indel, runs, wr_runs);
+            if (op == 0) { --i; --j; } else if (op == 2) --i; else --j;
         }
         __syncwarp();
     }
-    if (i >= 0) { bt_emit(2, (uint32_t)(i + 1), cur_op, cur_len, cigar, n, lane); aln += i + 1; }
-    if (j >= 0) { bt_emit(1, (uint32_t)(j + 1), cur_op, cur_len, cigar, n, lane); aln += j + 1; }
-    bt_emit(0xFFFFFFFEu, 0, cur_op, cur_len, cigar, n, lane);          // flush
+    // leading gap (ksw2.h:146-147); it lies left of any 8-column window, so the scan ignores it
+    if (i >= 0) { bt_emit(2, (uint32_t)(i + 1), cur_op, cur_len, cigar, n, wr_cigar); aln += i + 1; }
+    if (j >= 0) { bt_emit(1, (uint32_t)(j + 1), cur_op, cur_len, cigar, n, wr_cigar); aln += j + 1; }
+    bt_emit(0xFFFFFFFEu, 0, cur_op, cur_len, cigar, n, wr_cigar);      // flush
     __syncwarp();
     // the walk produced last-op-first; the reference returns first-op-first (ksw2.h:148-150)
-    for (int a = lane; a < n / 2; a += 32) {
-        const uint32_t x = cigar[a], y = cigar[n - 1 - a];
-        cigar[a] = y; cigar[n - 1 - a] = x;
+    if (job.cigar_cap)
+        for (int a = lane; a < n / 2; a += 32) {
+            const uint32_t x = cigar[a], y = cigar[n - 1 - a];
+            cigar[a] = y; cigar[n - 1 - a] = x;
+        }
+    if (lane == 0) {
+        KswOut o;
+        o.n_cigar = n; o.aln_size = (int)aln; o.n_match = n_match; o.status = 1;
+        o.trunc_ok = z.have_right && !z.right_fail && z.s_valid && !z.s_at_end;
+        o.qb = z.qb; o.qe = z.qe; o.sb = z.sb; o.se = z.se;
+        o.eff_mat = z.s_eff_mat; o.eff_len = z.s_eff_len; o.trim_mat = z.s_mat; o.trim_len = z.s_len;
+        o.n_runs = z.s_runs;
+        *out = o;
     }
-    if (lane == 0) { out->n_cigar = n; out->aln_size = (int)aln; out->n_match = n_match; out->status = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -158,7 +267,8 @@ template <int NT>
 __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 512 / NT))
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
-              uint32_t* __restrict__ cigar_pool, KswOut* __restrict__ outs, int* counter)
+              uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
+              KswOut* __restrict__ outs, int* counter)
 {
     constexpr int NW = NT / 32;
     extern __shared__ uint32_t seq_s[];
@@ -209,9 +319,123 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             __syncthreads();
         }
         if (warp == 0)
-            backtrack_warp(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off, outs + jid, bt, lane);
+            backtrack_warp(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off,
+                           run_pool + job.sig_off, outs + jid, bt, lane);
         __syncthreads();
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// wide bands (window > 512 blocks: full-band retries, chained dual HSPs)
+// ---------------------------------------------------------------------------------------------
+// Same per-block code, but a thread steps through several band slots per anti-diagonal and the
+// slot contexts live in global memory (L2-resident, structure of arrays so that a warp's loads
+// coalesce).  ~10 % extra traffic on a path that is rare by construction.
+constexpr int kWideNT = 512;
+constexpr int kCtxWords = sizeof(ThreadCtx) / 4;
+static_assert(sizeof(ThreadCtx) % 4 == 0, "ThreadCtx is an array of 32-bit words");
+
+__device__ __forceinline__ void ctx_load(ThreadCtx& c, const uint32_t* base, int nslot, int s)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(&c);
+#pragma unroll
+    for (int k = 0; k < kCtxWords; ++k) w[k] = base[(size_t)k * nslot + s];
+}
+__device__ __forceinline__ void ctx_store(const ThreadCtx& c, uint32_t* base, int nslot, int s)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&c);
+#pragma unroll
+    for (int k = 0; k < kCtxWords; ++k) base[(size_t)k * nslot + s] = w[k];
+}
+
+__global__ void __launch_bounds__(kWideNT, 1)
+ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
+                   const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
+                   uint32_t* __restrict__ scratch_base, size_t scratch_stride_words, int max_slots,
+                   uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
+                   KswOut* __restrict__ outs, int* counter)
+{
+    extern __shared__ uint32_t seq_s[];
+    __shared__ int s_job;
+    __shared__ BtShared bt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* const arena = arena_base + (size_t)blockIdx.x * arena_stride;
+    uint32_t* const scratch = scratch_base + (size_t)blockIdx.x * scratch_stride_words;
+
+    for (;;) {
+        if (tid == 0) s_job = atomicAdd(counter, 1);
+        __syncthreads();
+        const int ji = s_job;
+        if (ji >= njobs) break;
+        const int jid = order[ji];
+        const KswJob job = jobs[jid];
+        const int qlen = job.qlen, tlen = job.tlen, w = job.w;
+        const int ntw = (int)tp_words(tlen), nqw = (int)qrp_words(qlen);
+        uint32_t* tp_s = seq_s;
+        uint32_t* qrp_s = seq_s + ntw;
+        for (int x = tid; x < ntw; x += kWideNT) tp_s[x] = pool[job.tp_off + x];
+        for (int x = tid; x < nqw; x += kWideNT) qrp_s[x] = pool[job.qrp_off + x];
+        int nslot = window_blocks(tlen, w);
+        nslot = (nslot + kWideNT - 1) / kWideNT * kWideNT;        // <= max_slots by construction
+        uint32_t* ctxs = scratch;                                  // [kCtxWords][nslot]
+        uint2* pub = reinterpret_cast<uint2*>(scratch + (size_t)kCtxWords * max_slots);   // [2][nslot]
+        {
+            ThreadCtx c;
+            c.myB = -1; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
+            c.b.init();
+            for (int sidx = tid; sidx < nslot; sidx += kWideNT) ctx_store(c, ctxs, nslot, sidx);
+        }
+        __syncthreads();
+        const int nrow = qlen + tlen - 1;
+        const size_t prow = (size_t)job.tb_blocks * 16;
+        for (int r = 0; r < nrow; ++r) {
+            const RowGeom g = row_geom(r, qlen, tlen, w);
+            const int bst = g.st0 >> 4, bwr = g.wr >> 4;
+            uint2* pub_r = pub + (size_t)(r & 1) * nslot;
+            const uint2* pub_p = pub + (size_t)((r + 1) & 1) * nslot;
+            // visit only slots whose block can be live this row: blocks bst..bwr
+            for (int B = bst + tid; B <= bwr; B += kWideNT) {
+                const int sidx = B % nslot;
+                ThreadCtx c;
+                ctx_load(c, ctxs, nslot, sidx);
+                const uint2 pv = pub_p[(sidx + nslot - 1) % nslot];
+                Carry cin; cin.xv = pv.x; cin.x2 = pv.y;
+                Carry cout;
+                uint32_t tb[4];
+                int tbb = 0;
+                if (thread_row_step(c, sidx, nslot, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
+                    *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)tbb * 16) =
+                        make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                    pub_r[sidx] = make_uint2(cout.xv, cout.x2);
+                }
+                ctx_store(c, ctxs, nslot, sidx);
+            }
+            __syncthreads();
+        }
+        if (warp == 0)
+            backtrack_warp(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off,
+                           run_pool + job.sig_off, outs + jid, bt, lane);
+        __syncthreads();
+    }
+}
+
+size_t ksw_wide_scratch_words(int max_slots) { return (size_t)kCtxWords * max_slots + 4 * (size_t)max_slots; }
+int ksw_wide_slots(int tlen, int w)
+{
+    const int n = window_blocks(tlen, w);
+    return (n + kWideNT - 1) / kWideNT * kWideNT;
+}
+
+void launch_ksw_wide(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
+                     const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_scratch,
+                     size_t scratch_stride_words, int max_slots, uint32_t* d_cigar, KswGapRun* d_runs,
+                     KswOut* d_out, int* d_counter, cudaStream_t s)
+{
+    cudaFuncSetAttribute(ksw_dp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ksw_dp_wide_kernel<<<n_ctas, kWideNT, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                                     d_scratch, scratch_stride_words, max_slots, d_cigar,
+                                                     d_runs, d_out, d_counter);
 }
 
 size_t ksw_smem_bytes(int max_qlen, int max_tlen)
@@ -224,22 +448,22 @@ int ksw_ctas_per_sm(int nt) { return nt >= 512 ? 1 : 512 / nt; }
 template <int NT>
 static void launch_t(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
                      const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                     KswOut* d_out, int* d_counter, cudaStream_t s)
+                     KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
     cudaFuncSetAttribute(ksw_dp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ksw_dp_kernel<NT><<<n_ctas, NT, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                               d_cigar, d_out, d_counter);
+                                               d_cigar, d_runs, d_out, d_counter);
 }
 
 void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
                 const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                KswOut* d_out, int* d_counter, cudaStream_t s)
+                KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
     switch (nt) {
-        case 64:  launch_t<64>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_out, d_counter, s); break;
-        case 128: launch_t<128>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_out, d_counter, s); break;
-        case 256: launch_t<256>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_out, d_counter, s); break;
-        default:  launch_t<512>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_out, d_counter, s); break;
+        case 64:  launch_t<64>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
+        case 128: launch_t<128>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
+        case 256: launch_t<256>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
+        default:  launch_t<512>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
     }
 }
 

@@ -11,11 +11,29 @@ struct KswJob {
     int tb_blocks;            // 16-byte blocks per traceback row (n_col_, ksw2_extd2_sse.c:85-86)
     uint32_t tp_off;          // word offset of the packed target (16 bases per word) in the pool
     uint32_t qrp_off;         // word offset of the packed REVERSED query (first word is a zero pad)
-    uint64_t seq_off_q;       // byte offset of the query codes in the raw upload buffer
-    uint64_t seq_off_t;       // byte offset of the target codes
+    // where the residues come from (pack kernel):
+    //   src = 0: one code (0..3) per byte; seq_off_q / seq_off_t are byte offsets into the raw upload
+    //   src = 1: lesv .pac (2 bits per base, base l at byte l>>2, bits (~l&3)<<1, hbn_aux.h:125-126);
+    //            seq_off_q = residue index of forward-read base qoff inside the raw upload,
+    //            seq_off_t = residue index of the first target base inside the resident subject .pac
+    uint64_t seq_off_q;
+    uint64_t seq_off_t;
+    int32_t src;
+    int32_t qdir;             // src = 1: 1 = align the reverse complement of the read range (REV)
     uint64_t cigar_off;       // u32 offset of this job's CIGAR slot in the cigar pool
-    uint32_t cigar_cap;       // capacity of that slot (qlen + tlen + 2)
+    uint32_t cigar_cap;       // capacity of that slot (qlen + tlen + 2); 0 = do not write a CIGAR
+    int32_t min_indel;        // > 0: scan the alignment for gap runs >= min_indel (qx2svsig)
+    uint32_t sig_off;         // first KswGapRun slot of this job (kSigCap slots)
     uint32_t pad_;
+};
+
+constexpr int kSigCap = 64;   // gap-run records kept per alignment
+
+// A gap run found by the alignment scan (find_sv_signature, find_sv_signature.c:126-220), in
+// coordinates of the aligned sub-sequences: DEL = gap in the read, INS = gap in the reference.
+struct KswGapRun {
+    int type;                 // 0 = DEL, 6 = INS (eGapAlignDel / eGapAlignIns, gapinfo.h:47-53)
+    int qfrom, qto, sfrom, sto;
 };
 
 // per job results written by the kernels
@@ -23,7 +41,13 @@ struct KswOut {
     int n_cigar;              // CIGAR entries (reference order: first op first), 0 = failure
     int aln_size;             // alignment columns
     int n_match;              // identical columns (calc_ident_perc numerator)
-    int status;               // 0 ok, else LESVGPU_E_*
+    int status;               // 1 = alignment done
+    // alignment scan (truncate_align_bad_ends, calc_effective_ident_perc, find_sv_signature)
+    int trunc_ok;             // truncate_align_bad_ends' return value
+    int qb, qe, sb, se;       // trimmed sub-sequence coordinates
+    int eff_mat, eff_len;     // calc_effective_ident_perc = 100.0 * eff_mat / eff_len
+    int trim_mat, trim_len;   // calc_ident_perc over the trimmed alignment
+    int n_runs;               // gap runs >= min_indel inside the trimmed alignment (may exceed kSigCap)
 };
 
 // words of packed sequence pool one job needs
@@ -31,20 +55,29 @@ __host__ __device__ static inline uint32_t tp_words(int tlen) { return (uint32_t
 __host__ __device__ static inline uint32_t qrp_words(int qlen) { return (uint32_t)(qlen >> 4) + 7; }
 
 // largest band window (in 16-column blocks) the register-resident kernel with NT threads holds
-static inline int window_blocks(int tlen, int w)
+__host__ __device__ static inline int window_blocks(int tlen, int w)
 {
     int cols = w + 1 < tlen ? w + 1 : tlen;
     return (cols + 15) / 16 + 3;
 }
 
-void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, uint32_t* d_pool, cudaStream_t s);
+void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const uint8_t* d_subject_pac,
+                 uint32_t* d_pool, cudaStream_t s);
 
 // Persistent DP + backtrack kernel; `nt` in {64,128,256,512}. job_order[0..njobs) lists the jobs
 // of this launch (indices into d_jobs); d_counter must be zero on entry.
 // smem = ksw_smem_bytes(longest query, longest target among these jobs).
 void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_job_order, int njobs,
                 const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                KswOut* d_out, int* d_counter, cudaStream_t s);
+                KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
+
+// Bands wider than 512 blocks: slot contexts in global scratch (ksw_wide_scratch_words per CTA).
+void launch_ksw_wide(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
+                     const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_scratch,
+                     size_t scratch_stride_words, int max_slots, uint32_t* d_cigar, KswGapRun* d_runs,
+                     KswOut* d_out, int* d_counter, cudaStream_t s);
+size_t ksw_wide_scratch_words(int max_slots);
+int ksw_wide_slots(int tlen, int w);
 
 int ksw_ctas_per_sm(int nt);
 size_t ksw_smem_bytes(int max_qlen, int max_tlen);

@@ -62,14 +62,18 @@ struct lesvgpu_ctx {
     cudaEvent_t ev[8] = {};
     std::string err;
     lesvgpu_timing timing = {};
-    DevBuf<uint8_t> d_raw, d_arena;
-    DevBuf<uint32_t> d_pool, d_cigar;
+    DevBuf<uint8_t> d_raw, d_arena, d_subject;
+    size_t subject_bytes = 0;
+    DevBuf<uint32_t> d_pool, d_cigar, d_scratch;
     DevBuf<KswJob> d_jobs;
     DevBuf<KswOut> d_outs;
+    DevBuf<KswGapRun> d_runs;
     DevBuf<int> d_order, d_counter;
     PinBuf<uint8_t> h_raw;
     PinBuf<uint32_t> h_cigar;
     PinBuf<KswOut> h_outs;
+    PinBuf<KswGapRun> h_runs;
+    std::vector<lesvgpu_svsig> sigs;
 };
 
 #define CK(call)                                                                              \
@@ -117,9 +121,10 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_raw.release(); ctx->d_arena.release(); ctx->d_pool.release(); ctx->d_cigar.release();
-    ctx->d_jobs.release(); ctx->d_outs.release(); ctx->d_order.release(); ctx->d_counter.release();
-    ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release();
+    ctx->d_raw.release(); ctx->d_arena.release(); ctx->d_subject.release(); ctx->d_pool.release();
+    ctx->d_cigar.release(); ctx->d_scratch.release(); ctx->d_jobs.release(); ctx->d_outs.release();
+    ctx->d_runs.release(); ctx->d_order.release(); ctx->d_counter.release();
+    ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -160,86 +165,56 @@ extern "C" int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* 
     return cells;
 }
 
-extern "C" int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs, int n,
-                                 lesvgpu_ksw_result* results, const uint32_t** cigar_pool)
+// ---------------------------------------------------------------------------------------------
+// shared runner: jobs[] have qlen/tlen/w/src/seq offsets/min_indel filled in and cigar_cap set to
+// 0 or 1 (1 = wants a CIGAR); pool/cigar/run offsets are assigned here.
+// ---------------------------------------------------------------------------------------------
+static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_bytes, bool want_cigar, bool want_runs)
 {
-    if (!ctx || n < 0 || (n && (!pairs || !results))) return LESVGPU_E_ARG;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
-    ctx->timing = lesvgpu_timing{};
-    if (cigar_pool) *cigar_pool = nullptr;
-    if (n == 0) return LESVGPU_OK;
-
-    // ---- plan ---------------------------------------------------------------------------------
     static const int kClasses[4] = {64, 128, 256, 512};
-    std::vector<KswJob> jobs;
-    std::vector<int> job_pair;                      // job -> pair index
-    std::vector<std::vector<int>> cls(4);
-    std::vector<size_t> tb_bytes;
-    jobs.reserve(n); job_pair.reserve(n); tb_bytes.reserve(n);
-    size_t raw_bytes = 0, pool_words = 0, cigar_words = 0;
-    for (int i = 0; i < n; ++i) {
-        lesvgpu_ksw_result& R = results[i];
-        R.ok = 0; R.n_cigar = 0; R.cigar_off = 0; R.aln_size = 0; R.n_match = 0;
-        const lesvgpu_ksw_pair& P = pairs[i];
-        if (P.qlen <= 0 || P.tlen <= 0) continue;              // ksw2_extd2_sse.c:68 -> n_cigar 0
-        if (!P.query || !P.target) { ctx->err = "null sequence pointer"; return LESVGPU_E_ARG; }
-        const int w = effective_band(P.qlen, P.tlen, P.max_distance);
-        if (!band_reaches_end(P.qlen, P.tlen, w)) continue;    // partial CIGAR -> wrapper returns 0
-        const int wb = window_blocks(P.tlen, w);
+    const int nj = (int)jobs.size();
+    std::vector<std::vector<int>> cls(5);            // 4 register-resident classes + wide
+    std::vector<size_t> tb_bytes(nj);
+    size_t pool_words = 0, cigar_words = 0;
+    for (int k = 0; k < nj; ++k) {
+        KswJob& J = jobs[k];
+        const int wb = window_blocks(J.tlen, J.w);
         int c = 0;
         while (c < 4 && kClasses[c] < wb) ++c;
-        if (c == 4) {
-            char b[160];
-            snprintf(b, sizeof b, "pair %d: band of %d columns needs %d blocks (> 512): wide kernel not built yet", i, w, wb);
-            ctx->err = b;
-            return LESVGPU_E_NOMEM;
-        }
-        KswJob J;
-        memset(&J, 0, sizeof J);
-        J.qlen = P.qlen; J.tlen = P.tlen; J.w = w;
-        J.tb_blocks = tb_row_blocks(P.qlen, P.tlen, w);
-        J.seq_off_q = raw_bytes; raw_bytes += (size_t)P.qlen;
-        J.seq_off_t = raw_bytes; raw_bytes += (size_t)P.tlen;
-        J.tp_off = (uint32_t)pool_words; pool_words += tp_words(P.tlen);
-        J.qrp_off = (uint32_t)pool_words; pool_words += qrp_words(P.qlen);
-        J.cigar_off = cigar_words; J.cigar_cap = (uint32_t)(P.qlen + P.tlen + 2);
+        J.tb_blocks = tb_row_blocks(J.qlen, J.tlen, J.w);
+        J.tp_off = (uint32_t)pool_words; pool_words += tp_words(J.tlen);
+        J.qrp_off = (uint32_t)pool_words; pool_words += qrp_words(J.qlen);
+        J.cigar_off = cigar_words;
+        J.cigar_cap = want_cigar ? (uint32_t)(J.qlen + J.tlen + 2) : 0u;
         cigar_words += J.cigar_cap;
+        J.sig_off = (uint32_t)k * kSigCap;
         if (pool_words > 0xFFFFFFF0ull) { ctx->err = "batch too large (packed pool offsets are 32-bit)"; return LESVGPU_E_ARG; }
-        const size_t tb = (size_t)(P.qlen + P.tlen - 1) * (size_t)J.tb_blocks * 16;
-        if (tb > ctx->arena_limit) {
-            ctx->err = "one alignment's traceback does not fit the arena";
-            return LESVGPU_E_NOMEM;
-        }
-        cls[c].push_back((int)jobs.size());
-        jobs.push_back(J); job_pair.push_back(i); tb_bytes.push_back(tb);
-    }
-    const int nj = (int)jobs.size();
-    if (nj == 0) return LESVGPU_OK;
-
-    // ---- upload -------------------------------------------------------------------------------
-    CK(ctx->h_raw.reserve(raw_bytes));
-    for (int k = 0; k < nj; ++k) {
-        const lesvgpu_ksw_pair& P = pairs[job_pair[k]];
-        memcpy(ctx->h_raw.p + jobs[k].seq_off_q, P.query, (size_t)P.qlen);
-        memcpy(ctx->h_raw.p + jobs[k].seq_off_t, P.target, (size_t)P.tlen);
+        tb_bytes[k] = (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
+        if (tb_bytes[k] > ctx->arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
+        cls[c].push_back(k);
     }
     std::vector<int> order;
     order.reserve(nj);
-    struct Launch { int nt, first, count, n_ctas; size_t stride, smem; };
+    struct Launch { int nt, first, count, n_ctas, max_slots; size_t stride, smem; };
     std::vector<Launch> launches;
-    size_t arena_need = 0;
-    for (int c = 0; c < 4; ++c) {
+    size_t arena_need = 0, scratch_need = 0;
+    for (int c = 0; c < 5; ++c) {
         if (cls[c].empty()) continue;
         std::sort(cls[c].begin(), cls[c].end(), [&](int a, int b) {
             return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
         });
         Launch L;
-        L.nt = kClasses[c]; L.first = (int)order.size(); L.count = (int)cls[c].size();
+        L.nt = c < 4 ? kClasses[c] : 0; L.first = (int)order.size(); L.count = (int)cls[c].size();
+        L.max_slots = 0;
         L.stride = (tb_bytes[cls[c][0]] + 255) & ~(size_t)255;
         int mq = 0, mt = 0;
-        for (int k : cls[c]) { mq = std::max(mq, jobs[k].qlen); mt = std::max(mt, jobs[k].tlen); order.push_back(k); }
+        for (int k : cls[c]) {
+            mq = std::max(mq, jobs[k].qlen); mt = std::max(mt, jobs[k].tlen); order.push_back(k);
+            if (c == 4) L.max_slots = std::max(L.max_slots, ksw_wide_slots(jobs[k].tlen, jobs[k].w));
+        }
         L.smem = ksw_smem_bytes(mq, mt);
-        int per_sm = ksw_ctas_per_sm(L.nt);
+        if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
+        int per_sm = c < 4 ? ksw_ctas_per_sm(L.nt) : 1;
         const size_t smem_cap = 200 * 1024;
         while (per_sm > 1 && (L.smem + 4096) * per_sm > smem_cap) --per_sm;
         int ctas = std::min(L.count, ctx->n_sm * per_sm);
@@ -248,18 +223,22 @@ extern "C" int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs
         if (ctas < 1) { ctx->err = "arena too small"; return LESVGPU_E_NOMEM; }
         L.n_ctas = ctas;
         arena_need = std::max(arena_need, L.stride * (size_t)ctas);
+        if (c == 4) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)ctas);
         launches.push_back(L);
     }
-    CK(ctx->d_raw.reserve(raw_bytes));
+    CK(ctx->d_raw.reserve(raw_bytes + 16));
     CK(ctx->d_pool.reserve(pool_words));
-    CK(ctx->d_cigar.reserve(cigar_words));
+    CK(ctx->d_cigar.reserve(cigar_words + 1));
     CK(ctx->d_jobs.reserve(nj));
     CK(ctx->d_outs.reserve(nj));
+    CK(ctx->d_runs.reserve((size_t)nj * kSigCap));
     CK(ctx->d_order.reserve(nj));
     CK(ctx->d_counter.reserve(launches.size()));
     CK(ctx->d_arena.reserve(arena_need));
+    CK(ctx->d_scratch.reserve(scratch_need));
     CK(ctx->h_outs.reserve(nj));
-    CK(ctx->h_cigar.reserve(cigar_words));
+    if (want_cigar) CK(ctx->h_cigar.reserve(cigar_words));
+    if (want_runs) CK(ctx->h_runs.reserve((size_t)nj * kSigCap));
 
     cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -269,37 +248,193 @@ extern "C" int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int) * launches.size(), s));
     CK(cudaMemsetAsync(ctx->d_outs.p, 0, sizeof(KswOut) * nj, s));
     CK(cudaEventRecord(ctx->ev[1], s));
-    launch_pack(ctx->d_jobs.p, nj, ctx->d_raw.p, ctx->d_pool.p, s);
+    launch_pack(ctx->d_jobs.p, nj, ctx->d_raw.p, ctx->d_subject.p, ctx->d_pool.p, s);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], s));
     for (size_t li = 0; li < launches.size(); ++li) {
         const Launch& L = launches[li];
-        launch_ksw(L.nt, L.n_ctas, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
-                   ctx->d_arena.p, L.stride, ctx->d_cigar.p, ctx->d_outs.p, ctx->d_counter.p + li, s);
+        if (L.nt)
+            launch_ksw(L.nt, L.n_ctas, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
+                       ctx->d_arena.p, L.stride, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p,
+                       ctx->d_counter.p + li, s);
+        else
+            launch_ksw_wide(L.n_ctas, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
+                            ctx->d_arena.p, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
+                            L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, s);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[3], s));
+    size_t d2h = sizeof(KswOut) * nj;
     CK(cudaMemcpyAsync(ctx->h_outs.p, ctx->d_outs.p, sizeof(KswOut) * nj, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->d_cigar.p, sizeof(uint32_t) * cigar_words, cudaMemcpyDeviceToHost, s));
+    if (want_cigar && cigar_words) {
+        CK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->d_cigar.p, sizeof(uint32_t) * cigar_words, cudaMemcpyDeviceToHost, s));
+        d2h += sizeof(uint32_t) * cigar_words;
+    }
+    if (want_runs) {
+        CK(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs.p, sizeof(KswGapRun) * (size_t)nj * kSigCap, cudaMemcpyDeviceToHost, s));
+        d2h += sizeof(KswGapRun) * (size_t)nj * kSigCap;
+    }
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaStreamSynchronize(s));
 
-    for (int k = 0; k < nj; ++k) {
-        lesvgpu_ksw_result& R = results[job_pair[k]];
-        const KswOut& O = ctx->h_outs.p[k];
-        R.n_cigar = O.n_cigar; R.cigar_off = jobs[k].cigar_off;
-        R.aln_size = O.aln_size; R.n_match = O.n_match;
-        R.ok = O.n_cigar > 0 && O.status == 0;
-    }
-    if (cigar_pool) *cigar_pool = ctx->h_cigar.p;
     lesvgpu_timing& T = ctx->timing;
     cudaEventElapsedTime(&T.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&T.pack_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&T.dp_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&T.d2h_ms, ctx->ev[3], ctx->ev[4]);
+    T.scan_ms = 0.f;                                  // the scan runs inside the traceback walk
     T.dp_launches = (int)launches.size();
     T.kernel_launches = 1 + (int)launches.size();
     T.h2d_bytes = raw_bytes + sizeof(KswJob) * nj + sizeof(int) * nj;
-    T.d2h_bytes = sizeof(KswOut) * nj + sizeof(uint32_t) * cigar_words;
+    T.d2h_bytes = d2h;
+    return LESVGPU_OK;
+}
+
+extern "C" int lesvgpu_ksw_batch(lesvgpu_ctx* ctx, const lesvgpu_ksw_pair* pairs, int n,
+                                 lesvgpu_ksw_result* results, const uint32_t** cigar_pool)
+{
+    if (!ctx || n < 0 || (n && (!pairs || !results))) return LESVGPU_E_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
+    ctx->timing = lesvgpu_timing{};
+    if (cigar_pool) *cigar_pool = nullptr;
+    std::vector<KswJob> jobs;
+    std::vector<int> job_pair;
+    jobs.reserve(n); job_pair.reserve(n);
+    size_t raw_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        lesvgpu_ksw_result& R = results[i];
+        R.ok = 0; R.n_cigar = 0; R.cigar_off = 0; R.aln_size = 0; R.n_match = 0;
+        const lesvgpu_ksw_pair& P = pairs[i];
+        if (P.qlen <= 0 || P.tlen <= 0) continue;              // ksw2_extd2_sse.c:68 -> n_cigar 0
+        if (!P.query || !P.target) { ctx->err = "null sequence pointer"; return LESVGPU_E_ARG; }
+        const int w = effective_band(P.qlen, P.tlen, P.max_distance);
+        if (!band_reaches_end(P.qlen, P.tlen, w)) continue;    // partial CIGAR -> the wrapper returns 0
+        KswJob J;
+        memset(&J, 0, sizeof J);
+        J.qlen = P.qlen; J.tlen = P.tlen; J.w = w;
+        J.seq_off_q = raw_bytes; raw_bytes += (size_t)P.qlen;
+        J.seq_off_t = raw_bytes; raw_bytes += (size_t)P.tlen;
+        jobs.push_back(J); job_pair.push_back(i);
+    }
+    const int nj = (int)jobs.size();
+    if (nj == 0) return LESVGPU_OK;
+    CK(ctx->h_raw.reserve(raw_bytes));
+    for (int k = 0; k < nj; ++k) {
+        const lesvgpu_ksw_pair& P = pairs[job_pair[k]];
+        memcpy(ctx->h_raw.p + jobs[k].seq_off_q, P.query, (size_t)P.qlen);
+        memcpy(ctx->h_raw.p + jobs[k].seq_off_t, P.target, (size_t)P.tlen);
+    }
+    const int rc = run_jobs(ctx, jobs, raw_bytes, cigar_pool != nullptr, false);
+    if (rc != LESVGPU_OK) return rc;
+    for (int k = 0; k < nj; ++k) {
+        lesvgpu_ksw_result& R = results[job_pair[k]];
+        const KswOut& O = ctx->h_outs.p[k];
+        R.n_cigar = O.n_cigar; R.cigar_off = jobs[k].cigar_off;
+        R.aln_size = O.aln_size; R.n_match = O.n_match;
+        R.ok = O.n_cigar > 0 && O.status == 1;
+    }
+    if (cigar_pool) *cigar_pool = ctx->h_cigar.p;
+    return LESVGPU_OK;
+}
+
+extern "C" int lesvgpu_subject_load(lesvgpu_ctx* ctx, const uint8_t* subject_pac, size_t pac_bytes)
+{
+    if (!ctx || !subject_pac || !pac_bytes) return LESVGPU_E_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
+    CK(ctx->d_subject.reserve(pac_bytes + 16));
+    CK(cudaMemcpyAsync(ctx->d_subject.p, subject_pac, pac_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->subject_bytes = pac_bytes;
+    return LESVGPU_OK;
+}
+
+extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
+                                   const uint8_t* query_pac, const size_t* query_read_offset,
+                                   size_t subject_seq_offset, int subject_size,
+                                   const lesvgpu_svread* reads, int n, int min_indel_size,
+                                   const char* trf_mask,
+                                   lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs)
+{
+    if (!ctx || n < 0 || (n && (!reads || !per_read || !query_pac || !query_read_offset))) return LESVGPU_E_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
+    if (!ctx->subject_bytes) { ctx->err = "lesvgpu_subject_load has not been called"; return LESVGPU_E_ARG; }
+    ctx->timing = lesvgpu_timing{};
+    ctx->sigs.clear();
+    if (sigs) *sigs = nullptr;
+    if (n_sigs) *n_sigs = 0;
+    std::vector<KswJob> jobs;
+    std::vector<int> job_read;
+    jobs.reserve(n); job_read.reserve(n);
+    // pass 1: size the raw upload (the .pac bytes covering each read range)
+    size_t raw_bytes = 0;
+    std::vector<size_t> src_byte(n), dst_byte(n), nbytes(n);
+    for (int i = 0; i < n; ++i) {
+        lesvgpu_svsig_read& R = per_read[i];
+        memset(&R, 0, sizeof R);
+        const lesvgpu_svread& S = reads[i];
+        const int qn = S.qend - S.qoff, sn = S.send - S.soff;
+        if (qn <= 0 || sn <= 0 || S.qend > S.qsize || S.send > subject_size || S.qoff < 0 || S.soff < 0) {
+            ctx->err = "SvRead range outside its sequence"; return LESVGPU_E_ARG;
+        }
+        if (!query_read_offset[S.query_id]) { ctx->err = "read not loaded (raw_read_offset_array == 0)"; return LESVGPU_E_ARG; }
+        // discover_func :272-316: band (int)(dist*1.2) [0 -> 10 % rule], then max(qlen, slen)
+        int w = effective_band(qn, sn, (int)(S.dist * 1.2));
+        if (!band_reaches_end(qn, sn, w)) w = qn > sn ? qn : sn;
+        R.band = w;
+        const size_t res0 = query_read_offset[S.query_id] - 1 + (size_t)S.qoff;   // forward-strand range
+        src_byte[i] = res0 >> 2;
+        nbytes[i] = ((res0 + (size_t)qn - 1) >> 2) - src_byte[i] + 1;
+        dst_byte[i] = raw_bytes;
+        raw_bytes += nbytes[i];
+        KswJob J;
+        memset(&J, 0, sizeof J);
+        J.qlen = qn; J.tlen = sn; J.w = w;
+        J.src = 1; J.qdir = S.qdir;
+        J.seq_off_q = dst_byte[i] * 4 + (res0 & 3);
+        J.seq_off_t = subject_seq_offset + (size_t)S.soff;
+        if (((J.seq_off_t + (size_t)sn + 3) >> 2) > ctx->subject_bytes) { ctx->err = "subject range outside the loaded .pac"; return LESVGPU_E_ARG; }
+        J.min_indel = min_indel_size;
+        jobs.push_back(J); job_read.push_back(i);
+    }
+    const int nj = (int)jobs.size();
+    if (nj == 0) return LESVGPU_OK;
+    CK(ctx->h_raw.reserve(raw_bytes));
+    for (int i = 0; i < n; ++i) memcpy(ctx->h_raw.p + dst_byte[i], query_pac + src_byte[i], nbytes[i]);
+    const int rc = run_jobs(ctx, jobs, raw_bytes, false, true);
+    if (rc != LESVGPU_OK) return rc;
+    for (int k = 0; k < nj; ++k) {
+        const int i = job_read[k];
+        const lesvgpu_svread& S = reads[i];
+        lesvgpu_svsig_read& R = per_read[i];
+        const KswOut& O = ctx->h_outs.p[k];
+        R.qb = O.qb; R.qe = O.qe; R.sb = O.sb; R.se = O.se;
+        R.eff_mat = O.eff_mat; R.eff_len = O.eff_len;
+        if (O.status != 1 || O.n_cigar <= 0) { R.status = 0; continue; }
+        if (!O.trunc_ok) { R.status = -1; continue; }
+        const int fqb = O.qb + S.qoff, fqe = O.qe + S.qoff;          // :334-337 (forward qoff even for REV)
+        const int fsb = O.sb + S.soff, fse = O.se + S.soff;
+        if (trf_mask) {                                              // fall_in_trf_subseq, trf_array.cpp:74-83
+            size_t cnt = 0;
+            for (size_t x = subject_seq_offset + fsb; x < subject_seq_offset + (size_t)fse; ++x) cnt += trf_mask[x];
+            if ((size_t)(fse - fsb) - cnt <= 2000) { R.status = -2; continue; }
+        }
+        const double eff = O.eff_len == 0 ? 0.0 : 100.0 * O.eff_mat / O.eff_len;   // hbn_traceback_aux.c:93-94
+        if (eff < 70.0) { R.status = -3; continue; }
+        if (O.n_runs > kSigCap) { ctx->err = "more than 64 SV-sized gap runs in one alignment"; return LESVGPU_E_NOMEM; }
+        R.status = 1; R.n_sig = O.n_runs;
+        const KswGapRun* g = ctx->h_runs.p + (size_t)k * kSigCap;
+        for (int x = O.n_runs - 1; x >= 0; --x) {                    // the walk found them right-to-left
+            lesvgpu_svsig v;
+            v.qid = S.query_id; v.qdir = S.qdir;
+            v.qfrom = g[x].qfrom; v.qto = g[x].qto;
+            v.fqfrom = fqb; v.fqto = fqe; v.qsize = S.qsize;
+            v.sfrom = S.soff + g[x].sfrom; v.sto = S.soff + g[x].sto;
+            v.fsfrom = fsb; v.fsto = fse; v.ssize = subject_size;
+            v.type = g[x].type;
+            ctx->sigs.push_back(v);
+        }
+    }
+    if (sigs) *sigs = ctx->sigs.data();
+    if (n_sigs) *n_sigs = (int)ctx->sigs.size();
     return LESVGPU_OK;
 }

@@ -170,3 +170,72 @@ def random_pair(rng, it, max_len=700, small=80):
 
 def cigar_str(c):
     return "".join(f"{x >> 4}{'MID'[x & 15]}" for x in c)
+
+
+# ---- lesv packed database -------------------------------------------------
+class LesvDb:
+    """numpy view of <db_dir>/<title>.{pac,seq_info,hdr,volume_info.bin} (corelib/seqdb.c)."""
+
+    def __init__(self, db_dir, title):
+        base = os.path.join(db_dir, title + ".")
+        vi = np.fromfile(base + "volume_info.bin", dtype=np.uint8)[:64]
+        self.num_seqs = int(np.frombuffer(vi[4:8].tobytes(), dtype=np.int32)[0])
+        f = np.frombuffer(vi[8:64].tobytes(), dtype=np.uint64)
+        self.seq_offset_to = int(f[2])
+        si = np.fromfile(base + "seq_info", dtype=np.uint64).reshape(-1, 6)[:self.num_seqs]
+        self.seq_offset = si[:, 0].astype(np.int64)
+        self.seq_size = si[:, 1].astype(np.int64)
+        self.hdr_offset = si[:, 2].astype(np.int64)
+        self.hdr = open(base + "hdr", "rb").read()
+        self.pac = np.fromfile(base + "pac", dtype=np.uint8)
+        self.read_offset = (self.seq_offset + 1).astype(np.uint64)   # raw_read_offset_array
+
+    def name(self, i):
+        o = int(self.hdr_offset[i])
+        return self.hdr[o:self.hdr.index(b"\0", o)].decode()
+
+    def codes(self, i):
+        """forward residues of sequence i as uint8 codes (_get_pac, hbn_aux.h:126)."""
+        off, n = int(self.seq_offset[i]), int(self.seq_size[i])
+        l = np.arange(off, off + n, dtype=np.int64)
+        return ((self.pac[l >> 2] >> ((~l & 3) << 1)) & 3).astype(np.uint8)
+
+
+def load_sv_reads(path):
+    out = []
+    with open(path) as f:
+        for line in f:
+            p = line.rstrip("\n").split("\t")
+            v = [int(x) for x in p[:9]]
+            # file order: qid qdir qoff qend qsize sid soff send dist
+            out.append((v[0], v[5], v[1], v[2], v[3], v[4], v[6], v[7], v[8]))
+    return out  # (query_id, subject_id, qdir, qoff, qend, qsize, soff, send, dist)
+
+
+def load_sv_signatures(path):
+    """-> (ins multiset, del multiset) as sorted lists of 13-int tuples + read name."""
+    ins, dele = [], []
+    with open(path) as f:
+        for line in f:
+            p = line.rstrip("\n").split("\t")
+            rec = tuple(int(x) for x in p[:13]) + (p[13],)
+            (ins if rec[12] == 6 else dele).append(rec)
+    return sorted(ins), sorted(dele)
+
+
+class OracleSvRead(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("qid", "sid", "qdir", "qoff", "qend", "qsize", "soff", "send", "dist")]
+
+
+class OracleSvSig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("qid", "qdir", "qfrom", "qto", "fqfrom", "fqto", "qsize", "sfrom", "sto",
+                                       "fsfrom", "fsto", "ssize", "type")]
+
+
+def oracle_discover(svr, read_fwd, contig, min_indel):
+    """lesv_oracle_discover_one -> (n or -1, list of 13-int tuples)."""
+    lib, _ = oracle()
+    s = OracleSvRead(*[int(x) for x in (svr[0], svr[1], svr[2], svr[3], svr[4], svr[5], svr[6], svr[7], svr[8])])
+    out = (OracleSvSig * 64)()
+    n = lib.lesv_oracle_discover_one(C.byref(s), _ptr(read_fwd), len(read_fwd), _ptr(contig), len(contig), min_indel, out, 64)
+    return n, [tuple(getattr(out[i], f) for f, _ in OracleSvSig._fields_) for i in range(max(n, 0))]

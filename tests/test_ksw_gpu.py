@@ -72,3 +72,18 @@ def test_identity_counts(ctx):
             si += n
     assert (qi, si) == (len(q), len(t))
     assert res[0].n_match == m
+
+
+def test_wide_band_full_matrix(ctx):
+    """Bands wider than 512 blocks run through the wide kernel (slot contexts in HBM)."""
+    from lesv_b200.synth import mutate
+    rng = np.random.default_rng(21)
+    cases = []
+    for n in (8300, 9100):
+        q = rng.integers(0, 4, n, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, 0.12, rng))
+        cases.append((q, t, -1))                       # no band: max(qlen, tlen)
+    q = rng.integers(0, 4, 9000, dtype=np.uint8)
+    t = np.ascontiguousarray(np.concatenate([q[:4000], q[5500:]]))      # 1.5 kb deletion, band too small -> full
+    cases.append((q, t, max(len(q), len(t))))
+    _check(ctx, cases)
