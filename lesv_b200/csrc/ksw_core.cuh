@@ -298,28 +298,29 @@ KSW_HD int tb_row_blocks(int qlen, int tlen, int w)
 struct ThreadCtx {
     BlockState b;
     int myB;               // block currently held (-1 = none)
+    int cand;              // next block this thread can own: == slot (mod nt), >= every block it has held
     uint32_t tword;        // 16 target bases of block myB, 2 bits each, column c at bits 2c
     uint32_t qlo, qhi;     // window into the packed reversed query: words qwi, qwi+1 of qrp
     int qwi;
 };
 
-KSW_HD int owned_block(int tid, int nt, int bst)
+KSW_HD void thread_ctx_reset(ThreadCtx& c, int slot)
 {
-    int d = (tid - bst) % nt;
-    if (d < 0) d += nt;
-    return bst + d;
+    c.myB = -1; c.cand = slot; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
+    c.b.init();
 }
 
 // tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by
 // +1 (qrp[0] is a zero pad word so that index -1..-16 reads zeros).
 // Returns true if the thread computed DP cells this row (then cout/tb are valid).
-KSW_HD bool thread_row_step(ThreadCtx& c, int tid, int nt, int r, int qlen, int tlen, int w,
+KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w,
                             const uint32_t* tp, const uint32_t* qrp,
                             const Carry cin_from_left, Carry& cout, uint32_t tb[4], int& tb_block)
 {
     const RowGeom g = row_geom(r, qlen, tlen, w);
     const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
-    const int B = owned_block(tid, nt, bst);
+    while (c.cand < bst) c.cand += nt;      // the band left this thread's block behind: take the next one
+    const int B = c.cand;
     if (B > bwr) return false;
     if (B != c.myB) {                       // take ownership of a new block
         c.myB = B;

@@ -263,16 +263,17 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
 // ---------------------------------------------------------------------------------------------
 // DP kernel
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 512 / NT))
+constexpr int kMaxNT = 640;
+
+__global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
               uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
               KswOut* __restrict__ outs, int* counter)
 {
-    constexpr int NW = NT / 32;
+    const int NT = blockDim.x, NW = NT >> 5;
     extern __shared__ uint32_t seq_s[];
-    __shared__ uint2 carry_slot[2][NW];
+    __shared__ uint2 carry_slot[2][kMaxNT / 32];
     __shared__ int s_job;
     __shared__ BtShared bt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -294,8 +295,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         __syncthreads();
 
         ThreadCtx c;
-        c.myB = -1; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
-        c.b.init();
+        thread_ctx_reset(c, tid);
         Carry prev_out = carry_init();
         const int nrow = qlen + tlen - 1;
         const size_t prow = (size_t)job.tb_blocks * 16;
@@ -304,13 +304,13 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
             cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
             if (lane == 0) {
-                const uint2 v = carry_slot[(r + 1) & 1][(warp + NW - 1) % NW];   // written in row r-1
+                const uint2 v = carry_slot[(r + 1) & 1][warp ? warp - 1 : NW - 1];   // written in row r-1
                 cin.xv = v.x; cin.x2 = v.y;
             }
             Carry cout;
             uint32_t tb[4];
             int tbb = 0;
-            if (thread_row_step(c, tid, NT, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
+            if (thread_row_step(c, NT, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
                 *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)tbb * 16) =
                     make_uint4(tb[0], tb[1], tb[2], tb[3]);
                 prev_out = cout;
@@ -381,10 +381,11 @@ ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ orde
         uint32_t* ctxs = scratch;                                  // [kCtxWords][nslot]
         uint2* pub = reinterpret_cast<uint2*>(scratch + (size_t)kCtxWords * max_slots);   // [2][nslot]
         {
-            ThreadCtx c;
-            c.myB = -1; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
-            c.b.init();
-            for (int sidx = tid; sidx < nslot; sidx += kWideNT) ctx_store(c, ctxs, nslot, sidx);
+            for (int sidx = tid; sidx < nslot; sidx += kWideNT) {
+                ThreadCtx c;
+                thread_ctx_reset(c, sidx);
+                ctx_store(c, ctxs, nslot, sidx);
+            }
         }
         __syncthreads();
         const int nrow = qlen + tlen - 1;
@@ -404,7 +405,7 @@ ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ orde
                 Carry cout;
                 uint32_t tb[4];
                 int tbb = 0;
-                if (thread_row_step(c, sidx, nslot, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
+                if (thread_row_step(c, nslot, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
                     *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)tbb * 16) =
                         make_uint4(tb[0], tb[1], tb[2], tb[3]);
                     pub_r[sidx] = make_uint2(cout.xv, cout.x2);
@@ -443,28 +444,15 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
     return (size_t)(tp_words(max_tlen) + qrp_words(max_qlen)) * sizeof(uint32_t);
 }
 
-int ksw_ctas_per_sm(int nt) { return nt >= 512 ? 1 : 512 / nt; }
-
-template <int NT>
-static void launch_t(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
-                     const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                     KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
-{
-    cudaFuncSetAttribute(ksw_dp_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ksw_dp_kernel<NT><<<n_ctas, NT, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                               d_cigar, d_runs, d_out, d_counter);
-}
+int ksw_ctas_per_sm(int nt) { int n = 640 / nt; return n < 1 ? 1 : n > 8 ? 8 : n; }
 
 void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
                 const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
                 KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
-    switch (nt) {
-        case 64:  launch_t<64>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
-        case 128: launch_t<128>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
-        case 256: launch_t<256>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
-        default:  launch_t<512>(n_ctas, smem, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs, d_out, d_counter, s); break;
-    }
+    cudaFuncSetAttribute(ksw_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ksw_dp_kernel<<<n_ctas, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                           d_cigar, d_runs, d_out, d_counter);
 }
 
 }  // namespace lesvksw

@@ -64,7 +64,7 @@ __host__ __device__ static inline int window_blocks(int tlen, int w)
 void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const uint8_t* d_subject_pac,
                  uint32_t* d_pool, cudaStream_t s);
 
-// Persistent DP + backtrack kernel; `nt` in {64,128,256,512}. job_order[0..njobs) lists the jobs
+// Persistent DP + backtrack kernel; `nt` = threads per CTA, any multiple of 32 up to 640. job_order[0..njobs) lists the jobs
 // of this launch (indices into d_jobs); d_counter must be zero on entry.
 // smem = ksw_smem_bytes(longest query, longest target among these jobs).
 void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_job_order, int njobs,

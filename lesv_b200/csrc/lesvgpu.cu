@@ -171,16 +171,19 @@ extern "C" int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* 
 // ---------------------------------------------------------------------------------------------
 static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_bytes, bool want_cigar, bool want_runs)
 {
-    static const int kClasses[4] = {64, 128, 256, 512};
+    // thread-count classes of the register-resident kernel (one 16-column block per thread): the
+    // smallest class that holds the band window wastes the fewest lanes
+    static const int kClasses[] = {32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448, 480, 512, 544, 576, 608, 640};
+    constexpr int kNC = (int)(sizeof(kClasses) / sizeof(int));
     const int nj = (int)jobs.size();
-    std::vector<std::vector<int>> cls(5);            // 4 register-resident classes + wide
+    std::vector<std::vector<int>> cls(kNC + 1);      // register-resident classes + wide
     std::vector<size_t> tb_bytes(nj);
     size_t pool_words = 0, cigar_words = 0;
     for (int k = 0; k < nj; ++k) {
         KswJob& J = jobs[k];
         const int wb = window_blocks(J.tlen, J.w);
         int c = 0;
-        while (c < 4 && kClasses[c] < wb) ++c;
+        while (c < kNC && kClasses[c] < wb) ++c;
         J.tb_blocks = tb_row_blocks(J.qlen, J.tlen, J.w);
         J.tp_off = (uint32_t)pool_words; pool_words += tp_words(J.tlen);
         J.qrp_off = (uint32_t)pool_words; pool_words += qrp_words(J.qlen);
@@ -198,23 +201,23 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     struct Launch { int nt, first, count, n_ctas, max_slots; size_t stride, smem; };
     std::vector<Launch> launches;
     size_t arena_need = 0, scratch_need = 0;
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c <= kNC; ++c) {
         if (cls[c].empty()) continue;
         std::sort(cls[c].begin(), cls[c].end(), [&](int a, int b) {
             return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
         });
         Launch L;
-        L.nt = c < 4 ? kClasses[c] : 0; L.first = (int)order.size(); L.count = (int)cls[c].size();
+        L.nt = c < kNC ? kClasses[c] : 0; L.first = (int)order.size(); L.count = (int)cls[c].size();
         L.max_slots = 0;
         L.stride = (tb_bytes[cls[c][0]] + 255) & ~(size_t)255;
         int mq = 0, mt = 0;
         for (int k : cls[c]) {
             mq = std::max(mq, jobs[k].qlen); mt = std::max(mt, jobs[k].tlen); order.push_back(k);
-            if (c == 4) L.max_slots = std::max(L.max_slots, ksw_wide_slots(jobs[k].tlen, jobs[k].w));
+            if (c == kNC) L.max_slots = std::max(L.max_slots, ksw_wide_slots(jobs[k].tlen, jobs[k].w));
         }
         L.smem = ksw_smem_bytes(mq, mt);
         if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
-        int per_sm = c < 4 ? ksw_ctas_per_sm(L.nt) : 1;
+        int per_sm = c < kNC ? ksw_ctas_per_sm(L.nt) : 1;
         const size_t smem_cap = 200 * 1024;
         while (per_sm > 1 && (L.smem + 4096) * per_sm > smem_cap) --per_sm;
         int ctas = std::min(L.count, ctx->n_sm * per_sm);
@@ -223,7 +226,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (ctas < 1) { ctx->err = "arena too small"; return LESVGPU_E_NOMEM; }
         L.n_ctas = ctas;
         arena_need = std::max(arena_need, L.stride * (size_t)ctas);
-        if (c == 4) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)ctas);
+        if (c == kNC) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)ctas);
         launches.push_back(L);
     }
     CK(ctx->d_raw.reserve(raw_bytes + 16));

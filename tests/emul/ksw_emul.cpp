@@ -52,7 +52,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
     pack_words(target, tlen, 0, tp, 0, (tlen >> 4) + 4);
     pack_words(query, qlen, 1, qrp, 1, (qlen >> 4) + 6);
     std::vector<ThreadCtx> th(nt);
-    for (auto& t : th) { t.myB = -1; t.qwi = -0x7fffffff; }
+    for (int t = 0; t < nt; ++t) thread_ctx_reset(th[t], t);
     std::vector<Carry> pub(nt), pub_next(nt);
     for (auto& c : pub) c = carry_init();
     for (int r = 0; r < (int)nrow; ++r) {
@@ -61,7 +61,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
         for (int tid = 0; tid < nt; ++tid) {
             Carry cout; uint32_t tb[4]; int tbb = 0;
             const Carry cin = pub[(tid + nt - 1) % nt];
-            if (thread_row_step(th[tid], tid, nt, r, qlen, tlen, w, tp.data(), qrp.data(), cin, cout, tb, tbb)) {
+            if (thread_row_step(th[tid], nt, r, qlen, tlen, w, tp.data(), qrp.data(), cin, cout, tb, tbb)) {
                 if (tbb < 0 || tbb >= prow_blocks) return -2;
                 memcpy(&p[(size_t)r * prow + (size_t)tbb * 16], tb, 16);
                 pub_next[tid] = cout;

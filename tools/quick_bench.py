@@ -5,13 +5,13 @@ import numpy as np
 from lesv_b200 import capi
 from lesv_b200.synth import mutate
 
-def run(ctx, n, length, err, rng, reps=2):
+def run(ctx, n, length, err, rng, reps=2, full=False):
     qs, ts, ws = [], [], []
     for _ in range(n):
         t = rng.integers(0, 4, length, dtype=np.uint8)
         q = np.ascontiguousarray(mutate(t, err, rng))
         dist = int((len(q) + len(t)) * (100 - 100 * (1 - err)) / 200)
-        ws.append(int(dist * 1.2)); qs.append(q); ts.append(t)
+        ws.append(-1 if full else int(dist * 1.2)); qs.append(q); ts.append(t)
     cells = sum(capi.ksw_cells(len(q), len(t), w)[0] for q, t, w in zip(qs, ts, ws))
     for rep in range(reps):
         t0 = time.time()
@@ -24,7 +24,8 @@ def run(ctx, n, length, err, rng, reps=2):
 if __name__ == "__main__":
     ctx = capi.Context(0)
     rng = np.random.default_rng(1)
-    run(ctx, 64, 2000, 0.12, rng)
     run(ctx, 592, 10000, 0.12, rng)
+    run(ctx, 148, 50000, 0.10, rng, reps=1)
     run(ctx, 148, 50000, 0.12, rng)
-    run(ctx, 296, 50000, 0.12, rng, reps=1)
+    run(ctx, 148, 50000, 0.15, rng, reps=1)
+    run(ctx, 16, 20000, 0.12, rng, reps=1, full=True)
