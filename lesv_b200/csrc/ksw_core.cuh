@@ -208,18 +208,26 @@ KSW_HD void update_scores(BlockState& b, uint32_t mis, uint32_t fresh16)
     }
 }
 
-// One anti-diagonal step of a 16-column block.  `cin` holds the previous-row values of the column
-// left of the block; on return `cout` holds this row's values of column 15 and tb[0..3] the 16
-// traceback bytes (column order given by tb_byte_pos).
-KSW_HD void block_row(BlockState& b, const Carry cin, Carry& cout, uint32_t tb[4])
+// One anti-diagonal step of a 16-column block.  `carry()` returns the previous-row values of the
+// column left of the block; it is called as late as possible (just before pair 0, the last pair
+// processed) so that a neighbour that is still finishing its previous row is not waited for.  On
+// return `cout` holds this row's values of column 15 and tb[0..3] the 16 traceback bytes (column
+// order given by tb_byte_pos).
+template <class CarryFn>
+KSW_HD void block_row(BlockState& b, CarryFn&& carry, Carry& cout, uint32_t tb[4])
 {
-    // previous-row left neighbours of pair 0 = (column -1, column 7)
-    const uint32_t xl0 = prmt(cin.xv, b.X[7], 0x5410);     // lo = cin X, hi = X[7].lo
-    const uint32_t vl0 = prmt(cin.xv, b.V[7], 0x5432);     // lo = cin V, hi = V[7].lo
-    const uint32_t x2l0 = prmt(cin.x2, b.X2[7], 0x5410);
+    // previous-row values of column 7 = left neighbours of column 8 (high lane of pair 0)
+    const uint32_t x7 = b.X[7], v7 = b.V[7], x27 = b.X2[7];
+    uint32_t xl0 = 0, vl0 = 0, x2l0 = 0;
     uint32_t kk[8];
 #pragma unroll
     for (int j = 7; j >= 0; --j) {          // descending: pair j-1 still holds the previous row
+        if (j == 0) {
+            const Carry cin = carry();
+            xl0 = prmt(cin.xv, x7, 0x5410);        // lo = carried X (column -1), hi = X of column 7
+            vl0 = prmt(cin.xv, v7, 0x5432);        // lo = carried V, hi = V of column 7
+            x2l0 = prmt(cin.x2, x27, 0x5410);
+        }
         const uint32_t x1 = j ? b.X[j - 1] : xl0;
         const uint32_t v1 = j ? b.V[j - 1] : vl0;
         const uint32_t x21 = j ? b.X2[j - 1] : x2l0;
@@ -294,7 +302,7 @@ KSW_HD int tb_row_blocks(int qlen, int tlen, int w)
 }
 
 // ---- the per-thread row step shared by the kernel and the host emulation ----------------------
-// A thread owns, at any row, the unique block B = bst + ((tid - bst) mod NT) of the live window.
+// A thread (slot) owns, at any row, the unique block B == slot (mod nt) of the live window.
 struct ThreadCtx {
     BlockState b;
     int myB;               // block currently held (-1 = none)
@@ -302,21 +310,51 @@ struct ThreadCtx {
     uint32_t tword;        // 16 target bases of block myB, 2 bits each, column c at bits 2c
     uint32_t qlo, qhi;     // window into the packed reversed query: words qwi, qwi+1 of qrp
     int qwi;
+    int fast_lo, fast_hi;  // rows in which block myB lies strictly inside the band (fast path)
+    int tb_off;            // byte offset of block myB inside a traceback row: 16 * (myB mod tb_blocks)
 };
 
 KSW_HD void thread_ctx_reset(ThreadCtx& c, int slot)
 {
     c.myB = -1; c.cand = slot; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
+    c.fast_lo = 0; c.fast_hi = -1; c.tb_off = 0;
     c.b.init();
 }
 
-// tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by
-// +1 (qrp[0] is a zero pad word so that index -1..-16 reads zeros).
-// Returns true if the thread computed DP cells this row (then cout/tb are valid).
-KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w,
-                            const uint32_t* tp, const uint32_t* qrp,
-                            const Carry cin_from_left, Carry& cout, uint32_t tb[4], int& tb_block)
+// Where block B of a row is stored: the live window never spans more than tb_blocks blocks
+// (ksw2_extd2_sse.c:182 asserts the same), so B mod tb_blocks is collision-free within a row.
+KSW_HD int tb_block_slot(int B, int tb_blocks) { return B % tb_blocks; }
+
+KSW_HD uint32_t query_window(ThreadCtx& c, const uint32_t* qrp, int qlen, int r, int B)
 {
+    // reversed-query index under column 0 of the block; it slides down by one per row
+    const int qbase = qlen - 1 - r + 16 * B;
+    const int wi = (qbase >> 4) + 1;        // arithmetic shift = floor; +1 skips the pad word
+    if (wi != c.qwi) {
+        if (wi == c.qwi - 1) { c.qhi = c.qlo; c.qlo = qrp[wi]; }
+        else { c.qlo = qrp[wi]; c.qhi = qrp[wi + 1]; }
+        c.qwi = wi;
+    }
+    return funnel_r(c.qlo, c.qhi, 2 * (qbase & 15));
+}
+
+// tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by
+// +1 (qrp[0] is a zero pad word so that index -1..-16 reads zeros).  `carry()` fetches what the
+// owner of block B-1 published for row r-1 (called at most once, and only if needed).
+// Returns true if the thread computed DP cells this row (then cout/tb are valid and the 16 bytes
+// belong at byte offset c.tb_off of traceback row r).
+template <class CarryFn>
+KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w, int tb_blocks,
+                            const uint32_t* tp, const uint32_t* qrp,
+                            CarryFn&& carry, Carry& cout, uint32_t tb[4])
+{
+    // ---- fast path: the block is strictly inside the band, nothing about the band edges matters
+    if (r >= c.fast_lo && r <= c.fast_hi) {
+        const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
+        update_scores<true>(c.b, mismatch_bits(c.tword, qword), 0xFFFF);
+        block_row(c.b, carry, cout, tb);
+        return true;
+    }
     const RowGeom g = row_geom(r, qlen, tlen, w);
     const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
     while (c.cand < bst) c.cand += nt;      // the band left this thread's block behind: take the next one
@@ -327,16 +365,20 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
         c.b.init();
         c.tword = tp[B];
         c.qwi = -0x7fffffff;
+        c.tb_off = 16 * tb_block_slot(B, tb_blocks);
+        // rows with st0 <= 16B-1 (so block B-1 was live one row earlier) and en0 >= 16B+15:
+        //   en0 = min(tlen-1, r, (r+w)>>1) >= c15  <=>  r >= max(c15, 2*c15 - w)      (c15 <= tlen-1);
+        //   row c15 itself still gets the top-row reset of column c15 below, so start one row later
+        //   st0 = max(0, r-qlen+1, (r-w+1)>>1) <= c0-1  <=>  r <= min(c0+qlen-2, 2*c0-2+w+1)
+        const int c0 = 16 * B, c15 = c0 + 15;
+        c.fast_lo = 0; c.fast_hi = -1;
+        if (B > 0 && c15 <= tlen - 1) {
+            const int lo = c15 + 1 > 2 * c15 - w ? c15 + 1 : 2 * c15 - w;
+            const int h1 = c0 + qlen - 2, h2 = 2 * (c0 - 1) + w;
+            c.fast_lo = lo; c.fast_hi = h1 < h2 ? h1 : h2;
+        }
     }
-    // reversed-query index under column 0 of the block; it slides down by one per row
-    const int qbase = qlen - 1 - r + 16 * B;
-    const int wi = (qbase >> 4) + 1;        // arithmetic shift = floor; +1 skips the pad word
-    if (wi != c.qwi) {
-        if (wi == c.qwi - 1) { c.qhi = c.qlo; c.qlo = qrp[wi]; }
-        else { c.qlo = qrp[wi]; c.qhi = qrp[wi + 1]; }
-        c.qwi = wi;
-    }
-    const uint32_t qword = funnel_r(c.qlo, c.qhi, 2 * (qbase & 15));
+    const uint32_t qword = query_window(c, qrp, qlen, r, B);
     const uint32_t mis = mismatch_bits(c.tword, qword);
     const int c0 = 16 * B;
     const bool interior = c0 >= g.st0 && c0 + 15 <= g.en0;
@@ -361,19 +403,13 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                 c.b.Y2[jj] &= ~m;
             }
     }
-    Carry cin;
-    if (B == 0) cin = carry_left_boundary(r);
-    else {
-        // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
-        bool left_live = false;
-        if (r > 0) {
-            const RowGeom gp = row_geom(r - 1, qlen, tlen, w);
-            left_live = B - 1 >= (gp.st0 >> 4);
-        }
-        cin = left_live ? cin_from_left : carry_init();
-    }
-    block_row(c.b, cin, cout, tb);
-    tb_block = B - bst;
+    // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
+    bool left_live = false;
+    if (B > 0 && r > 0) left_live = B - 1 >= (row_geom(r - 1, qlen, tlen, w).st0 >> 4);
+    block_row(c.b, [&]() -> Carry {
+        if (B == 0) return carry_left_boundary(r);
+        return left_live ? carry() : carry_init();
+    }, cout, tb);
     return true;
 }
 

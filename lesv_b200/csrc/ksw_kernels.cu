@@ -199,8 +199,8 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
                 b1 = b0 + ((ic & 15) >= 8 ? 1 : -1);
                 if (b1 < bst || b1 > ben) b1 = -1;
                 const uint8_t* row = arena + (size_t)r * prow;
-                sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + (size_t)(b0 - bst) * 16);
-                if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + (size_t)(b1 - bst) * 16);
+                sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16);
+                if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16);
             }
             sh.blk[k][0] = b0; sh.blk[k][1] = b1;
         }
@@ -263,68 +263,174 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
 // ---------------------------------------------------------------------------------------------
 // DP kernel
 // ---------------------------------------------------------------------------------------------
+// No CTA-wide barrier inside the anti-diagonal loop.  The only cross-thread dependency of a row is
+// "column 15 of the block to my left, one row earlier": inside a warp that is a shuffle of a value
+// the neighbour lane already holds; across warps (and, for clusters, across CTAs) it goes through a
+// small ring of tagged slots in (distributed) shared memory.  Lane 31 of a warp publishes after its
+// row, lane 0 of the next warp picks the value up just before it needs it (pair 0 is processed
+// last), so warps drift apart by a row or two instead of all waiting for the slowest one.  A
+// consumed-rows counter flowing the other way keeps a producer from lapping its consumer.
 constexpr int kMaxNT = 640;
+constexpr int kMaxWarps = kMaxNT / 32;
+constexpr int kRingD = 4;
 
+struct CarrySlot { uint32_t xv, x2, tag, pad; };
+struct PipeShared {
+    CarrySlot inbox[kMaxWarps][kRingD];   // inbox[w]: rows published by the left neighbour of warp w
+    uint32_t consumed[kMaxWarps];         // rows warp w has taken out of inbox[w]
+    uint32_t right_consumed;              // cluster: rows taken by warp 0 of the CTA to the right
+    int job;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool kCluster> __device__ __forceinline__ uint32_t ld_acquire(uint32_t addr)
+{
+    uint32_t v;
+    if (kCluster) asm volatile("ld.acquire.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    else asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <bool kCluster> __device__ __forceinline__ void st_release(uint32_t addr, uint32_t v)
+{
+    if (kCluster) asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    else asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+template <bool kCluster> __device__ __forceinline__ void st_pair(uint32_t addr, uint32_t a, uint32_t b)
+{
+    if (kCluster) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+    else asm volatile("st.shared::cta.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+template <bool kCluster> __device__ __forceinline__ void ld_pair(uint32_t addr, uint32_t& a, uint32_t& b)
+{
+    if (kCluster) asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+    else asm volatile("ld.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool kCluster>
 __global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
               uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
               KswOut* __restrict__ outs, int* counter)
 {
-    const int NT = blockDim.x, NW = NT >> 5;
     extern __shared__ uint32_t seq_s[];
-    __shared__ uint2 carry_slot[2][kMaxNT / 32];
-    __shared__ int s_job;
+    __shared__ PipeShared ps;
     __shared__ BtShared bt;
+    const int NT = blockDim.x, NW = NT >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* const arena = arena_base + (size_t)blockIdx.x * arena_stride;
+    const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
+    const int NTT = NT * (int)ncta;
+    uint8_t* const arena = arena_base + (size_t)(blockIdx.x / ncta) * arena_stride;
+
+    // ring endpoints of this thread (only lane 0 / lane 31 use them)
+    // consumer side: my warp's inbox, and where my "consumed" counter lives (the producer reads it)
+    uint32_t in_addr = smem_addr(&ps.inbox[warp][0]);
+    uint32_t cons_addr = smem_addr(&ps.consumed[warp]);
+    // producer side: the inbox I publish into and the counter I watch
+    uint32_t out_addr = smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]);
+    uint32_t watch_addr = smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]);
+    if (kCluster) {
+        in_addr = map_rank(in_addr, rank);
+        cons_addr = map_rank(cons_addr, rank);
+        out_addr = map_rank(out_addr, rank);
+        watch_addr = map_rank(watch_addr, rank);
+        if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
+        if (warp == NW - 1) {
+            out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
+            watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
+        }
+    }
 
     for (;;) {
-        if (tid == 0) s_job = atomicAdd(counter, 1);
-        __syncthreads();
-        const int ji = s_job;
+        if (kCluster) {
+            if (rank == 0 && tid == 0) {
+                const int j = atomicAdd(counter, 1);
+                for (uint32_t rr = 0; rr < ncta; ++rr) st_release<true>(map_rank(smem_addr(&ps.job), rr), (uint32_t)j);
+            }
+            __syncthreads();
+            cluster_sync_all();
+        } else {
+            if (tid == 0) ps.job = atomicAdd(counter, 1);
+            __syncthreads();
+        }
+        const int ji = ps.job;
         if (ji >= njobs) break;
         const int jid = order[ji];
         const KswJob job = jobs[jid];
-        const int qlen = job.qlen, tlen = job.tlen, w = job.w;
+        const int qlen = job.qlen, tlen = job.tlen, w = job.w, tb_blocks = job.tb_blocks;
         const int ntw = (int)tp_words(tlen), nqw = (int)qrp_words(qlen);
         uint32_t* tp_s = seq_s;
         uint32_t* qrp_s = seq_s + ntw;
         for (int x = tid; x < ntw; x += NT) tp_s[x] = pool[job.tp_off + x];
         for (int x = tid; x < nqw; x += NT) qrp_s[x] = pool[job.qrp_off + x];
+        for (int x = tid; x < kMaxWarps * kRingD; x += NT) ps.inbox[x / kRingD][x % kRingD].tag = 0xFFFFFFFFu;
+        if (tid < kMaxWarps) ps.consumed[tid] = 0;
+        if (tid == 0) ps.right_consumed = 0;
         __syncthreads();
+        if (kCluster) cluster_sync_all();          // every CTA's ring is reset before anyone publishes
 
         ThreadCtx c;
-        thread_ctx_reset(c, tid);
+        thread_ctx_reset(c, (int)rank * NT + tid);
         Carry prev_out = carry_init();
         const int nrow = qlen + tlen - 1;
-        const size_t prow = (size_t)job.tb_blocks * 16;
+        const size_t prow = (size_t)tb_blocks * 16;
         for (int r = 0; r < nrow; ++r) {
             Carry cin;
             cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
             cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-            if (lane == 0) {
-                const uint2 v = carry_slot[(r + 1) & 1][warp ? warp - 1 : NW - 1];   // written in row r-1
-                cin.xv = v.x; cin.x2 = v.y;
-            }
+            bool fetched = false;
+            auto consume = [&]() -> Carry {        // lane 0: take row r-1 out of the inbox
+                Carry v = carry_init();
+                fetched = true;
+                if (r == 0) return v;
+                const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                while (ld_acquire<kCluster>(slot + 8) != (uint32_t)(r - 1)) { }
+                ld_pair<kCluster>(slot, v.xv, v.x2);
+                st_release<kCluster>(cons_addr, (uint32_t)r);
+                return v;
+            };
             Carry cout;
             uint32_t tb[4];
-            int tbb = 0;
-            if (thread_row_step(c, NT, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
-                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)tbb * 16) =
+            const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                             [&]() -> Carry { return lane == 0 ? consume() : cin; }, cout, tb);
+            if (did) {
+                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
                     make_uint4(tb[0], tb[1], tb[2], tb[3]);
                 prev_out = cout;
             }
-            if (lane == 31) carry_slot[r & 1][warp] = make_uint2(prev_out.xv, prev_out.x2);
-            __syncthreads();
+            if (lane == 0 && !fetched) consume();                      // flow control only
+            if (lane == 31) {                                          // publish row r
+                if (r >= kRingD)
+                    while ((int)ld_acquire<kCluster>(watch_addr) < r - kRingD + 1) { }
+                const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                st_pair<kCluster>(slot, prev_out.xv, prev_out.x2);
+                st_release<kCluster>(slot + 8, (uint32_t)r);
+            }
+            __syncwarp();
         }
-        if (warp == 0)
+        __syncthreads();
+        if (kCluster) { __threadfence(); cluster_sync_all(); }
+        if (rank == 0 && warp == 0)
             backtrack_warp(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off,
                            run_pool + job.sig_off, outs + jid, bt, lane);
         __syncthreads();
+        if (kCluster) cluster_sync_all();
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // wide bands (window > 512 blocks: full-band retries, chained dual HSPs)
@@ -404,9 +510,9 @@ ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ orde
                 Carry cin; cin.xv = pv.x; cin.x2 = pv.y;
                 Carry cout;
                 uint32_t tb[4];
-                int tbb = 0;
-                if (thread_row_step(c, nslot, r, qlen, tlen, w, tp_s, qrp_s, cin, cout, tb, tbb)) {
-                    *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)tbb * 16) =
+                if (thread_row_step(c, nslot, r, qlen, tlen, w, job.tb_blocks, tp_s, qrp_s,
+                                    [&]() -> Carry { return cin; }, cout, tb)) {
+                    *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
                         make_uint4(tb[0], tb[1], tb[2], tb[3]);
                     pub_r[sidx] = make_uint2(cout.xv, cout.x2);
                 }
@@ -446,13 +552,46 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 
 int ksw_ctas_per_sm(int nt) { int n = 640 / nt; return n < 1 ? 1 : n > 8 ? 8 : n; }
 
-void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
-                const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
+cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
+                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
+                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
-    cudaFuncSetAttribute(ksw_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ksw_dp_kernel<<<n_ctas, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                           d_cigar, d_runs, d_out, d_counter);
+    if (ncta <= 1) {
+        cudaFuncSetAttribute(ksw_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ksw_dp_kernel<false><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                                          d_cigar, d_runs, d_out, d_counter);
+        return cudaGetLastError();
+    }
+    cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
+    cfg.blockDim = dim3((unsigned)nt);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                              d_cigar, d_runs, d_out, d_counter);
+}
+
+// how many clusters of this shape can be co-resident on the device (0 = shape not launchable)
+int ksw_max_clusters(int nt, int ncta, size_t smem)
+{
+    if (ncta <= 1) return 1 << 20;
+    cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 }  // namespace lesvksw

@@ -64,14 +64,16 @@ __host__ __device__ static inline int window_blocks(int tlen, int w)
 void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const uint8_t* d_subject_pac,
                  uint32_t* d_pool, cudaStream_t s);
 
-// Persistent DP + backtrack kernel; `nt` = threads per CTA, any multiple of 32 up to 640. job_order[0..njobs) lists the jobs
-// of this launch (indices into d_jobs); d_counter must be zero on entry.
+// Persistent DP + backtrack kernel.  `nt` = threads per CTA (multiple of 32, <= 640), `ncta` = CTAs
+// per alignment (1, or a thread-block cluster of 2/4/8/16 CTAs for bands wider than 640 blocks);
+// job_order[0..njobs) lists the jobs of this launch; *d_counter must be zero on entry.
 // smem = ksw_smem_bytes(longest query, longest target among these jobs).
-void launch_ksw(int nt, int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_job_order, int njobs,
-                const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
-                KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
+cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_job_order,
+                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
+                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
+int ksw_max_clusters(int nt, int ncta, size_t smem);
 
-// Bands wider than 512 blocks: slot contexts in global scratch (ksw_wide_scratch_words per CTA).
+// Fallback for bands no cluster shape can hold: slot contexts in global scratch (ksw_wide_scratch_words per CTA).
 void launch_ksw_wide(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
                      const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_scratch,
                      size_t scratch_stride_words, int max_slots, uint32_t* d_cigar, KswGapRun* d_runs,

@@ -54,11 +54,15 @@ struct PinBuf {
 
 }  // namespace
 
+constexpr int kSideStreams = 8;
+
 struct lesvgpu_ctx {
     int device = 0;
     int n_sm = 0;
     size_t arena_limit = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[kSideStreams] = {};        // launch classes of one batch run concurrently
+    cudaEvent_t side_done[kSideStreams] = {};
     cudaEvent_t ev[8] = {};
     std::string err;
     lesvgpu_timing timing = {};
@@ -112,6 +116,8 @@ extern "C" int lesvgpu_ctx_create(int device, size_t arena_bytes, lesvgpu_ctx** 
     ctx->arena_limit = arena_bytes ? arena_bytes : (size_t)(free_b * 0.8);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LESVGPU_E_CUDA; }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& st : ctx->side) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (auto& e : ctx->side_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return LESVGPU_OK;
 }
@@ -126,6 +132,8 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     ctx->d_runs.release(); ctx->d_order.release(); ctx->d_counter.release();
     ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
+    for (auto& e : ctx->side_done) cudaEventDestroy(e);
+    for (auto& st : ctx->side) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -171,19 +179,30 @@ extern "C" int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* 
 // ---------------------------------------------------------------------------------------------
 static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_bytes, bool want_cigar, bool want_runs)
 {
-    // thread-count classes of the register-resident kernel (one 16-column block per thread): the
-    // smallest class that holds the band window wastes the fewest lanes
-    static const int kClasses[] = {32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384, 416, 448, 480, 512, 544, 576, 608, 640};
-    constexpr int kNC = (int)(sizeof(kClasses) / sizeof(int));
+    // A launch class = (CTAs per alignment, threads per CTA).  One 16-column block per thread: the
+    // smallest shape that holds the band window wastes the fewest lanes.  Bands wider than 640
+    // blocks run on a thread-block cluster (2/4/8/16 CTAs passing carries through DSMEM).
+    struct Shape { int ncta, nt; };
+    auto shape_of = [](int wb) -> Shape {
+        if (wb <= 640) return {1, (wb + 31) / 32 * 32};
+        for (int ncta = 2; ncta <= 16; ncta *= 2)
+            if (wb <= ncta * 640) return {ncta, ((wb + ncta - 1) / ncta + 63) / 64 * 64};
+        return {0, 0};                                   // wider than any cluster: global-memory fallback
+    };
     const int nj = (int)jobs.size();
-    std::vector<std::vector<int>> cls(kNC + 1);      // register-resident classes + wide
+    struct Launch {
+        int ncta, nt, first, count, n_clusters, max_slots;
+        size_t stride, smem, arena_off;
+        double work;
+        std::vector<int> ids;
+    };
+    std::vector<Launch> launches;
     std::vector<size_t> tb_bytes(nj);
     size_t pool_words = 0, cigar_words = 0;
+    double total_work = 0;
     for (int k = 0; k < nj; ++k) {
         KswJob& J = jobs[k];
-        const int wb = window_blocks(J.tlen, J.w);
-        int c = 0;
-        while (c < kNC && kClasses[c] < wb) ++c;
+        const Shape sh = shape_of(window_blocks(J.tlen, J.w));
         J.tb_blocks = tb_row_blocks(J.qlen, J.tlen, J.w);
         J.tp_off = (uint32_t)pool_words; pool_words += tp_words(J.tlen);
         J.qrp_off = (uint32_t)pool_words; pool_words += qrp_words(J.qlen);
@@ -194,41 +213,63 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (pool_words > 0xFFFFFFF0ull) { ctx->err = "batch too large (packed pool offsets are 32-bit)"; return LESVGPU_E_ARG; }
         tb_bytes[k] = (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
         if (tb_bytes[k] > ctx->arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
-        cls[c].push_back(k);
+        size_t li = 0;
+        for (; li < launches.size(); ++li)
+            if (launches[li].ncta == sh.ncta && launches[li].nt == sh.nt) break;
+        if (li == launches.size()) { Launch L{}; L.ncta = sh.ncta; L.nt = sh.nt; launches.push_back(L); }
+        launches[li].ids.push_back(k);
+        launches[li].work += (double)tb_bytes[k];
+        total_work += (double)tb_bytes[k];
     }
+    // biggest alignments first, both across launches and inside each launch's queue
+    std::sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
+        return a.ncta * a.nt != b.ncta * b.nt ? a.ncta * a.nt > b.ncta * b.nt : a.nt > b.nt;
+    });
     std::vector<int> order;
     order.reserve(nj);
-    struct Launch { int nt, first, count, n_ctas, max_slots; size_t stride, smem; };
-    std::vector<Launch> launches;
     size_t arena_need = 0, scratch_need = 0;
-    for (int c = 0; c <= kNC; ++c) {
-        if (cls[c].empty()) continue;
-        std::sort(cls[c].begin(), cls[c].end(), [&](int a, int b) {
+    // SM budget: every launch gets SMs in proportion to its share of the work (traceback bytes ~ cells)
+    const double budget = ctx->n_sm * 1.0;
+    for (Launch& L : launches) {
+        std::sort(L.ids.begin(), L.ids.end(), [&](int a, int b) {
             return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
         });
-        Launch L;
-        L.nt = c < kNC ? kClasses[c] : 0; L.first = (int)order.size(); L.count = (int)cls[c].size();
+        L.first = (int)order.size(); L.count = (int)L.ids.size();
+        L.stride = (tb_bytes[L.ids[0]] + 255) & ~(size_t)255;
         L.max_slots = 0;
-        L.stride = (tb_bytes[cls[c][0]] + 255) & ~(size_t)255;
         int mq = 0, mt = 0;
-        for (int k : cls[c]) {
+        for (int k : L.ids) {
             mq = std::max(mq, jobs[k].qlen); mt = std::max(mt, jobs[k].tlen); order.push_back(k);
-            if (c == kNC) L.max_slots = std::max(L.max_slots, ksw_wide_slots(jobs[k].tlen, jobs[k].w));
+            if (L.ncta == 0) L.max_slots = std::max(L.max_slots, ksw_wide_slots(jobs[k].tlen, jobs[k].w));
         }
         L.smem = ksw_smem_bytes(mq, mt);
         if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
-        int per_sm = c < kNC ? ksw_ctas_per_sm(L.nt) : 1;
-        const size_t smem_cap = 200 * 1024;
-        while (per_sm > 1 && (L.smem + 4096) * per_sm > smem_cap) --per_sm;
-        int ctas = std::min(L.count, ctx->n_sm * per_sm);
-        const size_t by_mem = ctx->arena_limit / L.stride;
-        if ((size_t)ctas > by_mem) ctas = (int)by_mem;
-        if (ctas < 1) { ctx->err = "arena too small"; return LESVGPU_E_NOMEM; }
-        L.n_ctas = ctas;
-        arena_need = std::max(arena_need, L.stride * (size_t)ctas);
-        if (c == kNC) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)ctas);
-        launches.push_back(L);
+        const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
+        const int per_sm = L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1;
+        double share = budget * L.work / total_work;                 // SMs this launch may occupy
+        int n = (int)(share * per_sm / sms_per_job + 0.999);
+        n = std::max(1, std::min(n, L.count));
+        if (L.ncta > 1) {
+            const int cap = ksw_max_clusters(L.nt, L.ncta, L.smem);
+            if (cap <= 0) { ctx->err = "cluster shape not launchable on this device"; return LESVGPU_E_CUDA; }
+            n = std::min(n, cap);
+        }
+        L.n_clusters = n;
     }
+    // fit the arenas: shrink the launches with the most clusters until everything fits
+    for (;;) {
+        arena_need = 0;
+        for (Launch& L : launches) { L.arena_off = arena_need; arena_need += L.stride * (size_t)L.n_clusters; }
+        if (arena_need <= ctx->arena_limit) break;
+        Launch* big = nullptr;
+        for (Launch& L : launches)
+            if (L.n_clusters > 1 && (!big || L.stride * L.n_clusters > big->stride * big->n_clusters)) big = &L;
+        if (!big) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
+        --big->n_clusters;
+    }
+    for (const Launch& L : launches)
+        if (L.ncta == 0) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)L.n_clusters);
+
     CK(ctx->d_raw.reserve(raw_bytes + 16));
     CK(ctx->d_pool.reserve(pool_words));
     CK(ctx->d_cigar.reserve(cigar_words + 1));
@@ -254,17 +295,25 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     launch_pack(ctx->d_jobs.p, nj, ctx->d_raw.p, ctx->d_subject.p, ctx->d_pool.p, s);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], s));
+    // the launch classes run concurrently: one side stream each, joined back into the main stream
     for (size_t li = 0; li < launches.size(); ++li) {
         const Launch& L = launches[li];
-        if (L.nt)
-            launch_ksw(L.nt, L.n_ctas, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
-                       ctx->d_arena.p, L.stride, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p,
-                       ctx->d_counter.p + li, s);
-        else
-            launch_ksw_wide(L.n_ctas, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
-                            ctx->d_arena.p, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
-                            L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, s);
-        CK(cudaGetLastError());
+        cudaStream_t ls = ctx->side[li % kSideStreams];
+        CK(cudaStreamWaitEvent(ls, ctx->ev[2], 0));
+        if (L.ncta > 0)
+            CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
+                          ctx->d_pool.p, ctx->d_arena.p + L.arena_off, L.stride, ctx->d_cigar.p, ctx->d_runs.p,
+                          ctx->d_outs.p, ctx->d_counter.p + li, ls));
+        else {
+            launch_ksw_wide(L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
+                            ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
+                            L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls);
+            CK(cudaGetLastError());
+        }
+    }
+    for (size_t k = 0; k < std::min<size_t>(launches.size(), kSideStreams); ++k) {
+        CK(cudaEventRecord(ctx->side_done[k], ctx->side[k]));
+        CK(cudaStreamWaitEvent(s, ctx->side_done[k], 0));
     }
     CK(cudaEventRecord(ctx->ev[3], s));
     size_t d2h = sizeof(KswOut) * nj;

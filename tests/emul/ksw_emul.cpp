@@ -59,11 +59,12 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
         const RowGeom g = row_geom(r, qlen, tlen, w);
         if ((g.wr >> 4) - (g.st0 >> 4) + 1 > nt) return -1;      // window does not fit NT threads
         for (int tid = 0; tid < nt; ++tid) {
-            Carry cout; uint32_t tb[4]; int tbb = 0;
+            Carry cout; uint32_t tb[4];
             const Carry cin = pub[(tid + nt - 1) % nt];
-            if (thread_row_step(th[tid], nt, r, qlen, tlen, w, tp.data(), qrp.data(), cin, cout, tb, tbb)) {
-                if (tbb < 0 || tbb >= prow_blocks) return -2;
-                memcpy(&p[(size_t)r * prow + (size_t)tbb * 16], tb, 16);
+            if (thread_row_step(th[tid], nt, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(),
+                                [&]() { return cin; }, cout, tb)) {
+                if (th[tid].tb_off < 0 || th[tid].tb_off >= (int)prow) return -2;
+                memcpy(&p[(size_t)r * prow + (size_t)th[tid].tb_off], tb, 16);
                 pub_next[tid] = cout;
             } else pub_next[tid] = carry_init();
         }
@@ -84,7 +85,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
         if (i < off) force = 2;
         if (i > off_end) force = 1;
         uint32_t byte = 0;
-        if (force < 0) byte = p[(size_t)r * prow + (size_t)((i >> 4) - (off >> 4)) * 16 + tb_byte_pos(i & 15)];
+        if (force < 0) byte = p[(size_t)r * prow + (size_t)tb_block_slot(i >> 4, prow_blocks) * 16 + tb_byte_pos(i & 15)];
         state = tb_next_state(state, byte, force);
         if (state == 0) { push(0, 1); --i; --j; }
         else if (state == 1 || state == 3) { push(2, 1); --i; }
@@ -103,7 +104,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
             const int nb = (g.en0 >> 4) - (g.st0 >> 4) + 1;
             for (int b = 0; b < nb; ++b)
                 for (int c = 0; c < 16; ++c) {
-                    const uint8_t x = p[r * prow + (size_t)b * 16 + tb_byte_pos(c)];
+                    const uint8_t x = p[r * prow + (size_t)tb_block_slot((g.st0 >> 4) + b, prow_blocks) * 16 + tb_byte_pos(c)];
                     t[r * prow + (size_t)b * 16 + c] = (uint8_t)((4 - (x & 7)) | ((x >> 7) & 1) << 3 | ((x >> 6) & 1) << 4 |
                                                              ((x >> 5) & 1) << 5 | ((x >> 4) & 1) << 6);
                 }

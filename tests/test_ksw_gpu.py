@@ -74,16 +74,34 @@ def test_identity_counts(ctx):
     assert res[0].n_match == m
 
 
-def test_wide_band_full_matrix(ctx):
-    """Bands wider than 512 blocks run through the wide kernel (slot contexts in HBM)."""
+def test_wide_bands_run_on_clusters(ctx):
+    """Bands wider than 640 blocks run on thread-block clusters (carries through DSMEM)."""
     from lesv_b200.synth import mutate
     rng = np.random.default_rng(21)
     cases = []
-    for n in (8300, 9100):
+    for n in (9100, 11000, 15000):                     # 1 CTA x 576 threads, then clusters of 2
         q = rng.integers(0, 4, n, dtype=np.uint8)
         t = np.ascontiguousarray(mutate(q, 0.12, rng))
         cases.append((q, t, -1))                       # no band: max(qlen, tlen)
     q = rng.integers(0, 4, 9000, dtype=np.uint8)
-    t = np.ascontiguousarray(np.concatenate([q[:4000], q[5500:]]))      # 1.5 kb deletion, band too small -> full
+    t = np.ascontiguousarray(np.concatenate([q[:4000], q[5500:]]))      # 1.5 kb deletion
     cases.append((q, t, max(len(q), len(t))))
+    q = rng.integers(0, 4, 24000, dtype=np.uint8)       # cluster of 4
+    cases.append((q, np.ascontiguousarray(mutate(q, 0.1, rng)), -1))
+    _check(ctx, cases)
+
+
+def test_many_small_and_mixed_shapes_in_one_batch(ctx):
+    """One batch spanning many launch classes (concurrent launches, shared arena)."""
+    from lesv_b200.synth import mutate
+    rng = np.random.default_rng(5)
+    cases = []
+    for it in range(300):
+        n = int(rng.integers(200, 6000))
+        q = rng.integers(0, 4, n, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, float(rng.uniform(0.02, 0.2)), rng))
+        if len(t) == 0:
+            t = q.copy()
+        w = int(abs(len(q) - len(t)) + rng.integers(1, 1 + n // 3))
+        cases.append((q, t, w))
     _check(ctx, cases)
