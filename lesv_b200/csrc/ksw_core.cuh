@@ -348,67 +348,68 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                             const uint32_t* tp, const uint32_t* qrp,
                             CarryFn&& carry, Carry& cout, uint32_t tb[4])
 {
-    // ---- fast path: the block is strictly inside the band, nothing about the band edges matters
+    // carry policy of this row: 0 = take what the left neighbour published, 1 = matrix edge
+    // (column 0), 2 = the left block was not computed one row earlier (initial values)
+    int policy = 0;
+    // fast path: the block is strictly inside the band, nothing about the band edges matters
     if (r >= c.fast_lo && r <= c.fast_hi) {
         const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
         update_scores<true>(c.b, mismatch_bits(c.tword, qword), 0xFFFF);
-        block_row(c.b, carry, cout, tb);
-        return true;
-    }
-    const RowGeom g = row_geom(r, qlen, tlen, w);
-    const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
-    while (c.cand < bst) c.cand += nt;      // the band left this thread's block behind: take the next one
-    const int B = c.cand;
-    if (B > bwr) return false;
-    if (B != c.myB) {                       // take ownership of a new block
-        c.myB = B;
-        c.b.init();
-        c.tword = tp[B];
-        c.qwi = -0x7fffffff;
-        c.tb_off = 16 * tb_block_slot(B, tb_blocks);
-        // rows with st0 <= 16B-1 (so block B-1 was live one row earlier) and en0 >= 16B+15:
-        //   en0 = min(tlen-1, r, (r+w)>>1) >= c15  <=>  r >= max(c15, 2*c15 - w)      (c15 <= tlen-1);
-        //   row c15 itself still gets the top-row reset of column c15 below, so start one row later
-        //   st0 = max(0, r-qlen+1, (r-w+1)>>1) <= c0-1  <=>  r <= min(c0+qlen-2, 2*c0-2+w+1)
-        const int c0 = 16 * B, c15 = c0 + 15;
-        c.fast_lo = 0; c.fast_hi = -1;
-        if (B > 0 && c15 <= tlen - 1) {
-            const int lo = c15 + 1 > 2 * c15 - w ? c15 + 1 : 2 * c15 - w;
-            const int h1 = c0 + qlen - 2, h2 = 2 * (c0 - 1) + w;
-            c.fast_lo = lo; c.fast_hi = h1 < h2 ? h1 : h2;
-        }
-    }
-    const uint32_t qword = query_window(c, qrp, qlen, r, B);
-    const uint32_t mis = mismatch_bits(c.tword, qword);
-    const int c0 = 16 * B;
-    const bool interior = c0 >= g.st0 && c0 + 15 <= g.en0;
-    if (interior) update_scores<true>(c.b, mis, 0xFFFF);
-    else {
-        // fresh columns: st0 <= c0 + col <= wr
-        int lo = g.st0 - c0, hi = g.wr - c0;
-        lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
-        uint32_t fresh = lo <= hi ? ((0xFFFFu >> (15 - hi)) & (0xFFFFu << lo)) & 0xFFFFu : 0u;
-        update_scores<false>(c.b, mis, fresh);
-    }
-    if (B > ben) return false;              // pre-block: only its score bytes exist so far
-    if ((r >> 4) == B) {                    // top row of the matrix reaches column r: :152-155
-        const int col = r & 15, j = col & 7;
-        const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
-        const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-            if (jj == j) {
-                c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
-                c.b.Y[jj] &= ~m;            // y = -(q+e), y2 = -(q2+e2)
-                c.b.Y2[jj] &= ~m;
+    } else {
+        const RowGeom g = row_geom(r, qlen, tlen, w);
+        const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
+        while (c.cand < bst) c.cand += nt;  // the band left this thread's block behind: take the next one
+        const int B = c.cand;
+        if (B > bwr) return false;
+        if (B != c.myB) {                   // take ownership of a new block
+            c.myB = B;
+            c.b.init();
+            c.tword = tp[B];
+            c.qwi = -0x7fffffff;
+            c.tb_off = 16 * tb_block_slot(B, tb_blocks);
+            // rows with st0 <= 16B-1 (so block B-1 was live one row earlier) and en0 >= 16B+15:
+            //   en0 = min(tlen-1, r, (r+w)>>1) >= c15  <=>  r >= max(c15, 2*c15 - w)   (c15 <= tlen-1);
+            //   row c15 itself still gets the top-row reset of column c15 below, so start one row later
+            //   st0 = max(0, r-qlen+1, (r-w+1)>>1) <= c0-1  <=>  r <= min(c0+qlen-2, 2*(c0-1)+w)
+            const int c0 = 16 * B, c15 = c0 + 15;
+            c.fast_lo = 0; c.fast_hi = -1;
+            if (B > 0 && c15 <= tlen - 1) {
+                const int lo = c15 + 1 > 2 * c15 - w ? c15 + 1 : 2 * c15 - w;
+                const int h1 = c0 + qlen - 2, h2 = 2 * (c0 - 1) + w;
+                c.fast_lo = lo; c.fast_hi = h1 < h2 ? h1 : h2;
             }
+        }
+        const uint32_t qword = query_window(c, qrp, qlen, r, B);
+        const uint32_t mis = mismatch_bits(c.tword, qword);
+        const int c0 = 16 * B;
+        if (c0 >= g.st0 && c0 + 15 <= g.en0) update_scores<true>(c.b, mis, 0xFFFF);
+        else {
+            // fresh columns: st0 <= c0 + col <= wr
+            int lo = g.st0 - c0, hi = g.wr - c0;
+            lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
+            uint32_t fresh = lo <= hi ? ((0xFFFFu >> (15 - hi)) & (0xFFFFu << lo)) & 0xFFFFu : 0u;
+            update_scores<false>(c.b, mis, fresh);
+        }
+        if (B > ben) return false;          // pre-block: only its score bytes exist so far
+        if ((r >> 4) == B) {                // top row of the matrix reaches column r: :152-155
+            const int col = r & 15, j = col & 7;
+            const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
+            const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+                if (jj == j) {
+                    c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
+                    c.b.Y[jj] &= ~m;        // y = -(q+e), y2 = -(q2+e2)
+                    c.b.Y2[jj] &= ~m;
+                }
+        }
+        // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
+        if (B == 0) policy = 1;
+        else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
     }
-    // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
-    bool left_live = false;
-    if (B > 0 && r > 0) left_live = B - 1 >= (row_geom(r - 1, qlen, tlen, w).st0 >> 4);
     block_row(c.b, [&]() -> Carry {
-        if (B == 0) return carry_left_boundary(r);
-        return left_live ? carry() : carry_init();
+        if (policy == 0) return carry();
+        return policy == 1 ? carry_left_boundary(r) : carry_init();
     }, cout, tb);
     return true;
 }

@@ -274,7 +274,7 @@ constexpr int kMaxNT = 640;
 constexpr int kMaxWarps = kMaxNT / 32;
 constexpr int kRingD = 4;
 
-struct CarrySlot { uint32_t xv, x2, tag, pad; };
+struct __align__(16) CarrySlot { uint32_t xv, x2, tag, pad; };
 struct PipeShared {
     CarrySlot inbox[kMaxWarps][kRingD];   // inbox[w]: rows published by the left neighbour of warp w
     uint32_t consumed[kMaxWarps];         // rows warp w has taken out of inbox[w]
@@ -284,27 +284,32 @@ struct PipeShared {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool kCluster> __device__ __forceinline__ uint32_t ld_acquire(uint32_t addr)
+// Slot protocol without fences: a slot is ONE 16-byte shared-memory word {xv, x2, tag, -}, written
+// with a single 128-bit store and polled with a single 128-bit load, so data and tag can never be
+// seen torn; the consumed-rows counter is a single word.  volatile = re-read on every poll.
+template <bool kCluster> __device__ __forceinline__ void st_slot(uint32_t addr, uint32_t a, uint32_t b, uint32_t tag)
+{
+    if (kCluster) asm volatile("st.volatile.shared::cluster.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(a), "r"(b), "r"(tag) : "memory");
+    else asm volatile("st.volatile.shared::cta.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(a), "r"(b), "r"(tag) : "memory");
+}
+template <bool kCluster> __device__ __forceinline__ uint32_t ld_slot(uint32_t addr, uint32_t& a, uint32_t& b)
+{
+    uint32_t tag, pad;
+    if (kCluster) asm volatile("ld.volatile.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(tag), "=r"(pad) : "r"(addr) : "memory");
+    else asm volatile("ld.volatile.shared::cta.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(tag), "=r"(pad) : "r"(addr) : "memory");
+    return tag;
+}
+template <bool kCluster> __device__ __forceinline__ void st_word(uint32_t addr, uint32_t v)
+{
+    if (kCluster) asm volatile("st.volatile.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    else asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+template <bool kCluster> __device__ __forceinline__ uint32_t ld_word(uint32_t addr)
 {
     uint32_t v;
-    if (kCluster) asm volatile("ld.acquire.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    else asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    if (kCluster) asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    else asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
-}
-template <bool kCluster> __device__ __forceinline__ void st_release(uint32_t addr, uint32_t v)
-{
-    if (kCluster) asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-    else asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-template <bool kCluster> __device__ __forceinline__ void st_pair(uint32_t addr, uint32_t a, uint32_t b)
-{
-    if (kCluster) asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-    else asm volatile("st.shared::cta.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-template <bool kCluster> __device__ __forceinline__ void ld_pair(uint32_t addr, uint32_t& a, uint32_t& b)
-{
-    if (kCluster) asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
-    else asm volatile("ld.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
 }
 // address of the same shared-memory variable in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_rank(uint32_t addr, uint32_t rank)
@@ -330,36 +335,15 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     extern __shared__ uint32_t seq_s[];
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
-    const int NT = blockDim.x, NW = NT >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
-    const int NTT = NT * (int)ncta;
     uint8_t* const arena = arena_base + (size_t)(blockIdx.x / ncta) * arena_stride;
-
-    // ring endpoints of this thread (only lane 0 / lane 31 use them)
-    // consumer side: my warp's inbox, and where my "consumed" counter lives (the producer reads it)
-    uint32_t in_addr = smem_addr(&ps.inbox[warp][0]);
-    uint32_t cons_addr = smem_addr(&ps.consumed[warp]);
-    // producer side: the inbox I publish into and the counter I watch
-    uint32_t out_addr = smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]);
-    uint32_t watch_addr = smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]);
-    if (kCluster) {
-        in_addr = map_rank(in_addr, rank);
-        cons_addr = map_rank(cons_addr, rank);
-        out_addr = map_rank(out_addr, rank);
-        watch_addr = map_rank(watch_addr, rank);
-        if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
-        if (warp == NW - 1) {
-            out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
-            watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
-        }
-    }
 
     for (;;) {
         if (kCluster) {
             if (rank == 0 && tid == 0) {
                 const int j = atomicAdd(counter, 1);
-                for (uint32_t rr = 0; rr < ncta; ++rr) st_release<true>(map_rank(smem_addr(&ps.job), rr), (uint32_t)j);
+                for (uint32_t rr = 0; rr < ncta; ++rr) st_word<true>(map_rank(smem_addr(&ps.job), rr), (uint32_t)j);
             }
             __syncthreads();
             cluster_sync_all();
@@ -375,18 +359,37 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         const int ntw = (int)tp_words(tlen), nqw = (int)qrp_words(qlen);
         uint32_t* tp_s = seq_s;
         uint32_t* qrp_s = seq_s + ntw;
-        for (int x = tid; x < ntw; x += NT) tp_s[x] = pool[job.tp_off + x];
-        for (int x = tid; x < nqw; x += NT) qrp_s[x] = pool[job.qrp_off + x];
-        for (int x = tid; x < kMaxWarps * kRingD; x += NT) ps.inbox[x / kRingD][x % kRingD].tag = 0xFFFFFFFFu;
+        for (int x = tid; x < ntw; x += blockDim.x) tp_s[x] = pool[job.tp_off + x];
+        for (int x = tid; x < nqw; x += blockDim.x) qrp_s[x] = pool[job.qrp_off + x];
+        for (int x = tid; x < kMaxWarps * kRingD; x += blockDim.x) ps.inbox[x / kRingD][x % kRingD].tag = 0xFFFFFFFFu;
         if (tid < kMaxWarps) ps.consumed[tid] = 0;
         if (tid == 0) ps.right_consumed = 0;
         __syncthreads();
         if (kCluster) cluster_sync_all();          // every CTA's ring is reset before anyone publishes
 
+        // this alignment uses the first NT threads of every CTA (the launch is sized for its tier)
+        const int NT = job.nt, NW = NT >> 5, NTT = NT * (int)ncta;
+        // ring endpoints of this thread (only lane 0 / lane 31 use them): my warp's inbox and where
+        // my consumed-rows counter lives; the inbox I publish into and the counter I watch
+        uint32_t in_addr = smem_addr(&ps.inbox[warp][0]);
+        uint32_t cons_addr = smem_addr(&ps.consumed[warp]);
+        uint32_t out_addr = smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]);
+        uint32_t watch_addr = smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]);
+        if (kCluster) {
+            in_addr = map_rank(in_addr, rank);
+            cons_addr = map_rank(cons_addr, rank);
+            out_addr = map_rank(out_addr, rank);
+            watch_addr = map_rank(watch_addr, rank);
+            if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
+            if (warp == NW - 1) {
+                out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
+                watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
+            }
+        }
         ThreadCtx c;
         thread_ctx_reset(c, (int)rank * NT + tid);
         Carry prev_out = carry_init();
-        const int nrow = qlen + tlen - 1;
+        const int nrow = warp < NW ? qlen + tlen - 1 : 0;     // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
         for (int r = 0; r < nrow; ++r) {
             Carry cin;
@@ -398,9 +401,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                 fetched = true;
                 if (r == 0) return v;
                 const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                while (ld_acquire<kCluster>(slot + 8) != (uint32_t)(r - 1)) { }
-                ld_pair<kCluster>(slot, v.xv, v.x2);
-                st_release<kCluster>(cons_addr, (uint32_t)r);
+                while (ld_slot<kCluster>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
+                st_word<kCluster>(cons_addr, (uint32_t)r);
                 return v;
             };
             Carry cout;
@@ -415,10 +417,9 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             if (lane == 0 && !fetched) consume();                      // flow control only
             if (lane == 31) {                                          // publish row r
                 if (r >= kRingD)
-                    while ((int)ld_acquire<kCluster>(watch_addr) < r - kRingD + 1) { }
+                    while ((int)ld_word<kCluster>(watch_addr) < r - kRingD + 1) { }
                 const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                st_pair<kCluster>(slot, prev_out.xv, prev_out.x2);
-                st_release<kCluster>(slot + 8, (uint32_t)r);
+                st_slot<kCluster>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
             }
             __syncwarp();
         }

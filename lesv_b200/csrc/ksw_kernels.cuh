@@ -24,7 +24,7 @@ struct KswJob {
     uint32_t cigar_cap;       // capacity of that slot (qlen + tlen + 2); 0 = do not write a CIGAR
     int32_t min_indel;        // > 0: scan the alignment for gap runs >= min_indel (qx2svsig)
     uint32_t sig_off;         // first KswGapRun slot of this job (kSigCap slots)
-    uint32_t pad_;
+    int32_t nt;               // threads per CTA this alignment uses (multiple of 32, <= blockDim.x)
 };
 
 constexpr int kSigCap = 64;   // gap-run records kept per alignment

@@ -182,12 +182,18 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     // A launch class = (CTAs per alignment, threads per CTA).  One 16-column block per thread: the
     // smallest shape that holds the band window wastes the fewest lanes.  Bands wider than 640
     // blocks run on a thread-block cluster (2/4/8/16 CTAs passing carries through DSMEM).
-    struct Shape { int ncta, nt; };
+    // `tier` is the CTA size of the launch (it fixes how many CTAs share an SM); `nt` what this
+    // alignment actually uses of it.
+    struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
-        if (wb <= 640) return {1, (wb + 31) / 32 * 32};
+        static const int tiers[] = {64, 96, 128, 160, 320, 640};
+        if (wb <= 640) {
+            const int nt = (wb + 31) / 32 * 32;
+            for (int t : tiers) if (nt <= t) return {1, t, nt};
+        }
         for (int ncta = 2; ncta <= 16; ncta *= 2)
-            if (wb <= ncta * 640) return {ncta, ((wb + ncta - 1) / ncta + 63) / 64 * 64};
-        return {0, 0};                                   // wider than any cluster: global-memory fallback
+            if (wb <= ncta * 640) return {ncta, 640, ((wb + ncta - 1) / ncta + 31) / 32 * 32};
+        return {0, 0, 0};                                // wider than any cluster: global-memory fallback
     };
     const int nj = (int)jobs.size();
     struct Launch {
@@ -215,8 +221,9 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (tb_bytes[k] > ctx->arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
         size_t li = 0;
         for (; li < launches.size(); ++li)
-            if (launches[li].ncta == sh.ncta && launches[li].nt == sh.nt) break;
-        if (li == launches.size()) { Launch L{}; L.ncta = sh.ncta; L.nt = sh.nt; launches.push_back(L); }
+            if (launches[li].ncta == sh.ncta && launches[li].nt == sh.tier) break;
+        if (li == launches.size()) { Launch L{}; L.ncta = sh.ncta; L.nt = sh.tier; launches.push_back(L); }
+        J.nt = sh.nt;
         launches[li].ids.push_back(k);
         launches[li].work += (double)tb_bytes[k];
         total_work += (double)tb_bytes[k];
