@@ -17,6 +17,7 @@
 #include "ksw_kernels.cuh"
 #include "ksw_core.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace lesvksw {
 
@@ -325,7 +326,7 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool kCluster>
+template <bool kCluster, bool kBarrier>
 __global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
@@ -389,7 +390,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         ThreadCtx c;
         thread_ctx_reset(c, (int)rank * NT + tid);
         Carry prev_out = carry_init();
-        const int nrow = warp < NW ? qlen + tlen - 1 : 0;     // warps beyond NT sit this alignment out
+        const int nrow = (kBarrier || warp < NW) ? qlen + tlen - 1 : 0;     // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
         for (int r = 0; r < nrow; ++r) {
             Carry cin;
@@ -401,27 +402,29 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                 fetched = true;
                 if (r == 0) return v;
                 const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                if (kBarrier) { ld_slot<kCluster>(slot, v.xv, v.x2); return v; }
                 while (ld_slot<kCluster>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
                 st_word<kCluster>(cons_addr, (uint32_t)r);
                 return v;
             };
             Carry cout;
             uint32_t tb[4];
-            const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+            const bool did = warp < NW &&
+                             thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
                                              [&]() -> Carry { return lane == 0 ? consume() : cin; }, cout, tb);
             if (did) {
                 *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
                     make_uint4(tb[0], tb[1], tb[2], tb[3]);
                 prev_out = cout;
             }
-            if (lane == 0 && !fetched) consume();                      // flow control only
-            if (lane == 31) {                                          // publish row r
-                if (r >= kRingD)
+            if (!kBarrier && lane == 0 && !fetched) consume();          // flow control only
+            if (lane == 31 && warp < NW) {                             // publish row r
+                if (!kBarrier && r >= kRingD)
                     while ((int)ld_word<kCluster>(watch_addr) < r - kRingD + 1) { }
                 const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
                 st_slot<kCluster>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
             }
-            __syncwarp();
+            if (kBarrier) __syncthreads(); else __syncwarp();
         }
         __syncthreads();
         if (kCluster) { __threadfence(); cluster_sync_all(); }
@@ -557,14 +560,25 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
                        KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
+    // Single-CTA alignments synchronise once per anti-diagonal with a CTA barrier (waiting warps
+    // sleep); the tagged-slot ring is what clusters need (no barrier spans CTAs cheaply) and can be
+    // forced for single CTAs with LESV_KSW_RING=1 -- measured slower there: polling lanes burn issue
+    // slots of the ALU-bound SMSPs (profiles/ksw_r1_notes.md).
+    static const bool barrier_mode = !(getenv("LESV_KSW_RING") && atoi(getenv("LESV_KSW_RING")));
     if (ncta <= 1) {
-        cudaFuncSetAttribute(ksw_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ksw_dp_kernel<false><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                                          d_cigar, d_runs, d_out, d_counter);
+        if (barrier_mode) {
+            cudaFuncSetAttribute(ksw_dp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ksw_dp_kernel<false, true><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                                                    d_cigar, d_runs, d_out, d_counter);
+        } else {
+            cudaFuncSetAttribute(ksw_dp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ksw_dp_kernel<false, false><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                                                     d_cigar, d_runs, d_out, d_counter);
+        }
         return cudaGetLastError();
     }
-    cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
     cfg.blockDim = dim3((unsigned)nt);
@@ -574,7 +588,7 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true, false>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
 }
 
@@ -582,8 +596,8 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
-    cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
@@ -591,7 +605,7 @@ int ksw_max_clusters(int nt, int ncta, size_t smem)
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
