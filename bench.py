@@ -57,7 +57,7 @@ def pack_pac(seqs):
     return pac.astype(np.uint8), np.asarray(offs, dtype=np.int64)
 
 
-def make_workload(n_reads: int, seed: int, read_len: int = READ_LEN, ref_len: int = REF_LEN):
+def make_workload(n_reads: int, seed: int, read_len: int = READ_LEN, ref_len: int = REF_LEN, sv_frac: float = 0.2):
     """C2-shaped SvRead batch: (reference contig, reads, SvRead tuples)."""
     rng = np.random.default_rng(seed)
     ref = synth.random_codes(ref_len, rng)
@@ -67,7 +67,7 @@ def make_workload(n_reads: int, seed: int, read_len: int = READ_LEN, ref_len: in
         tgt_len = read_len
         sample = ref[s:s + tgt_len]
         sv = 0
-        if rng.random() < 0.2:                       # ~1 event per 250 kb of read
+        if rng.random() < sv_frac:                   # ~1 event per 250 kb of read
             size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
             pos = int(rng.integers(2000, read_len - 2000))
             if rng.random() < 0.5:                   # insertion in the sample
@@ -219,7 +219,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=296)
+    ap.add_argument("--reads-per-step", type=int, default=1184)
+    ap.add_argument("--no-sv", action="store_true", help="profiling aid: no planted INS/DEL (no cluster launches)")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -270,7 +271,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ref, reads, svreads, pairs = make_workload(args.reads_per_step, args.seed + 1000 * rank)
+    ref, reads, svreads, pairs = make_workload(args.reads_per_step, args.seed + 1000 * rank,
+                                               sv_frac=0.0 if args.no_sv else 0.2)
     subject_pac, _ = pack_pac([ref])
     query_pac, qoffs = pack_pac(reads)
     read_offset = (qoffs + 1).astype(np.uint64)

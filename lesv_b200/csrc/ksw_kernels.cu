@@ -329,7 +329,8 @@ __device__ __forceinline__ void cluster_sync_all()
 template <bool kCluster, bool kBarrier>
 __global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
-              const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, size_t arena_stride,
+              const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
+              const size_t* __restrict__ arena_off,
               uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
               KswOut* __restrict__ outs, int* counter)
 {
@@ -338,20 +339,25 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     __shared__ BtShared bt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
-    uint8_t* const arena = arena_base + (size_t)(blockIdx.x / ncta) * arena_stride;
+    // The queue is sorted by decreasing traceback size and cluster i starts with job i, so the arena
+    // of cluster i only has to hold job i: everything it pulls later is smaller.
+    const int cluster_id = (int)(blockIdx.x / ncta);
+    uint8_t* const arena = arena_base + arena_off[cluster_id];
+    bool first = true;
 
     for (;;) {
         if (kCluster) {
             if (rank == 0 && tid == 0) {
-                const int j = atomicAdd(counter, 1);
+                const int j = first ? cluster_id : atomicAdd(counter, 1);
                 for (uint32_t rr = 0; rr < ncta; ++rr) st_word<true>(map_rank(smem_addr(&ps.job), rr), (uint32_t)j);
             }
             __syncthreads();
             cluster_sync_all();
         } else {
-            if (tid == 0) ps.job = atomicAdd(counter, 1);
+            if (tid == 0) ps.job = first ? cluster_id : atomicAdd(counter, 1);
             __syncthreads();
         }
+        first = false;
         const int ji = ps.job;
         if (ji >= njobs) break;
         const int jid = order[ji];
@@ -557,7 +563,7 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 int ksw_ctas_per_sm(int nt) { int n = 640 / nt; return n < 1 ? 1 : n > 8 ? 8 : n; }
 
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
-                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
+                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* arena_stride, uint32_t* d_cigar,
                        KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
     // Single-CTA alignments synchronise once per anti-diagonal with a CTA barrier (waiting warps

@@ -66,10 +66,11 @@ void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const ui
 
 // Persistent DP + backtrack kernel.  `nt` = threads per CTA (multiple of 32, <= 640), `ncta` = CTAs
 // per alignment (1, or a thread-block cluster of 2/4/8/16 CTAs for bands wider than 640 blocks);
-// job_order[0..njobs) lists the jobs of this launch; *d_counter must be zero on entry.
+// job_order[0..njobs) lists the jobs of this launch by decreasing traceback size; cluster i starts
+// with job i and writes its traceback at d_arena + d_arena_off[i]; *d_counter must be n_clusters.
 // smem = ksw_smem_bytes(longest query, longest target among these jobs).
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_job_order,
-                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_cigar,
+                       int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* d_arena_off, uint32_t* d_cigar,
                        KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
 int ksw_max_clusters(int nt, int ncta, size_t smem);
 

@@ -73,6 +73,7 @@ struct lesvgpu_ctx {
     DevBuf<KswOut> d_outs;
     DevBuf<KswGapRun> d_runs;
     DevBuf<int> d_order, d_counter;
+    DevBuf<size_t> d_aoff;
     PinBuf<uint8_t> h_raw;
     PinBuf<uint32_t> h_cigar;
     PinBuf<KswOut> h_outs;
@@ -129,7 +130,7 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_raw.release(); ctx->d_arena.release(); ctx->d_subject.release(); ctx->d_pool.release();
     ctx->d_cigar.release(); ctx->d_scratch.release(); ctx->d_jobs.release(); ctx->d_outs.release();
-    ctx->d_runs.release(); ctx->d_order.release(); ctx->d_counter.release();
+    ctx->d_runs.release(); ctx->d_order.release(); ctx->d_counter.release(); ctx->d_aoff.release();
     ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->side_done) cudaEventDestroy(e);
@@ -198,7 +199,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     const int nj = (int)jobs.size();
     struct Launch {
         int ncta, nt, first, count, n_clusters, max_slots;
-        size_t stride, smem, arena_off;
+        size_t stride, smem, arena_off, arena_bytes;
         double work;
         std::vector<int> ids;
     };
@@ -254,7 +255,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
         const int per_sm = L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1;
         double share = budget * L.work / total_work;                 // SMs this launch may occupy
-        int n = (int)(share * per_sm / sms_per_job + 0.999);
+        int n = (int)(share * per_sm / sms_per_job);       // round down: never oversubscribe the SMs
         n = std::max(1, std::min(n, L.count));
         if (L.ncta > 1) {
             const int cap = ksw_max_clusters(L.nt, L.ncta, L.smem);
@@ -263,16 +264,37 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         }
         L.n_clusters = n;
     }
-    // fit the arenas: shrink the launches with the most clusters until everything fits
+    // fit the arenas.  Cluster i of a launch starts with job i of its (size-sorted) queue and only
+    // ever pulls smaller ones, so its arena is exactly job i's traceback; the wide fallback keeps
+    // a uniform stride.  Shrink the launch with the largest footprint until everything fits.
+    auto footprint = [&](const Launch& L) {
+        if (L.ncta == 0) return L.stride * (size_t)L.n_clusters;
+        size_t b = 0;
+        for (int i = 0; i < L.n_clusters; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
+        return b;
+    };
     for (;;) {
         arena_need = 0;
-        for (Launch& L : launches) { L.arena_off = arena_need; arena_need += L.stride * (size_t)L.n_clusters; }
+        for (Launch& L : launches) { L.arena_off = arena_need; L.arena_bytes = footprint(L); arena_need += L.arena_bytes; }
         if (arena_need <= ctx->arena_limit) break;
         Launch* big = nullptr;
         for (Launch& L : launches)
-            if (L.n_clusters > 1 && (!big || L.stride * L.n_clusters > big->stride * big->n_clusters)) big = &L;
+            if (L.n_clusters > 1 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
         --big->n_clusters;
+    }
+    std::vector<size_t> arena_offs;                 // per launch: n_clusters offsets relative to its arena_off
+    std::vector<int> counters(launches.size());
+    std::vector<size_t> offs_first(launches.size());
+    for (size_t li = 0; li < launches.size(); ++li) {
+        const Launch& L = launches[li];
+        offs_first[li] = arena_offs.size();
+        size_t b = 0;
+        for (int i = 0; i < L.n_clusters; ++i) {
+            arena_offs.push_back(b);
+            b += L.ncta == 0 ? L.stride : ((tb_bytes[L.ids[i]] + 255) & ~(size_t)255);
+        }
+        counters[li] = L.ncta == 0 ? 0 : L.n_clusters;       // clusters start with jobs 0..n-1
     }
     for (const Launch& L : launches)
         if (L.ncta == 0) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)L.n_clusters);
@@ -285,6 +307,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_runs.reserve((size_t)nj * kSigCap));
     CK(ctx->d_order.reserve(nj));
     CK(ctx->d_counter.reserve(launches.size()));
+    CK(ctx->d_aoff.reserve(arena_offs.size()));
     CK(ctx->d_arena.reserve(arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
     CK(ctx->h_outs.reserve(nj));
@@ -296,7 +319,8 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(cudaMemcpyAsync(ctx->d_raw.p, ctx->h_raw.p, raw_bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KswJob) * nj, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int) * launches.size(), s));
+    CK(cudaMemcpyAsync(ctx->d_counter.p, counters.data(), sizeof(int) * launches.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_aoff.p, arena_offs.data(), sizeof(size_t) * arena_offs.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->d_outs.p, 0, sizeof(KswOut) * nj, s));
     CK(cudaEventRecord(ctx->ev[1], s));
     launch_pack(ctx->d_jobs.p, nj, ctx->d_raw.p, ctx->d_subject.p, ctx->d_pool.p, s);
@@ -309,8 +333,8 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         CK(cudaStreamWaitEvent(ls, ctx->ev[2], 0));
         if (L.ncta > 0)
             CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
-                          ctx->d_pool.p, ctx->d_arena.p + L.arena_off, L.stride, ctx->d_cigar.p, ctx->d_runs.p,
-                          ctx->d_outs.p, ctx->d_counter.p + li, ls));
+                          ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
+                          ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls));
         else {
             launch_ksw_wide(L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
                             ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
