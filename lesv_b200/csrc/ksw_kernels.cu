@@ -326,7 +326,33 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool kCluster, bool kBarrier>
+// kSync selects how a row's "column 15 of my left neighbour, one row earlier" dependency is honoured
+// across warps:  kSyncBar  = one CTA barrier per anti-diagonal;
+//                kSyncMbar = split-phase barrier on two mbarriers: a warp ARRIVES when its row is
+//                            done and only WAITS (hardware sleep, no polling) right before it needs
+//                            the neighbour's value in the next row, so the tail of row r overlaps
+//                            the head of row r+1;
+//                kSyncRing = tagged slots polled by the consumer (what clusters use across CTAs).
+enum { kSyncRing = 0, kSyncBar = 1, kSyncMbar = 2 };
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_LOOP;\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+
+template <bool kCluster, int kSync>
 __global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
@@ -337,6 +363,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     extern __shared__ uint32_t seq_s[];
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
+    __shared__ __align__(8) uint64_t row_bar[2];
+    constexpr bool kBarrier = kSync != kSyncRing;       // slots need no tags / flow control
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
     // The queue is sorted by decreasing traceback size and cluster i starts with job i, so the arena
@@ -376,6 +404,14 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
 
         // this alignment uses the first NT threads of every CTA (the launch is sized for its tier)
         const int NT = job.nt, NW = NT >> 5, NTT = NT * (int)ncta;
+        if (kSync == kSyncMbar) {
+            if (tid == 0) {
+                mbar_init(smem_addr(&row_bar[0]), (uint32_t)NW);
+                mbar_init(smem_addr(&row_bar[1]), (uint32_t)NW);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+        }
         // ring endpoints of this thread (only lane 0 / lane 31 use them): my warp's inbox and where
         // my consumed-rows counter lives; the inbox I publish into and the counter I watch
         uint32_t in_addr = smem_addr(&ps.inbox[warp][0]);
@@ -396,7 +432,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         ThreadCtx c;
         thread_ctx_reset(c, (int)rank * NT + tid);
         Carry prev_out = carry_init();
-        const int nrow = (kBarrier || warp < NW) ? qlen + tlen - 1 : 0;     // warps beyond NT sit this alignment out
+        const int nrow = (kSync == kSyncBar || warp < NW) ? qlen + tlen - 1 : 0;   // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
         for (int r = 0; r < nrow; ++r) {
             Carry cin;
@@ -408,6 +444,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                 fetched = true;
                 if (r == 0) return v;
                 const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                if (kSync == kSyncMbar)      // every warp has finished row r-1 once this phase completes
+                    mbar_wait(smem_addr(&row_bar[(r - 1) & 1]), (uint32_t)(((r - 1) >> 1) & 1));
                 if (kBarrier) { ld_slot<kCluster>(slot, v.xv, v.x2); return v; }
                 while (ld_slot<kCluster>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
                 st_word<kCluster>(cons_addr, (uint32_t)r);
@@ -423,14 +461,18 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                     make_uint4(tb[0], tb[1], tb[2], tb[3]);
                 prev_out = cout;
             }
-            if (!kBarrier && lane == 0 && !fetched) consume();          // flow control only
+            if (kSync != kSyncBar && lane == 0 && !fetched) consume();  // flow control only
             if (lane == 31 && warp < NW) {                             // publish row r
                 if (!kBarrier && r >= kRingD)
                     while ((int)ld_word<kCluster>(watch_addr) < r - kRingD + 1) { }
                 const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
                 st_slot<kCluster>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
             }
-            if (kBarrier) __syncthreads(); else __syncwarp();
+            if (kSync == kSyncBar) __syncthreads();
+            else {
+                __syncwarp();
+                if (kSync == kSyncMbar && lane == 0) mbar_arrive(smem_addr(&row_bar[r & 1]));
+            }
         }
         __syncthreads();
         if (kCluster) { __threadfence(); cluster_sync_all(); }
@@ -570,21 +612,22 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     // sleep); the tagged-slot ring is what clusters need (no barrier spans CTAs cheaply) and can be
     // forced for single CTAs with LESV_KSW_RING=1 -- measured slower there: polling lanes burn issue
     // slots of the ALU-bound SMSPs (profiles/ksw_r1_notes.md).
-    static const bool barrier_mode = !(getenv("LESV_KSW_RING") && atoi(getenv("LESV_KSW_RING")));
+    static const int sync_mode = getenv("LESV_KSW_SYNC") ? atoi(getenv("LESV_KSW_SYNC")) : kSyncBar;
     if (ncta <= 1) {
-        if (barrier_mode) {
-            cudaFuncSetAttribute(ksw_dp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            ksw_dp_kernel<false, true><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                                                    d_cigar, d_runs, d_out, d_counter);
-        } else {
-            cudaFuncSetAttribute(ksw_dp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            ksw_dp_kernel<false, false><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                                                     d_cigar, d_runs, d_out, d_counter);
-        }
+#define LESV_LAUNCH1(MODE)                                                                                         \
+    do {                                                                                                           \
+        cudaFuncSetAttribute(ksw_dp_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ksw_dp_kernel<false, MODE><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,          \
+                                                                arena_stride, d_cigar, d_runs, d_out, d_counter);  \
+    } while (0)
+        if (sync_mode == kSyncMbar) LESV_LAUNCH1(kSyncMbar);
+        else if (sync_mode == kSyncRing) LESV_LAUNCH1(kSyncRing);
+        else LESV_LAUNCH1(kSyncBar);
+#undef LESV_LAUNCH1
         return cudaGetLastError();
     }
-    cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
     cfg.blockDim = dim3((unsigned)nt);
@@ -594,7 +637,7 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true, false>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true, kSyncRing>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
 }
 
@@ -602,8 +645,8 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
-    cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
@@ -611,7 +654,7 @@ int ksw_max_clusters(int nt, int ncta, size_t smem)
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true, kSyncRing>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
