@@ -128,6 +128,36 @@ int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
                         const char* trf_mask,
                         lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs);
 
+/* ---- qx2svr: align_and_refine_subseq_with_ksw in batch form -----------------------------------
+ * Stands in for
+ *   BOOL align_and_refine_subseq_with_ksw(RawReadReader* query_reader, RawReadReader* subject_reader,
+ *            HbnTracebackData*, const int max_dist, int query_gid, int query_dir, int query_from,
+ *            int query_to, int subject_gid, int subject_from, int subject_to, SubseqAlignResult*)
+ *                                                       app/necat2sv/align_subseqs.c:192-342
+ * i.e. extract both sub-sequences, nw_ksw2_extd2 with band max_dist (< 0: the longer length), one
+ * retry with the longer length if the band was cut and max_dist < KSW_MAX_BW (:233-277),
+ * truncate_align_bad_ends, the 0.8-coverage test (:307) and the two identity figures.  Called by
+ * calc_m4_eff_perc_identity (find_sv_reads.c:130-164) and s_chain_dual_m4s (:341-430).
+ */
+typedef struct {
+    int query_id, query_dir;          /* query_from/query_to are coordinates on strand query_dir */
+    int query_from, query_to, query_size;
+    size_t subject_seq_offset;        /* CSeqInfo.seq_offset of the contig */
+    int subject_from, subject_to;
+    int max_dist;
+} lesvgpu_refine_job;
+
+typedef struct {
+    int ok;                           /* the function's BOOL */
+    int qb, qe, sb, se;               /* SubseqAlignResult.qb.. (offsets already added back) */
+    int mat, len;                     /* perc_identity = 100.0*mat/len; dist = len-mat; score = 8*len-mat */
+    int eff_mat, eff_len;             /* eff_perc_identity = 100.0*eff_mat/eff_len */
+    int band;
+} lesvgpu_refine_result;
+
+int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
+                               const lesvgpu_refine_job* jobs, int n, lesvgpu_refine_result* results);
+
 /* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
  * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */
 int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* ok);

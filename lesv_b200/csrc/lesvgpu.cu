@@ -521,3 +521,69 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
     if (n_sigs) *n_sigs = (int)ctx->sigs.size();
     return LESVGPU_OK;
 }
+
+extern "C" int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
+                                          const lesvgpu_refine_job* rj, int n, lesvgpu_refine_result* results)
+{
+    if (!ctx || n < 0 || (n && (!rj || !results || !query_pac || !query_read_offset))) return LESVGPU_E_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
+    if (!ctx->subject_bytes) { ctx->err = "lesvgpu_subject_load has not been called"; return LESVGPU_E_ARG; }
+    ctx->timing = lesvgpu_timing{};
+    constexpr int kKswMaxBw = 30000;                      // KSW_MAX_BW, algo/ksw2_wrapper.h:10
+    std::vector<KswJob> jobs;
+    std::vector<int> job_idx;
+    std::vector<size_t> src_byte, dst_byte, nbytes;
+    size_t raw_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        lesvgpu_refine_result& R = results[i];
+        memset(&R, 0, sizeof R);
+        const lesvgpu_refine_job& A = rj[i];
+        const int qn = A.query_to - A.query_from, sn = A.subject_to - A.subject_from;
+        if (qn <= 0 || sn <= 0 || A.query_from < 0 || A.query_to > A.query_size || A.subject_from < 0) {
+            ctx->err = "refine job range outside its sequence"; return LESVGPU_E_ARG;
+        }
+        const int longest = qn > sn ? qn : sn;
+        int band = A.max_dist < 0 ? longest : A.max_dist;                 // align_subseqs.c:233
+        int w = effective_band(qn, sn, band);                             // ksw2_wrapper.c:121
+        if (!band_reaches_end(qn, sn, w)) {
+            if (band < kKswMaxBw && band < longest) { band = longest; w = effective_band(qn, sn, band); }   // :255
+            if (!band_reaches_end(qn, sn, w)) continue;                   // "ksw fail"
+        }
+        R.band = w;
+        // forward-strand range of the read that strand coordinates [from, to) denote
+        const int ffrom = A.query_dir ? A.query_size - A.query_to : A.query_from;
+        if (!query_read_offset[A.query_id]) { ctx->err = "read not loaded (raw_read_offset_array == 0)"; return LESVGPU_E_ARG; }
+        const size_t res0 = query_read_offset[A.query_id] - 1 + (size_t)ffrom;
+        src_byte.push_back(res0 >> 2);
+        nbytes.push_back(((res0 + (size_t)qn - 1) >> 2) - (res0 >> 2) + 1);
+        dst_byte.push_back(raw_bytes);
+        KswJob J;
+        memset(&J, 0, sizeof J);
+        J.qlen = qn; J.tlen = sn; J.w = w;
+        J.src = 1; J.qdir = A.query_dir;
+        J.seq_off_q = raw_bytes * 4 + (res0 & 3);
+        J.seq_off_t = A.subject_seq_offset + (size_t)A.subject_from;
+        if (((J.seq_off_t + (size_t)sn + 3) >> 2) > ctx->subject_bytes) { ctx->err = "subject range outside the loaded .pac"; return LESVGPU_E_ARG; }
+        raw_bytes += nbytes.back();
+        jobs.push_back(J); job_idx.push_back(i);
+    }
+    const int nj = (int)jobs.size();
+    if (nj == 0) return LESVGPU_OK;
+    CK(ctx->h_raw.reserve(raw_bytes));
+    for (int k = 0; k < nj; ++k) memcpy(ctx->h_raw.p + dst_byte[k], query_pac + src_byte[k], nbytes[k]);
+    const int rc = run_jobs(ctx, jobs, raw_bytes, false, false);
+    if (rc != LESVGPU_OK) return rc;
+    for (int k = 0; k < nj; ++k) {
+        const lesvgpu_refine_job& A = rj[job_idx[k]];
+        lesvgpu_refine_result& R = results[job_idx[k]];
+        const KswOut& O = ctx->h_outs.p[k];
+        if (O.status != 1 || O.n_cigar <= 0 || !O.trunc_ok) continue;    // ksw / truncate fail
+        const int x = O.qe - O.qb, y = O.se - O.sb;
+        if (x < jobs[k].qlen * 0.8 && y < jobs[k].tlen * 0.8) continue;   // :307 "align too short"
+        R.ok = 1;
+        R.qb = O.qb + A.query_from; R.qe = O.qe + A.query_from;
+        R.sb = O.sb + A.subject_from; R.se = O.se + A.subject_from;
+        R.mat = O.trim_mat; R.len = O.trim_len; R.eff_mat = O.eff_mat; R.eff_len = O.eff_len;
+    }
+    return LESVGPU_OK;
+}

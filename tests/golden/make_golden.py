@@ -5,7 +5,7 @@
 
   ksw_kat.json          ksw_extd2_sse (flag 0, zdrop -1) CIGAR + score for a few (query, target, band)
   svsig_small/          a complete tiny run of  qx2splitseq -> qx2map -> qx2m4x -> qx2svr -> qx2svsig :
-      db/               packed database written by qx2map (query.* / subject.*)
+      db/               packed database written by qx2map (query.* / subject.*) + backup_results/*.m4x (qx2m4x)
       map.m4            qx2map output (sorted: line order is thread-schedule dependent)
       svr/              qx2svr output (Q*.sv_read, subject_*.sv_read)
       svsig/            qx2svsig output (subject_*.sv_signature)
@@ -74,7 +74,10 @@ def main():
     # keep what the tests need, drop bulky intermediates
     for name in ("split.fa", "log.txt"):
         os.remove(os.path.join(work, name))
-    shutil.rmtree(os.path.join(work, "db", "backup_results"), ignore_errors=True)
+    br = os.path.join(work, "db", "backup_results")
+    for f in os.listdir(br):
+        if not f.endswith(".m4x"):
+            os.remove(os.path.join(br, f))
     for f in os.listdir(os.path.join(work, "db")):
         if f.endswith(".txt") or f.endswith("_is_built"):
             os.remove(os.path.join(work, "db", f))

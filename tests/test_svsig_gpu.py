@@ -76,3 +76,66 @@ def test_binary_dropin_against_fresh_reference_run(tmp_path):
     subprocess.run([BIN, out, os.path.join(work, "svr"), os.path.join(work, "db"), "40", "4"], check=True)
     n = _compare_dirs(os.path.join(work, "svsig"), out)
     assert n >= 10
+
+
+# ---- qx2svr ------------------------------------------------------------------------------------
+SVR_BIN = os.path.join(H.ROOT, "lesv_b200", "bin", "qx2svr")
+
+
+def _read_lines(path):
+    with open(path) as f:
+        return [l.rstrip("\n") for l in f]
+
+
+def _compare_svr(ref_dir, got_dir):
+    n = 0
+    for f in sorted(os.listdir(ref_dir)):
+        if f.startswith("Q") and f.endswith(".sv_read"):            # thread order in the reference: multiset
+            assert sorted(_read_lines(os.path.join(ref_dir, f))) == sorted(_read_lines(os.path.join(got_dir, f))), f
+            n += len(_read_lines(os.path.join(ref_dir, f)))
+        elif f.startswith("subject_") and f.endswith(".sv_read"):    # ordered by query id: exact
+            assert _read_lines(os.path.join(ref_dir, f)) == _read_lines(os.path.join(got_dir, f)), f
+    assert _read_lines(os.path.join(ref_dir, "subject_sv_read_file_count")) == \
+        _read_lines(os.path.join(got_dir, "subject_sv_read_file_count"))
+    return n
+
+
+def test_svr_binary_dropin_on_golden(tmp_path):
+    out = tmp_path / "svr"
+    subprocess.run([SVR_BIN, str(out), os.path.join(GOLD, "db"), "3000", "70.0", "300", "4"], check=True)
+    assert _compare_svr(os.path.join(GOLD, "svr"), str(out)) >= 50
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2svr")), reason="oracle/_ref not built")
+def test_svr_and_svsig_dropin_on_repeats_and_large_svs(tmp_path):
+    """A reference with a diverged 20 kb duplication (several complete HSPs per read -> the ksw
+    re-scoring branch) and 2-6 kb deletions/insertions (split HSPs -> the dual-chaining branch)."""
+    sys.path.insert(0, os.path.join(H.ROOT, "tests", "golden"))
+    import make_golden
+    from lesv_b200 import synth
+    rng = np.random.default_rng(99)
+    ref = synth.random_codes(300000, rng)
+    ref[200000:220000] = synth.mutate(ref[50000:70000], 0.03, rng)[:20000]
+    sample = ref.copy()
+    pieces, prev = [], 0
+    for k, pos in enumerate(range(30000, 290000, 37000)):
+        size = int(rng.integers(2000, 6000))
+        pieces.append(sample[prev:pos])
+        if k % 2 == 0:
+            pieces.append(synth.random_codes(size, rng)); prev = pos
+        else:
+            prev = pos + size
+    pieces.append(sample[prev:])
+    sample = np.concatenate(pieces)
+    reads = synth.simulate_reads(sample, 260, 9000, np.random.default_rng(7), 0.10, 0.14)
+    work = str(tmp_path / "w")
+    os.makedirs(work)
+    synth.write_fasta(os.path.join(work, "ref.fa"), ["chrA"], [ref], width=80)
+    synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
+    make_golden.reference_pipeline(work, threads=os.cpu_count() or 4)
+    svr_out = os.path.join(work, "svr_gpu")
+    subprocess.run([SVR_BIN, svr_out, os.path.join(work, "db"), "3000", "70.0", "300", "4"], check=True)
+    assert _compare_svr(os.path.join(work, "svr"), svr_out) >= 100
+    sig_out = os.path.join(work, "svsig_gpu")
+    subprocess.run([BIN, sig_out, svr_out, os.path.join(work, "db"), "40", "4"], check=True)
+    assert _compare_dirs(os.path.join(work, "svsig"), sig_out) >= 20
