@@ -115,7 +115,8 @@ def test_svr_and_svsig_dropin_on_repeats_and_large_svs(tmp_path):
     from lesv_b200 import synth
     rng = np.random.default_rng(99)
     ref = synth.random_codes(300000, rng)
-    ref[200000:220000] = synth.mutate(ref[50000:70000], 0.03, rng)[:20000]
+    dup = synth.mutate(ref[50000:70000], 0.03, rng)
+    ref[200000:200000 + len(dup)] = dup
     sample = ref.copy()
     pieces, prev = [], 0
     for k, pos in enumerate(range(30000, 290000, 37000)):
