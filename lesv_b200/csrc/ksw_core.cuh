@@ -149,14 +149,20 @@ KSW_HD int tb_byte_pos(int c) { return 4 * ((c & 7) >> 1) + 2 * (c & 1) + (c >> 
 
 // ---- per-block register state -----------------------------------------------------------------
 struct BlockState {
-    uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8], S[8];    // X.. = AX.. of the header comment
+    uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8];          // X.. = AX.. of the header comment
+    // The score byte s[t] of a column is one of three values -- match, mismatch, or the calloc()ed 0
+    // of a column never written yet -- so the block keeps 2 bits per column (bit 2c: mismatch, bit
+    // 2c+1: never written) and rebuilds the S lanes of a row from them.  Stale bytes (columns of the
+    // 16-aligned band outside [st0, wr]) are simply bits that were not refreshed.
+    uint32_t sbits;
     KSW_HD void init()
     {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             U[j] = kInitU; V[j] = kInitU; X[j] = 0u; Y[j] = 0u;
-            X2[j] = 0u; Y2[j] = 0u; S[j] = kInitS;
+            X2[j] = 0u; Y2[j] = 0u;
         }
+        sbits = 0xAAAAAAAAu;
     }
 };
 
@@ -177,13 +183,6 @@ KSW_HD Carry carry_left_boundary(int r)     // column 0, :148-151
     return c;
 }
 
-// expand bit (7-sh) .. of a 16-bit column mask to a lane mask for pair j (columns j, j+8)
-KSW_HD uint32_t lane_mask(uint32_t m16, int j)
-{
-    // bit j -> low lane, bit j+8 -> high lane
-    uint32_t t = m16 << (7 - j);             // bit j at bit 7, bit j+8 at bit 15
-    return prmt(t, 0, 0x9988);               // replicate the sign of byte 0 / byte 1
-}
 
 // mismatch bits of a block: bit 2c set iff target column c differs from the query base under it
 KSW_HD uint32_t mismatch_bits(uint32_t tword, uint32_t qword)
@@ -192,18 +191,19 @@ KSW_HD uint32_t mismatch_bits(uint32_t tword, uint32_t qword)
     return (x | (x >> 1)) & 0x55555555u;
 }
 
-// Refresh S^ for the columns in fresh16 (bit c = column c gets a new score this row).
-template <bool kAllFresh>
-KSW_HD void update_scores(BlockState& b, uint32_t mis, uint32_t fresh16)
+// S lanes of a row from the block's score bits.
+KSW_HD void score_lanes(uint32_t sbits, uint32_t S[8])
 {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        uint32_t e = (mis >> (2 * j)) & 0x00010001u;
-        uint32_t s = e * kSStep + kSMatch;                    // per lane: match or mismatch
-        if (kAllFresh) b.S[j] = s;
-        else {
-            uint32_t m = lane_mask(fresh16, j);
-            b.S[j] = (s & m) | (b.S[j] & ~m);
+        const uint32_t e = (sbits >> (2 * j)) & 0x00010001u;
+        S[j] = e * kSStep + kSMatch;                          // per lane: match or mismatch
+    }
+    if (sbits & 0xAAAAAAAAu) {                                // leading-edge block only: columns still at calloc's 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t z = (sbits >> (2 * j + 1)) & 0x00010001u;
+            S[j] -= z * (uint32_t)((kSMatch - kInitS) & 0xFFFF);    // match score -> 0, no borrow between lanes
         }
     }
 }
@@ -214,7 +214,7 @@ KSW_HD void update_scores(BlockState& b, uint32_t mis, uint32_t fresh16)
 // return `cout` holds this row's values of column 15 and tb[0..3] the 16 traceback bytes (column
 // order given by tb_byte_pos).
 template <class CarryFn>
-KSW_HD void block_row(BlockState& b, CarryFn&& carry, Carry& cout, uint32_t tb[4])
+KSW_HD void block_row(BlockState& b, const uint32_t S[8], CarryFn&& carry, Carry& cout, uint32_t tb[4])
 {
     // previous-row values of column 7 = left neighbours of column 8 (high lane of pair 0)
     const uint32_t x7 = b.X[7], v7 = b.V[7], x27 = b.X2[7];
@@ -234,7 +234,7 @@ KSW_HD void block_row(BlockState& b, CarryFn&& carry, Carry& cout, uint32_t tb[4
         const uint32_t u0 = b.U[j];
         const uint32_t ka = vadd2(x1, vadd2(v1, kVa)), kb = vadd2(b.Y[j], vadd2(u0, kUa));
         const uint32_t ka2 = vadd2(x21, vadd2(v1, kVb)), kb2 = vadd2(b.Y2[j], vadd2(u0, kUb));
-        uint32_t k = vmax3(b.S[j], ka, kb);
+        uint32_t k = vmax3(S[j], ka, kb);
         k = vmax3(k, ka2, kb2);
         kk[j] = k;
         const uint32_t zc = vmin2(k | 0x00FF00FFu, kClampZ);
@@ -343,19 +343,23 @@ KSW_HD uint32_t query_window(ThreadCtx& c, const uint32_t* qrp, int qlen, int r,
 // owner of block B-1 published for row r-1 (called at most once, and only if needed).
 // Returns true if the thread computed DP cells this row (then cout/tb are valid and the 16 bytes
 // belong at byte offset c.tb_off of traceback row r).
-template <class CarryFn>
+// kEager: the neighbour's value is already at hand (the previous row ended with a CTA barrier), so
+// `carry()` is evaluated up front and the band-edge cases overwrite it inside the slow path; the
+// block update then sees one plain value and no per-row policy select.
+template <bool kEager = false, class CarryFn>
 KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w, int tb_blocks,
                             const uint32_t* tp, const uint32_t* qrp,
                             CarryFn&& carry, Carry& cout, uint32_t tb[4])
 {
+    Carry eager = carry_init();
+    if (kEager) eager = carry();
     // carry policy of this row: 0 = take what the left neighbour published, 1 = matrix edge
     // (column 0), 2 = the left block was not computed one row earlier (initial values)
     int policy = 0;
+    uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
+    bool pre_block = false;
     // fast path: the block is strictly inside the band, nothing about the band edges matters
-    if (r >= c.fast_lo && r <= c.fast_hi) {
-        const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
-        update_scores<true>(c.b, mismatch_bits(c.tword, qword), 0xFFFF);
-    } else {
+    if (r < c.fast_lo || r > c.fast_hi) {
         const RowGeom g = row_geom(r, qlen, tlen, w);
         const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
         while (c.cand < bst) c.cand += nt;  // the band left this thread's block behind: take the next one
@@ -379,38 +383,42 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                 c.fast_lo = lo; c.fast_hi = h1 < h2 ? h1 : h2;
             }
         }
-        const uint32_t qword = query_window(c, qrp, qlen, r, B);
-        const uint32_t mis = mismatch_bits(c.tword, qword);
         const int c0 = 16 * B;
-        if (c0 >= g.st0 && c0 + 15 <= g.en0) update_scores<true>(c.b, mis, 0xFFFF);
-        else {
-            // fresh columns: st0 <= c0 + col <= wr
-            int lo = g.st0 - c0, hi = g.wr - c0;
-            lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
-            uint32_t fresh = lo <= hi ? ((0xFFFFu >> (15 - hi)) & (0xFFFFu << lo)) & 0xFFFFu : 0u;
-            update_scores<false>(c.b, mis, fresh);
-        }
-        if (B > ben) return false;          // pre-block: only its score bytes exist so far
-        if ((r >> 4) == B) {                // top row of the matrix reaches column r: :152-155
-            const int col = r & 15, j = col & 7;
-            const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
-            const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
+        // fresh columns: st0 <= c0 + col <= wr
+        int lo = g.st0 - c0, hi = g.wr - c0;
+        lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
+        fm = lo <= hi ? (0xFFFFFFFFu >> (30 - 2 * hi)) & (0xFFFFFFFFu << (2 * lo)) : 0u;
+        pre_block = B > ben;                // pre-block: only its score bytes exist so far
+        if (!pre_block) {
+            if ((r >> 4) == B) {            // top row of the matrix reaches column r: :152-155
+                const int col = r & 15, j = col & 7;
+                const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
+                const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-                if (jj == j) {
-                    c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
-                    c.b.Y[jj] &= ~m;        // y = -(q+e), y2 = -(q2+e2)
-                    c.b.Y2[jj] &= ~m;
-                }
+                for (int jj = 0; jj < 8; ++jj)
+                    if (jj == j) {
+                        c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
+                        c.b.Y[jj] &= ~m;    // y = -(q+e), y2 = -(q2+e2)
+                        c.b.Y2[jj] &= ~m;
+                    }
+            }
+            // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
+            if (B == 0) policy = 1;
+            else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
+            if (kEager && policy) eager = policy == 1 ? carry_left_boundary(r) : carry_init();
         }
-        // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
-        if (B == 0) policy = 1;
-        else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
     }
-    block_row(c.b, [&]() -> Carry {
-        if (policy == 0) return carry();
-        return policy == 1 ? carry_left_boundary(r) : carry_init();
-    }, cout, tb);
+    const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
+    c.b.sbits = (mismatch_bits(c.tword, qword) & fm) | (c.b.sbits & ~fm);
+    if (pre_block) return false;
+    uint32_t S[8];
+    score_lanes(c.b.sbits, S);
+    if (kEager) block_row(c.b, S, [&]() -> Carry { return eager; }, cout, tb);
+    else
+        block_row(c.b, S, [&]() -> Carry {
+            if (policy == 0) return carry();
+            return policy == 1 ? carry_left_boundary(r) : carry_init();
+        }, cout, tb);
     return true;
 }
 

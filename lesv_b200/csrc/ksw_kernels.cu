@@ -333,7 +333,13 @@ __device__ __forceinline__ void cluster_sync_all()
 //                            the neighbour's value in the next row, so the tail of row r overlaps
 //                            the head of row r+1;
 //                kSyncRing = tagged slots polled by the consumer (what clusters use across CTAs).
-enum { kSyncRing = 0, kSyncBar = 1, kSyncMbar = 2 };
+//                kSyncSkew = the 32-block group g of the band runs kSkewK rows BEHIND group g-1, so
+//                            the carry a warp needs was published at least one barrier ago: warps
+//                            exchange column-15 values through a ring of 4*kSkewK slots and meet at
+//                            a CTA barrier only every kSkewK rows (tests/emul runs this schedule
+//                            with the warps of an interval in random order).
+enum { kSyncRing = 0, kSyncBar = 1, kSyncMbar = 2, kSyncSkew = 3 };
+constexpr int kSkewMaxK = 16;
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
 {
@@ -352,8 +358,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
         "@!p bra WAIT_LOOP;\n\t}" ::"r"(addr), "r"(parity) : "memory");
 }
 
-template <bool kCluster, int kSync>
-__global__ void __launch_bounds__(kMaxNT)
+template <bool kCluster, int kSync, int kSkewK = 8, int kBound = kMaxNT>
+__global__ void __launch_bounds__(kBound)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
               const size_t* __restrict__ arena_off,
@@ -364,6 +370,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
     __shared__ __align__(8) uint64_t row_bar[2];
+    __shared__ uint2 carry_sh[2][kMaxWarps];      // kSyncBar: column-15 values by row parity and consumer warp
+    __shared__ uint2 skew_ring[kSync == kSyncSkew ? kMaxWarps : 1][kSync == kSyncSkew ? 4 * kSkewK : 1];
     constexpr bool kBarrier = kSync != kSyncRing;       // slots need no tags / flow control
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
@@ -434,6 +442,70 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         Carry prev_out = carry_init();
         const int nrow = (kSync == kSyncBar || warp < NW) ? qlen + tlen - 1 : 0;   // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
+        if (kSync == kSyncSkew) {
+            constexpr int R = 4 * kSkewK;
+            const int maxB = ((tlen - 1) >> 4) + 1;              // right-most block that ever exists
+            const int nrow_all = qlen + tlen - 1;
+            const int nticks = nrow_all + kSkewK * (maxB >> 5);
+            const uint2* inbox = skew_ring[warp < NW ? warp : 0];
+            uint2* outbox = skew_ring[warp + 1 < NW ? warp + 1 : 0];
+            int r = -kSkewK * (c.cand >> 5);                     // this thread's anti-diagonal at tick 0
+            for (int s = 0; s < nticks; ++s, ++r) {
+                Carry cin;
+                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                if (warp < NW) {
+                    if (r < c.fast_lo || r > c.fast_hi)          // the band left my block behind: take the next one
+                        while (c.cand <= maxB &&
+                               (r >= nrow_all || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
+                            c.cand += NT;
+                            r = s - kSkewK * (c.cand >> 5);
+                        }
+                    if (r >= 0 && r < nrow_all && c.cand <= maxB) {
+                        Carry cout;
+                        uint32_t tb[4];
+                        const int rc = r;
+                        if (thread_row_step(c, NT, rc, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                            [&]() -> Carry {
+                                                if (lane) return cin;
+                                                const uint2 v = inbox[(rc - 1) & (R - 1)];
+                                                Carry x; x.xv = v.x; x.x2 = v.y; return x;
+                                            }, cout, tb)) {
+                            *reinterpret_cast<uint4*>(arena + (size_t)rc * prow + (size_t)c.tb_off) =
+                                make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                            prev_out = cout;
+                            if (lane == 31) outbox[rc & (R - 1)] = make_uint2(cout.xv, cout.x2);
+                        }
+                    }
+                }
+                if ((s & (kSkewK - 1)) == kSkewK - 1) __syncthreads();
+            }
+        } else if (kSync == kSyncBar && !kCluster) {
+            // Lean barrier loop: lane 31 leaves its column-15 values in carry_sh[row parity][next warp],
+            // every lane of the next warp reads them back (one broadcast LDS) at the top of the next
+            // row and lane 0 keeps them -- no divergent single-lane fetch in front of pair 0.
+            const int wnext = warp + 1 < NW ? warp + 1 : 0;
+            uint8_t* rowp = arena;
+            const int nrow_all = qlen + tlen - 1;
+            for (int r = 0; r < nrow_all; ++r, rowp += prow) {
+                if (warp < NW) {
+                    const uint2 nb = carry_sh[(r + 1) & 1][warp];
+                    Carry cin;
+                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                    if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    Carry cout;
+                    uint32_t tb[4];
+                    if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                              [&]() -> Carry { return cin; }, cout, tb)) {
+                        *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                        prev_out = cout;
+                    }
+                    if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
+                }
+                __syncthreads();
+            }
+        } else
         for (int r = 0; r < nrow; ++r) {
             Carry cin;
             cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
@@ -602,7 +674,8 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
     return (size_t)(tp_words(max_tlen) + qrp_words(max_qlen)) * sizeof(uint32_t);
 }
 
-int ksw_ctas_per_sm(int nt) { int n = 640 / nt; return n < 1 ? 1 : n > 8 ? 8 : n; }
+// 88 registers per thread (ptxas: 86) -> 744 threads per SM
+int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 11 ? 11 : n; }
 
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* arena_stride, uint32_t* d_cigar,
@@ -620,8 +693,29 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
         ksw_dp_kernel<false, MODE><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,          \
                                                                 arena_stride, d_cigar, d_runs, d_out, d_counter);  \
     } while (0)
-        if (sync_mode == kSyncMbar) LESV_LAUNCH1(kSyncMbar);
+        static const int skew_k = getenv("LESV_KSW_SKEW") ? atoi(getenv("LESV_KSW_SKEW")) : 8;
+        if (sync_mode == kSyncSkew) {
+#define LESV_LAUNCHS(KK)                                                                                              \
+    do {                                                                                                              \
+        cudaFuncSetAttribute(ksw_dp_kernel<false, kSyncSkew, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ksw_dp_kernel<false, kSyncSkew, KK><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,    \
+                                                                         arena_stride, d_cigar, d_runs, d_out, d_counter); \
+    } while (0)
+            if (skew_k <= 2) LESV_LAUNCHS(2);
+            else if (skew_k <= 4) LESV_LAUNCHS(4);
+            else if (skew_k <= 8) LESV_LAUNCHS(8);
+            else LESV_LAUNCHS(16);
+#undef LESV_LAUNCHS
+        }
+        else if (sync_mode == kSyncMbar) LESV_LAUNCH1(kSyncMbar);
         else if (sync_mode == kSyncRing) LESV_LAUNCH1(kSyncRing);
+        else if (nt <= 512 && getenv("LESV_KSW_512")) {     // measured slower (717 vs 745 GCUPS): off by default
+            // CTAs of <= 512 threads may use 128 registers per thread: room for the scheduler to
+            // interleave the eight independent pair updates of a row
+            cudaFuncSetAttribute(ksw_dp_kernel<false, kSyncBar, 8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ksw_dp_kernel<false, kSyncBar, 8, 512><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,
+                                                                                  arena_stride, d_cigar, d_runs, d_out, d_counter);
+        }
         else LESV_LAUNCH1(kSyncBar);
 #undef LESV_LAUNCH1
         return cudaGetLastError();

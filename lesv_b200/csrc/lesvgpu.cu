@@ -187,7 +187,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     // alignment actually uses of it.
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
-        static const int tiers[] = {64, 96, 128, 160, 320, 640};
+        static const int tiers[] = {64, 96, 128, 160, 320, 512, 640};
         if (wb <= 640) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};

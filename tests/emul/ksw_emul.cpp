@@ -21,7 +21,10 @@ static void pack_words(const uint8_t* s, int n, int reversed, std::vector<uint32
 }
 
 static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
-                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes);
+                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes,
+                     int skew_k = 0, unsigned seed = 0);
+static int g_eager = 0;     // 1: step with thread_row_step<true> (carry resolved up front, barrier-mode kernel)
+extern "C" void lesv_emul_set_eager(int on) { g_eager = on; }
 
 extern "C" int lesv_emul_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                    int w, int nt, uint32_t** cigar_out)
@@ -36,8 +39,20 @@ extern "C" int lesv_emul_ksw_extd2_tb(int qlen, const uint8_t* query, int tlen, 
     return emul_impl(qlen, query, tlen, target, w, nt, cigar_out, tb_out, tb_row_bytes);
 }
 
+// Skewed schedule (kSyncSkew of ksw_dp_kernel): the 32-block group g of the band runs skew_k rows
+// behind group g-1, warps exchange column-15 carries through a ring of 4*skew_k slots and meet at a
+// CTA barrier only every skew_k ticks.  Inside a barrier interval the warps are run one after the
+// other in a random order -- the most adversarial interleaving the barrier allows -- so a slot that
+// could be read before it is written, or overwritten before it is read, shows up as a wrong CIGAR.
+extern "C" int lesv_emul_ksw_extd2_skew(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                        int w, int nt, int skew_k, unsigned seed, uint32_t** cigar_out)
+{
+    return emul_impl(qlen, query, tlen, target, w, nt, cigar_out, nullptr, nullptr, skew_k, seed);
+}
+
 static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
-                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes)
+                     int w, int nt, uint32_t** cigar_out, uint8_t** tb_out, int* tb_row_bytes,
+                     int skew_k, unsigned seed)
 {
     *cigar_out = nullptr;
     if (qlen <= 0 || tlen <= 0) return 0;
@@ -55,14 +70,61 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
     for (int t = 0; t < nt; ++t) thread_ctx_reset(th[t], t);
     std::vector<Carry> pub(nt), pub_next(nt);
     for (auto& c : pub) c = carry_init();
+    if (skew_k > 0) {
+        if (nt % 32) return -3;
+        const int K = skew_k, R = 4 * K, NW = nt / 32;
+        for (int r = 0; r < (int)nrow; ++r) {
+            const RowGeom g = row_geom(r, qlen, tlen, w);
+            if ((g.wr >> 4) - (g.st0 >> 4) + 1 > nt) return -1;
+        }
+        const int maxB = ((tlen - 1) >> 4) + 1;
+        const int nticks = (int)nrow + K * (maxB >> 5);
+        std::vector<int> rr(nt);
+        std::vector<Carry> prev(nt, carry_init()), ring((size_t)NW * R, carry_init());
+        for (auto& c : ring) { c.xv = 0xDEADBEEFu; c.x2 = 0xDEADBEEFu; }
+        for (int t = 0; t < nt; ++t) rr[t] = -K * (th[t].cand >> 5);
+        std::vector<int> perm(NW);
+        for (int s0 = 0; s0 < nticks; s0 += K) {
+            for (int k = 0; k < NW; ++k) perm[k] = k;
+            for (int k = NW - 1; k > 0; --k) { seed = seed * 1664525u + 1013904223u; std::swap(perm[k], perm[(seed >> 8) % (k + 1)]); }
+            for (int wp : perm)
+                for (int s = s0; s < s0 + K && s < nticks; ++s) {
+                    Carry cin[32];
+                    for (int l = 1; l < 32; ++l) cin[l] = prev[wp * 32 + l - 1];
+                    for (int l = 0; l < 32; ++l) {
+                        const int tid = wp * 32 + l;
+                        ThreadCtx& c = th[tid];
+                        int& r = rr[tid];
+                        if (r < c.fast_lo || r > c.fast_hi)
+                            while (c.cand <= maxB && (r >= (int)nrow || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
+                                c.cand += nt; r = s - K * (c.cand >> 5);
+                            }
+                        if (r >= 0 && r < (int)nrow && c.cand <= maxB) {
+                            Carry cout; uint32_t tb[4];
+                            const int rcur = r;
+                            if (thread_row_step(c, nt, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(),
+                                                [&]() { return l ? cin[l] : ring[(size_t)wp * R + ((rcur - 1) & (R - 1))]; }, cout, tb)) {
+                                if (c.tb_off < 0 || c.tb_off >= (int)prow) return -2;
+                                memcpy(&p[(size_t)r * prow + (size_t)c.tb_off], tb, 16);
+                                prev[tid] = cout;
+                                if (l == 31) ring[(size_t)((wp + 1) % NW) * R + (r & (R - 1))] = cout;
+                            }
+                        }
+                        ++r;
+                    }
+                }
+        }
+    } else
     for (int r = 0; r < (int)nrow; ++r) {
         const RowGeom g = row_geom(r, qlen, tlen, w);
         if ((g.wr >> 4) - (g.st0 >> 4) + 1 > nt) return -1;      // window does not fit NT threads
         for (int tid = 0; tid < nt; ++tid) {
             Carry cout; uint32_t tb[4];
             const Carry cin = pub[(tid + nt - 1) % nt];
-            if (thread_row_step(th[tid], nt, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(),
-                                [&]() { return cin; }, cout, tb)) {
+            const bool did = g_eager
+                ? thread_row_step<true>(th[tid], nt, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(), [&]() { return cin; }, cout, tb)
+                : thread_row_step<false>(th[tid], nt, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(), [&]() { return cin; }, cout, tb);
+            if (did) {
                 if (th[tid].tb_off < 0 || th[tid].tb_off >= (int)prow) return -2;
                 memcpy(&p[(size_t)r * prow + (size_t)th[tid].tb_off], tb, 16);
                 pub_next[tid] = cout;

@@ -97,10 +97,22 @@ def ref_ksw(q, t, w):
     return out, ez.score
 
 
-def emul_ksw(q, t, w, nt):
+def emul_ksw(q, t, w, nt, eager=False):
     lib = emul()
+    lib.lesv_emul_set_eager(1 if eager else 0)
     cig = C.POINTER(C.c_uint32)()
     n = lib.lesv_emul_ksw_extd2(len(q), _ptr(q), len(t), _ptr(t), w, nt, C.byref(cig))
+    if n < 0:
+        return n
+    out = [cig[i] for i in range(n)]
+    _libc.free(cig)
+    return out
+
+
+def emul_ksw_skew(q, t, w, nt, k, seed):
+    lib = emul()
+    cig = C.POINTER(C.c_uint32)()
+    n = lib.lesv_emul_ksw_extd2_skew(len(q), _ptr(q), len(t), _ptr(t), w, nt, k, C.c_uint(seed), C.byref(cig))
     if n < 0:
         return n
     out = [cig[i] for i in range(n)]

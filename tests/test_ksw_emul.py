@@ -17,10 +17,29 @@ def test_emulated_kernel_cigar_equals_oracle(seed):
         need = H.min_threads(len(q), len(t), w)
         nt = max(need, int(rng.choice([need, need + 1, 64, 128])))
         a, _ = H.oracle_ksw(q, t, w)
-        b = H.emul_ksw(q, t, w, nt)
+        b = H.emul_ksw(q, t, w, nt, eager=bool(it & 1))     # both carry conventions of thread_row_step
         assert a == b, (it, len(q), len(t), w, nt)
         n += 1
     assert n > 800
+
+
+@pytest.mark.parametrize("k", [2, 8])
+def test_emulated_skewed_schedule_equals_oracle(k):
+    """kSyncSkew: warps `k` rows apart per 32-block group, a barrier only every k rows; the emulator
+    runs the warps of a barrier interval in random order (worst legal interleaving)."""
+    rng = np.random.default_rng(300 + k)
+    n = 0
+    for it in range(1200):
+        q, t, w = H.random_pair(rng, it, max_len=2500 if it % 7 == 0 else 700)
+        if not H.oracle_cells(len(q), len(t), w)[1]:
+            continue
+        need = (H.min_threads(len(q), len(t), w) + 31) // 32 * 32
+        nt = need + 32 * int(rng.integers(0, 2))
+        a, _ = H.oracle_ksw(q, t, w)
+        b = H.emul_ksw_skew(q, t, w, nt, k, it)
+        assert a == b, (it, len(q), len(t), w, nt)
+        n += 1
+    assert n > 600
 
 
 def test_emulated_kernel_traceback_bytes_equal_oracle():
