@@ -371,6 +371,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     __shared__ BtShared bt;
     __shared__ __align__(8) uint64_t row_bar[2];
     __shared__ uint2 carry_sh[2][kMaxWarps];      // kSyncBar: column-15 values by row parity and consumer warp
+    __shared__ uint2 cl_ring[kSync == kSyncSkew && kCluster ? 4 * kSkewK : 1];   // cluster skew: filled by the CTA to my left
     __shared__ uint2 skew_ring[kSync == kSyncSkew ? kMaxWarps : 1][kSync == kSyncSkew ? 4 * kSkewK : 1];
     constexpr bool kBarrier = kSync != kSyncRing;       // slots need no tags / flow control
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,7 +443,58 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         Carry prev_out = carry_init();
         const int nrow = (kSync == kSyncBar || warp < NW) ? qlen + tlen - 1 : 0;   // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
-        if (kSync == kSyncSkew) {
+        if (kSync == kSyncSkew && kCluster) {
+            // Cluster flavour of the skewed schedule: the groups are the CTAs.  Inside a CTA the lean
+            // barrier loop (one __syncthreads per tick); CTA k+1 works kSkewK rows behind CTA k, takes
+            // its left-edge carries from a ring the last warp of CTA k fills through DSMEM, and the
+            // cluster meets at a hardware cluster barrier only every kSkewK ticks.
+            constexpr int R = 4 * kSkewK;
+            const int maxB = ((tlen - 1) >> 4) + 1;
+            const int nrow_all = qlen + tlen - 1;
+            const int nticks = nrow_all + kSkewK * (maxB / NT);
+            const uint32_t ring_remote = map_rank(smem_addr(&cl_ring[0]), (rank + 1) % ncta);
+            int r = -kSkewK * (c.cand / NT);
+            for (int s = 0; s < nticks; ++s, ++r) {
+                if (warp < NW) {
+                    const uint2 nb = carry_sh[(s + 1) & 1][warp];
+                    Carry cin;
+                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                    if (r < c.fast_lo || r > c.fast_hi)
+                        while (c.cand <= maxB &&
+                               (r >= nrow_all || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
+                            c.cand += NTT;
+                            r = s - kSkewK * (c.cand / NT);
+                        }
+                    if (lane == 0) {
+                        if (warp == 0) {
+                            const volatile uint2* rp = &cl_ring[(r - 1) & (R - 1)];
+                            cin.xv = rp->x; cin.x2 = rp->y;
+                        } else { cin.xv = nb.x; cin.x2 = nb.y; }
+                    }
+                    bool did = false;
+                    Carry cout;
+                    uint32_t tb[4];
+                    if (r >= 0 && r < nrow_all && c.cand <= maxB)
+                        did = thread_row_step<true>(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                                    [&]() -> Carry { return cin; }, cout, tb);
+                    if (did) {
+                        *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
+                            make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                        prev_out = cout;
+                    }
+                    if (lane == 31) {
+                        if (warp == NW - 1) {
+                            if (did)
+                                asm volatile("st.volatile.shared::cluster.v2.u32 [%0], {%1, %2};" ::
+                                             "r"(ring_remote + (uint32_t)(r & (R - 1)) * 8u), "r"(cout.xv), "r"(cout.x2) : "memory");
+                        } else carry_sh[s & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
+                    }
+                }
+                __syncthreads();
+                if ((s & (kSkewK - 1)) == kSkewK - 1) cluster_sync_all();
+            }
+        } else if (kSync == kSyncSkew) {
             constexpr int R = 4 * kSkewK;
             const int maxB = ((tlen - 1) >> 4) + 1;              // right-most block that ever exists
             const int nrow_all = qlen + tlen - 1;
@@ -677,6 +729,20 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 // 88 registers per thread (ptxas: 86) -> 744 threads per SM
 int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 11 ? 11 : n; }
 
+// Cluster alignments: polled tagged-slot ring (551 GCUPS on 2-CTA clusters); LESV_KSW_CLUSTER_SKEW=1
+// selects skewed CTAs with a cluster barrier every LESV_KSW_SKEW rows (measured 517-549 GCUPS).
+using KswKernelFn = void (*)(const KswJob*, const int*, int, const uint32_t*, uint8_t*, const size_t*, uint32_t*,
+                             KswGapRun*, KswOut*, int*);
+static KswKernelFn cluster_kernel()
+{
+    static const bool ring = getenv("LESV_KSW_CLUSTER_SKEW") == nullptr;
+    static const int k = getenv("LESV_KSW_SKEW") ? atoi(getenv("LESV_KSW_SKEW")) : 8;
+    if (ring) return ksw_dp_kernel<true, kSyncRing>;
+    if (k <= 4) return ksw_dp_kernel<true, kSyncSkew, 4>;
+    if (k <= 8) return ksw_dp_kernel<true, kSyncSkew, 8>;
+    return ksw_dp_kernel<true, kSyncSkew, 16>;
+}
+
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* arena_stride, uint32_t* d_cigar,
                        KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
@@ -720,8 +786,9 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 #undef LESV_LAUNCH1
         return cudaGetLastError();
     }
-    cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    auto kern = cluster_kernel();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
     cfg.blockDim = dim3((unsigned)nt);
@@ -731,7 +798,7 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true, kSyncRing>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+    return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
 }
 
@@ -739,8 +806,9 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
-    cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true, kSyncRing>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    auto kern = cluster_kernel();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
@@ -748,7 +816,7 @@ int ksw_max_clusters(int nt, int ncta, size_t smem)
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ksw_dp_kernel<true, kSyncRing>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 

@@ -44,10 +44,21 @@ extern "C" int lesv_emul_ksw_extd2_tb(int qlen, const uint8_t* query, int tlen, 
 // CTA barrier only every skew_k ticks.  Inside a barrier interval the warps are run one after the
 // other in a random order -- the most adversarial interleaving the barrier allows -- so a slot that
 // could be read before it is written, or overwritten before it is read, shows up as a wrong CIGAR.
+static int g_group = 32;   // threads per skew group: 32 = warps of one CTA, NT = the CTAs of a cluster
 extern "C" int lesv_emul_ksw_extd2_skew(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                         int w, int nt, int skew_k, unsigned seed, uint32_t** cigar_out)
 {
+    g_group = 32;
     return emul_impl(qlen, query, tlen, target, w, nt, cigar_out, nullptr, nullptr, skew_k, seed);
+}
+// cluster flavour: `nt` threads in groups of `group` (one CTA each), lock-step inside a group
+extern "C" int lesv_emul_ksw_extd2_skew_group(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                              int w, int nt, int group, int skew_k, unsigned seed, uint32_t** cigar_out)
+{
+    g_group = group;
+    const int n = emul_impl(qlen, query, tlen, target, w, nt, cigar_out, nullptr, nullptr, skew_k, seed);
+    g_group = 32;
+    return n;
 }
 
 static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
@@ -71,33 +82,34 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
     std::vector<Carry> pub(nt), pub_next(nt);
     for (auto& c : pub) c = carry_init();
     if (skew_k > 0) {
-        if (nt % 32) return -3;
-        const int K = skew_k, R = 4 * K, NW = nt / 32;
+        const int G = g_group;
+        if (nt % G) return -3;
+        const int K = skew_k, R = 4 * K, NW = nt / G;
         for (int r = 0; r < (int)nrow; ++r) {
             const RowGeom g = row_geom(r, qlen, tlen, w);
             if ((g.wr >> 4) - (g.st0 >> 4) + 1 > nt) return -1;
         }
         const int maxB = ((tlen - 1) >> 4) + 1;
-        const int nticks = (int)nrow + K * (maxB >> 5);
+        const int nticks = (int)nrow + K * (maxB / G);
         std::vector<int> rr(nt);
         std::vector<Carry> prev(nt, carry_init()), ring((size_t)NW * R, carry_init());
         for (auto& c : ring) { c.xv = 0xDEADBEEFu; c.x2 = 0xDEADBEEFu; }
-        for (int t = 0; t < nt; ++t) rr[t] = -K * (th[t].cand >> 5);
+        for (int t = 0; t < nt; ++t) rr[t] = -K * (th[t].cand / G);
         std::vector<int> perm(NW);
         for (int s0 = 0; s0 < nticks; s0 += K) {
             for (int k = 0; k < NW; ++k) perm[k] = k;
             for (int k = NW - 1; k > 0; --k) { seed = seed * 1664525u + 1013904223u; std::swap(perm[k], perm[(seed >> 8) % (k + 1)]); }
             for (int wp : perm)
                 for (int s = s0; s < s0 + K && s < nticks; ++s) {
-                    Carry cin[32];
-                    for (int l = 1; l < 32; ++l) cin[l] = prev[wp * 32 + l - 1];
-                    for (int l = 0; l < 32; ++l) {
-                        const int tid = wp * 32 + l;
+                    std::vector<Carry> cin(G);
+                    for (int l = 1; l < G; ++l) cin[l] = prev[wp * G + l - 1];
+                    for (int l = 0; l < G; ++l) {
+                        const int tid = wp * G + l;
                         ThreadCtx& c = th[tid];
                         int& r = rr[tid];
                         if (r < c.fast_lo || r > c.fast_hi)
                             while (c.cand <= maxB && (r >= (int)nrow || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
-                                c.cand += nt; r = s - K * (c.cand >> 5);
+                                c.cand += nt; r = s - K * (c.cand / G);
                             }
                         if (r >= 0 && r < (int)nrow && c.cand <= maxB) {
                             Carry cout; uint32_t tb[4];
@@ -107,7 +119,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
                                 if (c.tb_off < 0 || c.tb_off >= (int)prow) return -2;
                                 memcpy(&p[(size_t)r * prow + (size_t)c.tb_off], tb, 16);
                                 prev[tid] = cout;
-                                if (l == 31) ring[(size_t)((wp + 1) % NW) * R + (r & (R - 1))] = cout;
+                                if (l == G - 1) ring[(size_t)((wp + 1) % NW) * R + (r & (R - 1))] = cout;
                             }
                         }
                         ++r;

@@ -120,6 +120,17 @@ def emul_ksw_skew(q, t, w, nt, k, seed):
     return out
 
 
+def emul_ksw_skew_group(q, t, w, nt, group, k, seed):
+    lib = emul()
+    cig = C.POINTER(C.c_uint32)()
+    n = lib.lesv_emul_ksw_extd2_skew_group(len(q), _ptr(q), len(t), _ptr(t), w, nt, group, k, C.c_uint(seed), C.byref(cig))
+    if n < 0:
+        return n
+    out = [cig[i] for i in range(n)]
+    _libc.free(cig)
+    return out
+
+
 def _tb(lib, fn, q, t, w, nt=None):
     cig = C.POINTER(C.c_uint32)()
     tb = C.POINTER(C.c_uint8)()

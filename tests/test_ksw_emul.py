@@ -42,6 +42,24 @@ def test_emulated_skewed_schedule_equals_oracle(k):
     assert n > 600
 
 
+def test_emulated_cluster_skew_equals_oracle():
+    """Cluster flavour of the skewed schedule: the CTAs of a cluster are the groups (lock-step inside)."""
+    rng = np.random.default_rng(77)
+    n = 0
+    for it in range(500):
+        q, t, w = H.random_pair(rng, it, max_len=3000 if it % 3 == 0 else 700)
+        if not H.oracle_cells(len(q), len(t), w)[1]:
+            continue
+        ncta = int(rng.choice([2, 4]))
+        need = H.min_threads(len(q), len(t), w)
+        per = ((need + ncta - 1) // ncta + 31) // 32 * 32
+        a, _ = H.oracle_ksw(q, t, w)
+        b = H.emul_ksw_skew_group(q, t, w, per * ncta, per, int(rng.choice([4, 8])), it)
+        assert a == b, (it, len(q), len(t), w, per, ncta)
+        n += 1
+    assert n > 250
+
+
 def test_emulated_kernel_traceback_bytes_equal_oracle():
     rng = np.random.default_rng(7)
     cells = 0
