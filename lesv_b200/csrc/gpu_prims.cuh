@@ -1,0 +1,27 @@
+// gpu_prims.cuh -- device-wide building blocks of the mapper stages: exclusive scan and a stable
+// LSD radix sort of (u64 key, u64 payload) records.  Hand-written for sm_100a; no CUB/Thrust.
+//
+// Why stable LSD: the reference's index is "k-mers sorted by hash, ties in ascending offset" because
+// its own sort is a stable 8-bit LSD radix sort (reference src/algo/hash_list_bucket_sort.c:93-235),
+// and the seed lists of a read are consumed in (subject offset, query offset) order.  Emitting
+// records in payload order and sorting them stably by key reproduces both without a second key.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace lesvmap {
+
+// out[i] = sum_{j<i} in[j]; returns nothing, the grand total lands in *d_total (may be null).
+// tmp must hold scan_tmp_words(n) uint32 words.
+size_t scan_tmp_words(size_t n);
+void exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_t* d_total,
+                        uint32_t* d_tmp, cudaStream_t s);
+
+// Stable sort of n records by bits [bit_lo, bit_hi) of the key.  Ping-pongs between (k0,v0) and
+// (k1,v1); returns 0 if the sorted records end up in (k0,v0), 1 if in (k1,v1).
+// tmp: radix_tmp_words(n) uint32 words.
+size_t radix_tmp_words(size_t n);
+int radix_sort_pairs(uint64_t* k0, uint64_t* v0, uint64_t* k1, uint64_t* v1, size_t n,
+                     int bit_lo, int bit_hi, uint32_t* d_tmp, cudaStream_t s);
+
+}  // namespace lesvmap

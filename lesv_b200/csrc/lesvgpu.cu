@@ -4,8 +4,7 @@
 // feeder thread hands a whole batch to one GPU: pairs are binned by band width into the thread
 // counts the DP kernel is instantiated for, each bin is sorted by decreasing traceback size and
 // pulled by persistent CTAs, and every CTA reuses one traceback arena in HBM.
-#include "../../include/lesvgpu.h"
-#include "ksw_kernels.cuh"
+#include "ctx_internal.cuh"
 #include "ksw_core.cuh"
 
 #include <algorithm>
@@ -15,82 +14,6 @@
 #include <vector>
 
 using namespace lesvksw;
-
-namespace {
-
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 64;
-        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-template <class T>
-struct PinBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 64;
-        cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-constexpr int kSideStreams = 8;
-
-struct lesvgpu_ctx {
-    int device = 0;
-    int n_sm = 0;
-    size_t arena_limit = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t side[kSideStreams] = {};        // launch classes of one batch run concurrently
-    cudaEvent_t side_done[kSideStreams] = {};
-    cudaEvent_t ev[8] = {};
-    std::string err;
-    lesvgpu_timing timing = {};
-    DevBuf<uint8_t> d_raw, d_arena, d_subject;
-    size_t subject_bytes = 0;
-    DevBuf<uint32_t> d_pool, d_cigar, d_scratch;
-    DevBuf<KswJob> d_jobs;
-    DevBuf<KswOut> d_outs;
-    DevBuf<KswGapRun> d_runs;
-    DevBuf<int> d_order, d_counter;
-    DevBuf<size_t> d_aoff;
-    PinBuf<uint8_t> h_raw;
-    PinBuf<uint32_t> h_cigar;
-    PinBuf<KswOut> h_outs;
-    PinBuf<KswGapRun> h_runs;
-    std::vector<lesvgpu_svsig> sigs;
-};
-
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            char b_[512];                                                                     \
-            snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-            ctx->err = b_;                                                                    \
-            return LESVGPU_E_CUDA;                                                            \
-        }                                                                                     \
-    } while (0)
 
 extern "C" int lesvgpu_device_count(void)
 {
@@ -136,6 +59,7 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     for (auto& e : ctx->side_done) cudaEventDestroy(e);
     for (auto& st : ctx->side) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->map) lesvmap_state_free(ctx->map);
     delete ctx;
 }
 
