@@ -158,6 +158,75 @@ typedef struct {
 int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
                                const lesvgpu_refine_job* jobs, int n, lesvgpu_refine_result* results);
 
+/* ---- qx2map, candidate stage: index, seeding, chaining, candidate windows ----------------------
+ * lesvgpu_index_build stands in for
+ *   LookupTable* build_lookup_table(const text_t* db, int kmer_size, int window_size,
+ *                                   int max_kmer_occ, int num_threads)     algo/lookup_table.h:29-33
+ * over the subject volume already resident through lesvgpu_subject_load: k-mers at offsets 0, w, 2w ..
+ * of every contig, sorted by (hash, offset) -- the reference's stable LSD radix sort,
+ * algo/hash_list_bucket_sort.c:138-235 -- runs longer than max_kmer_occ removed (lookup_table.c:95-138).
+ * The index stays in HBM; lesvgpu_index_export copies it out in the reference's layout
+ * (LookupTable.offset_list, LktblKmerInfo{hash, offset_list_idx, cnt}) for parity checks.
+ */
+typedef struct {            /* CSeqInfo.seq_offset / .seq_size, corelib/seqdb.h:20-27 */
+    uint64_t seq_offset;
+    uint64_t seq_size;
+} lesvgpu_seq;
+
+int lesvgpu_index_build(lesvgpu_ctx* ctx, const lesvgpu_seq* subject_seqs, int nseq,
+                        int kmer_size, int kmer_window, int max_kmer_occ);
+int lesvgpu_index_stats(const lesvgpu_ctx* ctx, uint64_t* n_offsets, uint64_t* n_distinct);
+/* offset_list[n_offsets], hashes[n_distinct], starts[n_distinct + 1] (cnt = starts[i+1] - starts[i]) */
+int lesvgpu_index_export(lesvgpu_ctx* ctx, uint64_t* offset_list, uint64_t* hashes, uint32_t* starts);
+
+/* lesvgpu_map_candidates stands in, for the reads [qfrom, qto) of a query volume, for
+ *   hbn_find_kmer_matches_mt(HbnWordFindData*, qfrom, qto, soff_max)       algo/hbn_word_finder.h:91-95
+ * followed, per read, by the first half of process_one_query
+ * (app/map/chain_and_extend_kmer_matches.c:188-232): find_candidates_for_one_context (:144-186, with
+ * chaining_find_candidates, algo/chain_dp.c:273) and find_candidate_subject_subseqs
+ * (app/map/hbn_find_subseq_hit.c:213).  The result is what `qx2map -outfmt subseq` prints:
+ * HbnSubseqHit records (app/map/hbn_subseq_hit.h:10-21) in the reference's order, read by read.
+ * query_pac / query_seqs describe the whole query volume (CSeqDB.packed_seq, seq_info_list).
+ */
+typedef struct {
+    int min_ddfs;           /* -min_ddfs, default 3  (chain min_cnt; min_score = (int)(min_ddfs*k*0.8)) */
+    int hitlist_size;       /* -max_target_seqs                                                        */
+} lesvgpu_map_opts;
+
+typedef struct {            /* HbnSubseqHit */
+    int qid, qdir, qoff;
+    int sid, soff;
+    size_t sfrom, sto;
+    int score;
+} lesvgpu_subseq_hit;
+
+typedef struct {            /* HbnInitHit as fill_init_hit_info leaves it (fields read downstream) */
+    int qid, qdir, qoff, qbeg, qend;
+    int sid;
+    int64_t soff, sbeg, send;   /* contig-relative */
+    int score;
+} lesvgpu_init_hit;
+
+typedef struct {            /* DDFKmerMatch, algo/hbn_word_finder.h:21-25 */
+    int context, qoff;
+    int64_t soff;
+} lesvgpu_kmer_match;
+
+typedef struct {
+    float h2d_ms, lookup_ms, emit_ms, sort_ms, chain_ms, d2h_ms;
+    uint64_t n_kmers, n_matches, n_segments, n_hits;
+    size_t h2d_bytes, d2h_bytes;
+} lesvgpu_map_timing;
+
+/* *windows / *first are library-owned: windows of read qfrom+i are (*windows)[(*first)[i] .. (*first)[i+1]). */
+int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac, const lesvgpu_seq* query_seqs,
+                           int qfrom, int qto, const lesvgpu_map_opts* opts,
+                           const lesvgpu_subseq_hit** windows, const int** first);
+/* intermediate results of the last lesvgpu_map_candidates call (parity checks, later stages) */
+int lesvgpu_map_last_init_hits(const lesvgpu_ctx* ctx, const lesvgpu_init_hit** hits, const int** first);
+int lesvgpu_map_last_matches(lesvgpu_ctx* ctx, int qfrom, const lesvgpu_kmer_match** matches, size_t* n);
+void lesvgpu_map_last_timing(const lesvgpu_ctx* ctx, lesvgpu_map_timing* t);
+
 /* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
  * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */
 int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* ok);

@@ -183,3 +183,114 @@ def svsig_batch(ctx: "Context", query_pac: np.ndarray, query_read_offset: np.nda
     if rc != OK:
         raise RuntimeError(f"lesvgpu_svsig_batch failed ({rc}): {ctx.error()}")
     return per, [sigs[i].astuple() for i in range(n_sigs.value)]
+
+
+# ---- qx2map candidate stage (include/lesvgpu.h: lesvgpu_index_build .. lesvgpu_map_candidates) --------
+class Seq(C.Structure):
+    _fields_ = [("seq_offset", C.c_uint64), ("seq_size", C.c_uint64)]
+
+
+class MapOpts(C.Structure):
+    _fields_ = [("min_ddfs", C.c_int), ("hitlist_size", C.c_int)]
+
+
+class SubseqHit(C.Structure):
+    _fields_ = [("qid", C.c_int), ("qdir", C.c_int), ("qoff", C.c_int), ("sid", C.c_int), ("soff", C.c_int),
+                ("sfrom", C.c_size_t), ("sto", C.c_size_t), ("score", C.c_int)]
+
+    def astuple(self):
+        return (self.qid, self.qdir, self.qoff, self.sid, self.soff, self.sfrom, self.sto, self.score)
+
+
+class InitHit(C.Structure):
+    _fields_ = [("qid", C.c_int), ("qdir", C.c_int), ("qoff", C.c_int), ("qbeg", C.c_int), ("qend", C.c_int),
+                ("sid", C.c_int), ("soff", C.c_int64), ("sbeg", C.c_int64), ("send", C.c_int64), ("score", C.c_int)]
+
+
+class KmerMatch(C.Structure):
+    _fields_ = [("context", C.c_int), ("qoff", C.c_int), ("soff", C.c_int64)]
+
+
+class MapTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "lookup_ms", "emit_ms", "sort_ms", "chain_ms", "d2h_ms")] + \
+               [(n, C.c_uint64) for n in ("n_kmers", "n_matches", "n_segments", "n_hits")] + \
+               [("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t)]
+
+
+def _bind_map(lib):
+    lib.lesvgpu_index_build.argtypes = [C.c_void_p, C.POINTER(Seq), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.lesvgpu_index_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.lesvgpu_index_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lesvgpu_map_candidates.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Seq), C.c_int, C.c_int, C.POINTER(MapOpts),
+                                           C.POINTER(C.POINTER(SubseqHit)), C.POINTER(C.POINTER(C.c_int))]
+    lib.lesvgpu_map_last_init_hits.argtypes = [C.c_void_p, C.POINTER(C.POINTER(InitHit)), C.POINTER(C.POINTER(C.c_int))]
+    lib.lesvgpu_map_last_matches.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(KmerMatch)), C.POINTER(C.c_size_t)]
+    lib.lesvgpu_map_last_timing.argtypes = [C.c_void_p, C.POINTER(MapTiming)]
+
+
+def _seq_array(offsets, sizes):
+    n = len(offsets)
+    arr = (Seq * max(1, n))()
+    for i in range(n):
+        arr[i].seq_offset, arr[i].seq_size = int(offsets[i]), int(sizes[i])
+    return arr
+
+
+def index_build(ctx: "Context", seq_offsets, seq_sizes, kmer_size=15, kmer_window=10, max_kmer_occ=200):
+    """build_lookup_table over the subject volume loaded with subject_load()."""
+    _bind_map(ctx.lib)
+    rc = ctx.lib.lesvgpu_index_build(ctx.h, _seq_array(seq_offsets, seq_sizes), len(seq_offsets), kmer_size, kmer_window,
+                                     max_kmer_occ)
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_index_build failed ({rc}): {ctx.error()}")
+
+
+def index_export(ctx: "Context"):
+    """(offset_list u64[n], hashes u64[d], starts u32[d+1]) -- LookupTable in the reference's order."""
+    _bind_map(ctx.lib)
+    n, d = C.c_uint64(), C.c_uint64()
+    ctx.lib.lesvgpu_index_stats(ctx.h, C.byref(n), C.byref(d))
+    off = np.zeros(max(1, n.value), dtype=np.uint64)
+    hs = np.zeros(max(1, d.value), dtype=np.uint64)
+    st = np.zeros(d.value + 1, dtype=np.uint32)
+    rc = ctx.lib.lesvgpu_index_export(ctx.h, off.ctypes.data, hs.ctypes.data, st.ctypes.data)
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_index_export failed ({rc}): {ctx.error()}")
+    return off[:n.value], hs[:d.value], st
+
+
+def map_candidates(ctx: "Context", query_pac, q_offsets, q_sizes, qfrom, qto, min_ddfs=3, hitlist_size=3):
+    """Candidate windows (HbnSubseqHit tuples) per read of [qfrom, qto): list of lists."""
+    _bind_map(ctx.lib)
+    query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
+    opts = MapOpts(min_ddfs, hitlist_size)
+    w, first = C.POINTER(SubseqHit)(), C.POINTER(C.c_int)()
+    rc = ctx.lib.lesvgpu_map_candidates(ctx.h, query_pac.ctypes.data, _seq_array(q_offsets, q_sizes), qfrom, qto,
+                                        C.byref(opts), C.byref(w), C.byref(first))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_map_candidates failed ({rc}): {ctx.error()}")
+    return [[w[j].astuple() for j in range(first[i], first[i + 1])] for i in range(qto - qfrom)]
+
+
+def map_last_matches(ctx: "Context", qfrom=0):
+    """DDFKmerMatch records of the last map_candidates call as an (n, 3) int64 array (context, qoff, soff),
+    sorted by (context, soff, qoff)."""
+    _bind_map(ctx.lib)
+    m, n = C.POINTER(KmerMatch)(), C.c_size_t()
+    rc = ctx.lib.lesvgpu_map_last_matches(ctx.h, qfrom, C.byref(m), C.byref(n))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_map_last_matches failed ({rc}): {ctx.error()}")
+    if n.value == 0:
+        return np.zeros((0, 3), dtype=np.int64)
+    raw = np.ctypeslib.as_array(C.cast(m, C.POINTER(C.c_int32)), shape=(n.value, 4))
+    out = np.empty((n.value, 3), dtype=np.int64)
+    out[:, 0] = raw[:, 0]; out[:, 1] = raw[:, 1]
+    out[:, 2] = raw[:, 2:4].copy().view(np.int64)[:, 0]
+    return out
+
+
+def map_last_timing(ctx: "Context") -> MapTiming:
+    _bind_map(ctx.lib)
+    t = MapTiming()
+    ctx.lib.lesvgpu_map_last_timing(ctx.h, C.byref(t))
+    return t

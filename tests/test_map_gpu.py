@@ -1,0 +1,102 @@
+"""qx2map candidate stage on the GPU through the C ABI (lesvgpu_index_build, lesvgpu_map_candidates)
+against the reference: the committed golden run (tests/golden/map_small, made by make_golden_map.py
+from the unmodified reference) and, when oracle/_ref travelled to the box, fresh reference runs on
+seeded synthetic data.  Integer outputs: bit-exact."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(H.ROOT, "tests", "golden", "map_small")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from lesv_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _load(ctx, db_dir, k=15, w=10, max_occ=200):
+    from lesv_b200 import capi
+    S, Q = H.LesvDb(db_dir, "subject"), H.LesvDb(db_dir, "query")
+    capi.subject_load(ctx, S.pac)
+    capi.index_build(ctx, S.seq_offset, S.seq_size, k, w, max_occ)
+    return S, Q
+
+
+def test_index_equals_reference_lookup_table(ctx):
+    from lesv_b200 import capi
+    _load(ctx, os.path.join(GOLD, "db"))
+    off, hashes, starts = capi.index_export(ctx)
+    z = np.load(os.path.join(GOLD, "index.npz"))
+    assert np.array_equal(off, z["offset_list"])            # sorted by (hash, offset), repeats removed
+    assert np.array_equal(hashes, z["hashes"])
+    assert np.array_equal(np.diff(starts.astype(np.int64)), z["counts"])
+
+
+def test_matches_and_windows_equal_golden(ctx):
+    import refmap
+    from lesv_b200 import capi
+    S, Q = _load(ctx, os.path.join(GOLD, "db"))
+    res = capi.map_candidates(ctx, Q.pac, Q.seq_offset, Q.seq_size, 0, Q.num_seqs, 3, 5)
+    m = capi.map_last_matches(ctx)
+    exp_m = np.load(os.path.join(GOLD, "matches.npy"))
+    assert m.shape == exp_m.shape and np.array_equal(m, exp_m)
+    exp = refmap.parse_subseq(os.path.join(GOLD, "cand.subseq.txt"))
+    assert sum(len(v) for v in exp.values()) > 100
+    for i, got in enumerate(res):
+        assert got == exp.get(i, []), (i, got, exp.get(i, []))
+
+
+def test_sub_batches_of_a_volume(ctx):
+    """[qfrom, qto) slices: ids stay volume-relative (on this data the batch-wide occurrence filter
+    does not bite for the first reads, so the windows are those of the whole-volume run)."""
+    import refmap
+    from lesv_b200 import capi
+    S, Q = _load(ctx, os.path.join(GOLD, "db"))
+    exp = refmap.parse_subseq(os.path.join(GOLD, "cand.subseq.txt"))
+    res = capi.map_candidates(ctx, Q.pac, Q.seq_offset, Q.seq_size, 7, 19, 3, 5)
+    for i, got in enumerate(res):
+        assert got == exp.get(7 + i, [])
+    assert capi.map_candidates(ctx, Q.pac, Q.seq_offset, Q.seq_size, 4, 4, 3, 5) == []
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(H.ROOT, "oracle", "_ref", "bin", "qx2map")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["contigs24", "long_reads", "k13w7"])
+def test_candidates_against_fresh_reference_run(ctx, tmp_path, case):
+    import refmap
+    from lesv_b200 import capi, synth
+    work = str(tmp_path)
+    k, w, occ = 15, 10, 200
+    extra = []
+    if case == "contigs24":
+        synth.make_dataset(work, ref_len=1_200_000, n_reads=120, read_len=8000, n_events=24, seed=31, n_contigs=24)
+    elif case == "long_reads":
+        synth.make_dataset(work, ref_len=2_000_000, n_reads=24, read_len=50000, n_events=10, seed=32, err_lo=0.10, err_hi=0.15)
+    else:
+        k, w, occ = 13, 7, 50
+        extra = ["-kmer_size", "13", "-kmer_window", "7", "-max_kmer_occ", "50"]
+        synth.make_dataset(work, ref_len=400_000, n_reads=60, read_len=5000, n_events=8, seed=33, n_contigs=2)
+    refmap.run_qx2map(work, ["-outfmt", "subseq", "-max_target_seqs", "5", "-max_hsps", "10", "-db_dir", "db", "-keep_db"] + extra,
+                      "cand.txt")
+    exp = refmap.parse_subseq(os.path.join(work, "cand.txt"))
+    db = os.path.join(work, "db")
+    S, Q = _load(ctx, db, k, w, occ)
+    off, hashes, starts = capi.index_export(ctx)
+    r_off, r_hashes, r_cnt, handles = refmap.ref_index(db, k, w, occ)
+    assert np.array_equal(off, r_off) and np.array_equal(hashes, r_hashes)
+    assert np.array_equal(np.diff(starts.astype(np.int64)), r_cnt)
+    res = capi.map_candidates(ctx, Q.pac, Q.seq_offset, Q.seq_size, 0, Q.num_seqs, 3, 5)
+    assert np.array_equal(capi.map_last_matches(ctx), refmap.ref_matches(db, k, occ, handles))
+    n = 0
+    for i, got in enumerate(res):
+        assert got == exp.get(i, []), (case, i, got, exp.get(i, []))
+        n += len(got)
+    assert n >= Q.num_seqs // 2
+    shutil.rmtree(work, ignore_errors=True)
