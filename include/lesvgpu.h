@@ -191,6 +191,15 @@ int lesvgpu_index_export(lesvgpu_ctx* ctx, uint64_t* offset_list, uint64_t* hash
 typedef struct {
     int min_ddfs;           /* -min_ddfs, default 3  (chain min_cnt; min_score = (int)(min_ddfs*k*0.8)) */
     int hitlist_size;       /* -max_target_seqs                                                        */
+    /* extension stage (lesvgpu_map_batch); 0 = the reference's default */
+    int max_hsps;           /* -max_hsps, default 5 for task rm (cmdline_args.cpp:692-698)             */
+    int memsc_kmer_size;    /* -memsc_kmer_size 10, -memsc_kmer_window 10, -memsc_score 30              */
+    int memsc_kmer_window;
+    int memsc_score;
+    int qcov_hsp_res;       /* -qcov_hsp_res 100: shortest alignment kept                               */
+    double perc_identity;   /* -perc_identity 0.0                                                       */
+    int skip_overhang;      /* -skip_overhang                                                           */
+    int want_ops;           /* copy the alignment columns back (needed for -cigar / -md / sam / paf)    */
 } lesvgpu_map_opts;
 
 typedef struct {            /* HbnSubseqHit */
@@ -217,6 +226,39 @@ typedef struct {
     uint64_t n_kmers, n_matches, n_segments, n_hits;
     size_t h2d_bytes, d2h_bytes;
 } lesvgpu_map_timing;
+
+/* One HSP as s_hbn_extend_subject_subseq_hit_list fills BlastHSP (app/map/hbn_extend_subseq_hit.c:279-345):
+ * perc_identity = 100.0 * n_match / aln_len, raw_score = 8 * aln_len - n_match
+ * (calc_ident_perc, algo/hbn_traceback_aux.c:4-19).  Query coordinates are on strand qdir, as in
+ * BlastHSP before dump_m4_hits flips them (chain_and_extend_kmer_matches.c:325-330). */
+typedef struct {
+    int qid, qdir, qoff, qend, qsize;
+    int sid, soff, send;
+    int64_t ssize;
+    int aln_len, n_match;
+    int chain_score, ddf_score;
+    size_t ops_off;         /* first alignment column in *ops_pool: 0 = both bases, 1 = read base over '-', 2 = '-' over reference base */
+    int flags;              /* bit 0 / 1: the left / right overhang extension (hbn_traceback.c:214-311) ran */
+} lesvgpu_hsp;
+
+typedef struct {
+    float ihf_ms, sort_ms, chain_ms, trace_ms, d2h_ms;
+    uint64_t n_windows, n_seeds, n_candidates;
+    uint64_t n_unsupported;        /* candidates dropped because a step is not available on the GPU (0 today) */
+    uint64_t n_overhang_skipped;   /* reserved (0)                                                             */
+    size_t d2h_bytes;
+} lesvgpu_extend_timing;
+
+/* lesvgpu_map_batch stands in, for the reads [qfrom, qto) of a query volume, for
+ *   hbn_find_kmer_matches_mt(...) + chain_and_extend_km_mt(HbnWordFindData*, const HbnProgramOptions*, CSeqDB* qvol,
+ *       CSeqDB* svol, int qfrom, int qto, FILE* out, FILE* backup_out)   app/map/chain_and_extend_kmer_matches.h:11-19
+ * up to, but not including, the text formatting of dump_m4_hits: HSPs read by read, inside a read contig
+ * group by contig group, inside a group by raw_score (remove_contained_hsp).  The caller prints them
+ * (print_one_m4_result, app/map/mecat_results.c:256). */
+int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const lesvgpu_seq* query_seqs,
+                      int qfrom, int qto, const lesvgpu_map_opts* opts,
+                      const lesvgpu_hsp** hsps, const int** first, const uint8_t** ops_pool);
+void lesvgpu_map_last_extend_timing(const lesvgpu_ctx* ctx, lesvgpu_extend_timing* t);
 
 /* *windows / *first are library-owned: windows of read qfrom+i are (*windows)[(*first)[i] .. (*first)[i+1]). */
 int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac, const lesvgpu_seq* query_seqs,

@@ -191,7 +191,22 @@ class Seq(C.Structure):
 
 
 class MapOpts(C.Structure):
-    _fields_ = [("min_ddfs", C.c_int), ("hitlist_size", C.c_int)]
+    _fields_ = [("min_ddfs", C.c_int), ("hitlist_size", C.c_int), ("max_hsps", C.c_int), ("memsc_kmer_size", C.c_int),
+                ("memsc_kmer_window", C.c_int), ("memsc_score", C.c_int), ("qcov_hsp_res", C.c_int),
+                ("perc_identity", C.c_double), ("skip_overhang", C.c_int), ("want_ops", C.c_int)]
+
+
+class Hsp(C.Structure):
+    _fields_ = [("qid", C.c_int), ("qdir", C.c_int), ("qoff", C.c_int), ("qend", C.c_int), ("qsize", C.c_int),
+                ("sid", C.c_int), ("soff", C.c_int), ("send", C.c_int), ("ssize", C.c_int64),
+                ("aln_len", C.c_int), ("n_match", C.c_int), ("chain_score", C.c_int), ("ddf_score", C.c_int),
+                ("ops_off", C.c_size_t), ("flags", C.c_int)]
+
+
+class ExtendTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ihf_ms", "sort_ms", "chain_ms", "trace_ms", "d2h_ms")] + \
+               [(n, C.c_uint64) for n in ("n_windows", "n_seeds", "n_candidates", "n_unsupported", "n_overhang_skipped")] + \
+               [("d2h_bytes", C.c_size_t)]
 
 
 class SubseqHit(C.Structure):
@@ -226,6 +241,9 @@ def _bind_map(lib):
     lib.lesvgpu_map_last_init_hits.argtypes = [C.c_void_p, C.POINTER(C.POINTER(InitHit)), C.POINTER(C.POINTER(C.c_int))]
     lib.lesvgpu_map_last_matches.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(KmerMatch)), C.POINTER(C.c_size_t)]
     lib.lesvgpu_map_last_timing.argtypes = [C.c_void_p, C.POINTER(MapTiming)]
+    lib.lesvgpu_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Seq), C.c_int, C.c_int, C.POINTER(MapOpts),
+                                      C.POINTER(C.POINTER(Hsp)), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_uint8))]
+    lib.lesvgpu_map_last_extend_timing.argtypes = [C.c_void_p, C.POINTER(ExtendTiming)]
 
 
 def _seq_array(offsets, sizes):
@@ -263,7 +281,7 @@ def map_candidates(ctx: "Context", query_pac, q_offsets, q_sizes, qfrom, qto, mi
     """Candidate windows (HbnSubseqHit tuples) per read of [qfrom, qto): list of lists."""
     _bind_map(ctx.lib)
     query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
-    opts = MapOpts(min_ddfs, hitlist_size)
+    opts = MapOpts(min_ddfs=min_ddfs, hitlist_size=hitlist_size)
     w, first = C.POINTER(SubseqHit)(), C.POINTER(C.c_int)()
     rc = ctx.lib.lesvgpu_map_candidates(ctx.h, query_pac.ctypes.data, _seq_array(q_offsets, q_sizes), qfrom, qto,
                                         C.byref(opts), C.byref(w), C.byref(first))
@@ -293,4 +311,35 @@ def map_last_timing(ctx: "Context") -> MapTiming:
     _bind_map(ctx.lib)
     t = MapTiming()
     ctx.lib.lesvgpu_map_last_timing(ctx.h, C.byref(t))
+    return t
+
+
+def map_batch(ctx: "Context", query_pac, q_offsets, q_sizes, qfrom, qto, hitlist_size=3, max_hsps=5, want_ops=False,
+              min_ddfs=3):
+    """chain_and_extend for the reads [qfrom, qto): per read a list of dicts (HSP fields; `ops` = alignment
+    columns as a uint8 array when want_ops)."""
+    _bind_map(ctx.lib)
+    query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
+    opts = MapOpts(min_ddfs=min_ddfs, hitlist_size=hitlist_size, max_hsps=max_hsps, want_ops=1 if want_ops else 0)
+    h, first, pool = C.POINTER(Hsp)(), C.POINTER(C.c_int)(), C.POINTER(C.c_uint8)()
+    rc = ctx.lib.lesvgpu_map_batch(ctx.h, query_pac.ctypes.data, _seq_array(q_offsets, q_sizes), qfrom, qto, C.byref(opts),
+                                   C.byref(h), C.byref(first), C.byref(pool))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_map_batch failed ({rc}): {ctx.error()}")
+    out = []
+    for i in range(qto - qfrom):
+        lst = []
+        for j in range(first[i], first[i + 1]):
+            d = {n: getattr(h[j], n) for n, _ in Hsp._fields_}
+            if want_ops:
+                d["ops"] = np.ctypeslib.as_array(pool, shape=(d["ops_off"] + d["aln_len"],))[d["ops_off"]:].copy() if d["aln_len"] else np.zeros(0, np.uint8)
+            lst.append(d)
+        out.append(lst)
+    return out
+
+
+def map_last_extend_timing(ctx: "Context") -> ExtendTiming:
+    _bind_map(ctx.lib)
+    t = ExtendTiming()
+    ctx.lib.lesvgpu_map_last_extend_timing(ctx.h, C.byref(t))
     return t

@@ -140,7 +140,7 @@ rs_scatter_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict_
         uint32_t d = 0, rank = 0;
         const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
         if (valid) {
-            k = keys[i]; v = vals[i];
+            k = keys[i]; v = vals ? vals[i] : 0ull;
             d = (uint32_t)(k >> shift) & mask;
             const unsigned same = __match_any_sync(vm, d);
             rank = __popc(same & ((1u << lane) - 1u));
@@ -160,7 +160,8 @@ rs_scatter_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict_
         __syncthreads();
         if (valid) {
             const uint32_t pos = wcnt[warp][d] + rank;
-            okeys[pos] = k; ovals[pos] = v;
+            okeys[pos] = k;
+            if (ovals) ovals[pos] = v;
         }
         __syncthreads();
     }

@@ -19,7 +19,7 @@ void exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_
 
 // Stable sort of n records by bits [bit_lo, bit_hi) of the key.  Ping-pongs between (k0,v0) and
 // (k1,v1); returns 0 if the sorted records end up in (k0,v0), 1 if in (k1,v1).
-// tmp: radix_tmp_words(n) uint32 words.
+// tmp: radix_tmp_words(n) uint32 words.  v0 == v1 == nullptr sorts keys only.
 size_t radix_tmp_words(size_t n);
 int radix_sort_pairs(uint64_t* k0, uint64_t* v0, uint64_t* k1, uint64_t* v1, size_t n,
                      int bit_lo, int bit_hi, uint32_t* d_tmp, cudaStream_t s);

@@ -1,0 +1,619 @@
+// map_extend.cu -- the extension stage of the mapper (qx2map) on the GPU: MEM-stage seeding inside each
+// candidate window, chaining, and the base-level alignment of the best chains.
+//
+// Replaces (paths relative to the reference's src/):
+//   hbn_extend_query_subseq_hit_list / s_hbn_extend_subject_subseq_hit_list   app/map/hbn_extend_subseq_hit.c:366, 203
+//   InitHitFindData_Init / _AddQuery / _FindHits / s_collect_seeds            algo/init_hit_finder.c:360, 334, 387, 134
+//   InitHitFindData_SetupMapAlignInfoFromHit, hbn_traceback (+ edlib)         trace_core.cuh
+//   remove_contained_hsp, the HSP bookkeeping                                 hbn_extend_subseq_hit.c:102-128, 279-345 (host side, below)
+//
+// The reference sorts all 2*len 10-mers of a read once (33 % of qx2map's time) and merges every
+// window's words against them.  Here the roles are swapped: a CTA sorts the ~len/10 words of one
+// window in shared memory (bitonic, <= 16 K words = 192 KB with the counters), then streams the read's
+// words of the one strand that window is on through a binary search, twice: once to count how often
+// each window word occurs in the read (the caps of s_collect_seeds, :161-199, need both sides'
+// multiplicities), once to emit the (window offset, read offset) seeds.  Seeds of all windows are
+// sorted by one keys-only radix sort on (window, read offset, window offset) -- the order
+// chain_seed_off_lt (:22-27) asks for; the seed SET does not depend on the reference's unstable word
+// sort.  Chaining and alignment then run one thread per window / per candidate (chain_core.cuh,
+// trace_core.cuh); the reference's sequential "stop after max_hsps, skip contained chains" logic is
+// replayed on the host over the speculatively computed candidates.
+#include "map_state.cuh"
+#include "gpu_prims.cuh"
+#include "trace_core.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace lesvmap;
+
+namespace {
+
+constexpr int kIhfThreads = 512;
+constexpr int kMaxCandPerWindow = 3;                  // max_k of s_hbn_extend_subject_subseq_hit_list (:243), task rm
+constexpr int kTraceThreadsPerBlock = 64;
+
+struct WinDev {
+    uint32_t read;           // read index inside the batch
+    uint32_t strand;
+    uint64_t s_off;          // residue index of the window's first base inside the subject .pac
+    uint32_t wlen;
+    uint32_t n_words;        // window words: offsets 0, stride, 2*stride ... <= wlen - word
+};
+
+struct CandOut {
+    int status;              // lesvtb::Status
+    int qoff, qend, soff, send, aln_len, n_match;
+    int flags;               // bit 0/1: the reference would have tried the left/right overhang step
+    int chain_score, n_mems;
+    int mem_qbeg, mem_qend, mem_sbeg, mem_send;       // first / last MEM (chain_seed_list_is_contained)
+    unsigned long long ops_off;
+};
+
+__device__ __forceinline__ uint32_t load_word(const uint8_t* __restrict__ pac, uint64_t pos, int k)   // k <= 13
+{
+    const uint8_t* b = pac + (pos >> 2);
+    const uint32_t v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    return (v << ((pos & 3) * 2)) >> (32 - 2 * k);
+}
+__device__ __forceinline__ uint32_t revcomp_word(uint32_t x, int k)
+{
+    x = ~x;
+    x = __brev(x);
+    x = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+    return x >> (32 - 2 * k);
+}
+
+// word of the read at strand position p
+__device__ __forceinline__ uint32_t read_word(const uint8_t* __restrict__ qpac, const ReadDev& rd, uint32_t strand, uint32_t p, int k)
+{
+    if (!strand) return load_word(qpac, rd.off + p, k);
+    return revcomp_word(load_word(qpac, rd.off + (rd.len - p - k), k), k);
+}
+
+__device__ __forceinline__ uint32_t lower_bound_hash(const uint64_t* keys, uint32_t n, uint32_t hash)
+{
+    const uint64_t x = (uint64_t)hash << 32;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (keys[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// One CTA per window (persistent).  keys/cnt live in shared memory when the window has <= smem_words
+// words, else in this CTA's slab of global scratch.
+__global__ void __launch_bounds__(kIhfThreads)
+ihf_kernel(const WinDev* __restrict__ wins, uint32_t n_win, const ReadDev* __restrict__ reads,
+           const uint8_t* __restrict__ qpac, const uint8_t* __restrict__ spac, int word, int stride,
+           uint32_t smem_words, uint64_t* __restrict__ gscratch, size_t gstride_words,
+           uint64_t* __restrict__ seed_keys, uint32_t seed_cap, uint32_t* __restrict__ seed_counter,
+           uint32_t* __restrict__ win_count, uint32_t* __restrict__ work_counter)
+{
+    extern __shared__ uint64_t smem64[];
+    __shared__ uint32_t s_w, s_base, s_emit, s_red[kIhfThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        if (tid == 0) s_w = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t w = s_w;
+        if (w >= n_win) break;
+        const WinDev W = wins[w];
+        const ReadDev rd = reads[W.read];
+        const uint32_t n_w = W.n_words;
+        uint32_t P = 1;
+        while (P < n_w) P <<= 1;
+        uint64_t* keys = P <= smem_words ? smem64 : gscratch + (size_t)blockIdx.x * gstride_words;
+        uint32_t* cnt = reinterpret_cast<uint32_t*>(keys + P);
+        for (uint32_t i = tid; i < P; i += kIhfThreads) {
+            keys[i] = i < n_w ? ((uint64_t)load_word(spac, W.s_off + (uint64_t)i * stride, word) << 32) | (i * (uint32_t)stride) : ~0ull;
+            cnt[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t k = 2; k <= P; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < (P >> 1); t += kIhfThreads) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const uint64_t a = keys[i], b = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+                __syncthreads();
+            }
+        // pass 1: how often does each window word occur in the read (this strand)
+        const uint32_t n_r = rd.len >= (uint32_t)word ? rd.len - word + 1 : 0;
+        for (uint32_t p = tid; p < n_r; p += kIhfThreads) {
+            const uint32_t h = read_word(qpac, rd, W.strand, p, word);
+            const uint32_t idx = lower_bound_hash(keys, n_w, h);
+            if (idx < n_w && (uint32_t)(keys[idx] >> 32) == h) atomicAdd(&cnt[idx], 1u);
+        }
+        __syncthreads();
+        // caps of s_collect_seeds (init_hit_finder.c:161-199): window side nq <= 8, read side nr <= 8, nq*nr <= 8
+        uint32_t mine = 0;
+        for (uint32_t i = tid; i < n_w; i += kIhfThreads) {
+            const uint32_t nr = cnt[i];
+            if (!nr) continue;                        // only group heads are ever counted
+            uint32_t nq = 1;
+            const uint32_t h = (uint32_t)(keys[i] >> 32);
+            while (nq <= 8 && i + nq < n_w && (uint32_t)(keys[i + nq] >> 32) == h) ++nq;
+            if (nq * nr <= 8) { cnt[i] = nr | (nq << 16); mine += nq * nr; }
+            else cnt[i] = 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, d);
+        if (lane == 0) s_red[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (int x = 0; x < kIhfThreads / 32; ++x) tot += s_red[x];
+            s_base = atomicAdd(seed_counter, tot);
+            s_emit = 0;
+            win_count[w] = tot;
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+        for (uint32_t p = tid; p < n_r; p += kIhfThreads) {
+            const uint32_t h = read_word(qpac, rd, W.strand, p, word);
+            const uint32_t idx = lower_bound_hash(keys, n_w, h);
+            if (idx >= n_w || (uint32_t)(keys[idx] >> 32) != h) continue;
+            const uint32_t c = cnt[idx];
+            if (!c) continue;
+            const uint32_t nq = c >> 16;
+            const uint32_t pos = atomicAdd(&s_emit, nq);
+            for (uint32_t x = 0; x < nq; ++x) {
+                const uint32_t o = base + pos + x;
+                if (o < seed_cap) seed_keys[o] = ((uint64_t)w << 40) | ((uint64_t)p << 20) | (uint32_t)keys[idx + x];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct ChainBufs {
+    lesvchain::Seed* seeds;
+    int *f, *p, *t, *v;
+    lesvchain::IntPair* u;
+};
+
+// One thread per window: chain the sorted seeds (InitHitFindData_FindHits, init_hit_finder.c:387-467),
+// keep the seed lists of the <= 3 best chains.
+__global__ void __launch_bounds__(64)
+ihf_chain_kernel(const uint64_t* __restrict__ seed_keys, const uint32_t* __restrict__ win_off, const uint32_t* __restrict__ win_count,
+                 uint32_t n_win, int word, int min_score, ChainBufs cb, int* __restrict__ hs_w, int* __restrict__ hs_r,
+                 int* __restrict__ cand_info /* per candidate: score, seed_off, seed_cnt */, int* __restrict__ cand_cnt)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_win) return;
+    const uint32_t a = win_off[w], n = win_count[w];
+    cand_cnt[w] = 0;
+    if (n == 0) return;
+    lesvchain::Seed* seeds = cb.seeds + a;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t key = seed_keys[a + i];
+        seeds[i].q = (int)(key & 0xFFFFF);            // chain "query" = window (roles as in init_hit_finder.c)
+        seeds[i].s = (int)((key >> 20) & 0xFFFFF);    // chain "subject" = read
+        seeds[i].len = word;
+    }
+    lesvchain::Hit pre[lesvchain::kMaxChains], out[lesvchain::kMaxJoined];
+    int members[lesvchain::kMaxChains], n_pre = 0;
+    const lesvchain::Params P = lesvchain::make_params(1, min_score);
+    const int nh = lesvchain::find_candidates(P, seeds, (int)n, false, cb.f + a, cb.p + a, cb.t + a, cb.v + a, cb.u + a,
+                                              pre, &n_pre, out, members);
+    if (nh == 0) return;
+    lesvsort::introsort(out, (size_t)nh, lesvchain::HitScoreGt());         // :465, on the already sorted list
+    const int* v = cb.v + a;
+    int pos = 0;
+    const int nc = nh < kMaxCandPerWindow ? nh : kMaxCandPerWindow;
+    for (int h = 0; h < nc; ++h) {
+        const int start = pos;
+        for (int m = 0; m < out[h].mem_cnt; ++m) {
+            const lesvchain::Hit& c = pre[members[out[h].mem_off + m]];
+            for (int x = c.v_cnt - 1; x >= 0; --x) {
+                const lesvchain::Seed& sd = seeds[v[c.v_off + x]];
+                hs_w[a + pos] = sd.q; hs_r[a + pos] = sd.s; ++pos;
+            }
+        }
+        int* ci = cand_info + 3 * (kMaxCandPerWindow * (size_t)w + h);
+        ci[0] = out[h].score; ci[1] = (int)a + start; ci[2] = pos - start;
+    }
+    cand_cnt[w] = nc;
+}
+
+struct TraceBufs {
+    uint64_t* P; uint64_t* M; int* score; uint64_t* peq;     // per thread slab
+    size_t cells, peq_words;
+    uint8_t* ops; size_t ops_cap;                             // per thread working ops
+    uint8_t* blk;                                             // per thread kBlkOpsCap
+    lesvtb::Mem* mem_pool; unsigned long long mem_cap; unsigned long long* mem_counter;   // MEMs + trace seeds of a candidate
+    uint8_t* pool; unsigned long long pool_cap; unsigned long long* pool_counter;
+    const int16_t* trim_table; const int16_t* trim_score; int path_ave;
+};
+
+// Persistent threads, one alignment candidate at a time per thread (trace_core.cuh).
+__global__ void __launch_bounds__(kTraceThreadsPerBlock)
+trace_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
+             const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, uint32_t n_cand,
+             const int* __restrict__ cand_info, const int* __restrict__ hs_w, const int* __restrict__ hs_r, int word,
+             int min_align_size, double min_ident, int over_hang, TraceBufs tb, CandOut* __restrict__ outs,
+             uint32_t* __restrict__ work_counter)
+{
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    lesvtb::Scratch sc;
+    sc.P = tb.P + slot * tb.cells; sc.M = tb.M + slot * tb.cells; sc.score = tb.score + slot * tb.cells;
+    sc.peq = tb.peq + slot * tb.peq_words; sc.cap_cells = tb.cells; sc.cap_peq = tb.peq_words;
+    sc.trim_table = tb.trim_table; sc.trim_score = tb.trim_score; sc.path_ave = tb.path_ave;
+    uint8_t* ops = tb.ops + slot * tb.ops_cap;
+    uint8_t* blk = tb.blk + slot * lesvtb::kBlkOpsCap;
+    for (;;) {
+        const uint32_t x = atomicAdd(work_counter, 1u);
+        if (x >= n_cand) break;
+        const int c = cand_list[x];                       // = 3 * window + rank
+        const WinDev W = wins[c / kMaxCandPerWindow];
+        const ReadDev rd = reads[W.read];
+        const int* ci = cand_info + 3 * (size_t)c;
+        const int seed_off = ci[1], seed_cnt = ci[2];
+        auto Q = [&](int i) -> uint32_t {
+            return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)i)) : pac_code(qpac, rd.off + (uint32_t)i);
+        };
+        auto S = [&](int j) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)j); };
+        CandOut o;
+        memset(&o, 0, sizeof o);
+        o.chain_score = ci[0];
+        // MEMs between the chain's seeds can outnumber the seeds: count, then take room from the pool
+        int n_mems = lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, (lesvtb::Mem*)nullptr, 0);
+        lesvtb::Mem* mems = nullptr;
+        lesvtb::Mem* ts = nullptr;
+        if (n_mems > 0) {
+            const unsigned long long need = 2ull * (unsigned)n_mems + 2;
+            const unsigned long long off = atomicAdd(tb.mem_counter, need);
+            if (off + need > tb.mem_cap) n_mems = -1;
+            else {
+                mems = tb.mem_pool + off; ts = mems + n_mems;
+                lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, mems, n_mems);
+            }
+        }
+        o.n_mems = n_mems;
+        if (n_mems > 0) {
+            o.mem_qbeg = mems[0].q; o.mem_sbeg = mems[0].s;
+            o.mem_qend = mems[n_mems - 1].q + mems[n_mems - 1].len; o.mem_send = mems[n_mems - 1].s + mems[n_mems - 1].len;
+            const int q0 = mems[0].q, s0 = mems[0].s;
+            size_t front = (size_t)q0 + (size_t)s0 + 8;
+            const size_t alt = (size_t)(2.5 * q0) + 512;
+            if (alt < front) front = alt;
+            if (front > tb.ops_cap / 2) front = tb.ops_cap / 2;
+            const lesvtb::Result R = lesvtb::traceback(Q, (int)rd.len, S, (int)W.wlen, mems, n_mems, ts, sc, ops, tb.ops_cap, front,
+                                                       blk, min_align_size, min_ident, over_hang != 0);
+            o.status = R.status; o.qoff = R.qoff; o.qend = R.qend; o.soff = R.soff; o.send = R.send;
+            o.aln_len = R.aln_len; o.n_match = R.n_match; o.flags = R.overhang_left | (R.overhang_right << 1);
+            if (R.status == lesvtb::kOk) {
+                const unsigned long long off = atomicAdd(tb.pool_counter, (unsigned long long)R.aln_len);
+                o.ops_off = off;
+                if (off + (unsigned long long)R.aln_len <= tb.pool_cap)
+                    for (int a = 0; a < R.aln_len; ++a) tb.pool[off + a] = ops[R.ops_beg + a];
+                else o.status = lesvtb::kOpsOverflow;
+            }
+        } else if (n_mems < 0) o.status = lesvtb::kScratchOverflow;
+        outs[c] = o;
+    }
+}
+
+__global__ void win_count_clear_kernel(uint32_t* p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+}  // namespace
+
+struct lesvmap_ext {
+    DevBuf<WinDev> d_wins;
+    DevBuf<uint64_t> d_keys0, d_keys1, d_gscratch, d_P, d_M, d_peq;
+    DevBuf<uint32_t> d_win_count, d_win_off, d_counters, d_tmp;
+    DevBuf<int> d_hs_w, d_hs_r, d_cand_info, d_cand_cnt, d_cand_list, d_score;
+    DevBuf<lesvchain::Seed> d_seeds;
+    DevBuf<int> d_f, d_p, d_t, d_v;
+    DevBuf<lesvchain::IntPair> d_u;
+    DevBuf<lesvtb::Mem> d_mems;
+    DevBuf<uint8_t> d_ops, d_blk, d_pool;
+    DevBuf<unsigned long long> d_pool_counter;
+    DevBuf<CandOut> d_outs;
+    DevBuf<int16_t> d_trim;                  // DALIGNER TABLE | SCORE
+    int path_ave = 0;
+    std::vector<lesvgpu_hsp> hsps;
+    std::vector<int> hsp_first;
+    std::vector<uint8_t> ops_host;
+    lesvgpu_extend_timing tm = {};
+};
+
+void lesvmap_ext_free(lesvmap_ext* e)
+{
+    if (!e) return;
+    e->d_wins.release(); e->d_keys0.release(); e->d_keys1.release(); e->d_gscratch.release(); e->d_P.release(); e->d_M.release();
+    e->d_peq.release(); e->d_win_count.release(); e->d_win_off.release(); e->d_counters.release(); e->d_tmp.release();
+    e->d_hs_w.release(); e->d_hs_r.release(); e->d_cand_info.release(); e->d_cand_cnt.release(); e->d_cand_list.release();
+    e->d_score.release(); e->d_seeds.release(); e->d_f.release(); e->d_p.release(); e->d_t.release(); e->d_v.release(); e->d_u.release();
+    e->d_mems.release(); e->d_ops.release(); e->d_blk.release(); e->d_pool.release(); e->d_pool_counter.release();
+    e->d_outs.release(); e->d_trim.release();
+    delete e;
+}
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+static inline int bitlen(uint64_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
+
+namespace {
+struct WinScoreGt {       // subseq_hit_score_gt, app/map/hbn_subseq_hit.c:5
+    bool operator()(const lesvgpu_subseq_hit& a, const lesvgpu_subseq_hit& b) const { return a.score > b.score; }
+};
+struct HspScoreGt {       // blasthsp_score_gt, ncbi_blast/setup/blast_hits.c:49
+    bool operator()(const lesvgpu_hsp& a, const lesvgpu_hsp& b) const { return 8 * a.aln_len - a.n_match > 8 * b.aln_len - b.n_match; }
+};
+// subseq_is_contained, hbn_extend_subseq_hit.c:47-62 (note `i < hit_idx - 1` and the int truncation)
+bool window_contained(const lesvgpu_subseq_hit* h, int idx)
+{
+    const int E = 200;
+    const int sfrom = (int)h[idx].sfrom, sto = (int)h[idx].sto, qdir = h[idx].qdir;
+    for (int i = 0; i < idx - 1; ++i) {
+        if (h[i].qdir != qdir) continue;
+        const int ss = (int)h[i].sfrom, st = (int)h[i].sto;
+        if (sfrom + E >= ss && sto <= st + E) return true;
+    }
+    return false;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: seed + chain + extend for one query batch
+// ---------------------------------------------------------------------------------------------
+extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const lesvgpu_seq* qseqs, int qfrom, int qto,
+                                 const lesvgpu_map_opts* opts, const lesvgpu_hsp** hsps, const int** first,
+                                 const uint8_t** ops_pool)
+{
+    if (hsps) *hsps = nullptr;
+    if (first) *first = nullptr;
+    if (ops_pool) *ops_pool = nullptr;
+    const lesvgpu_subseq_hit* wins_host = nullptr;
+    const int* wfirst = nullptr;
+    int rc = lesvgpu_map_candidates(ctx, query_pac, qseqs, qfrom, qto, opts, &wins_host, &wfirst);
+    if (rc != LESVGPU_OK) return rc;
+    lesvmap_state* M = ctx->map;
+    if (!M->ext) M->ext = new lesvmap_ext;
+    lesvmap_ext* E = M->ext;
+    cudaStream_t s = ctx->stream;
+    const int nr = qto - qfrom;
+    const int word = opts->memsc_kmer_size > 0 ? opts->memsc_kmer_size : 10;
+    const int stride = opts->memsc_kmer_window > 0 ? opts->memsc_kmer_window : 10;
+    const int memsc_score = opts->memsc_score > 0 ? opts->memsc_score : 30;
+    const int max_hsps = opts->max_hsps > 0 ? opts->max_hsps : 5;
+    const int min_align = opts->qcov_hsp_res > 0 ? opts->qcov_hsp_res : 100;
+    if (word > 13) { ctx->err = "memsc_kmer_size > 13 is not supported"; return LESVGPU_E_ARG; }
+    E->hsps.clear(); E->hsp_first.assign(nr + 1, 0); E->ops_host.clear();
+    E->tm = lesvgpu_extend_timing{};
+
+    // ---- which windows the reference could visit (s_hbn_extend_subject_subseq_hit_list :222-233) ------
+    struct Group { int read, first, count; };           // windows of one read on one contig, sorted by score
+    std::vector<lesvgpu_subseq_hit> sorted;              // all windows, group by group, in visiting order
+    std::vector<Group> groups;
+    std::vector<int> win_gpu;                            // per sorted window: index in the GPU window list or -1
+    std::vector<WinDev> wins;
+    uint32_t max_words = 0, max_qsize = 0;
+    uint64_t pool_cap = 0;
+    for (int r = 0; r < nr; ++r) {
+        int i = wfirst[r];
+        while (i < wfirst[r + 1]) {
+            int j = i + 1;
+            while (j < wfirst[r + 1] && wins_host[j].sid == wins_host[i].sid) ++j;
+            Group g{r, (int)sorted.size(), j - i};
+            sorted.insert(sorted.end(), wins_host + i, wins_host + j);
+            lesvsort::introsort(sorted.data() + g.first, (size_t)g.count, WinScoreGt());
+            for (int x = 0; x < g.count; ++x) {
+                int gi = -1;
+                if (x < max_hsps + 2 && !window_contained(sorted.data() + g.first, x)) {
+                    const lesvgpu_subseq_hit& h = sorted[g.first + x];
+                    WinDev W;
+                    W.read = (uint32_t)r; W.strand = (uint32_t)h.qdir;
+                    W.s_off = M->sseqs[h.sid].seq_offset + h.sfrom;
+                    W.wlen = (uint32_t)(h.sto - h.sfrom);
+                    W.n_words = W.wlen >= (uint32_t)word ? (W.wlen - word) / stride + 1 : 0;
+                    if (W.wlen >= (1u << 20) || M->h_reads[r].len >= (1u << 20)) { ctx->err = "read or window longer than 2^20"; return LESVGPU_E_ARG; }
+                    gi = (int)wins.size();
+                    wins.push_back(W);
+                    max_words = std::max(max_words, W.n_words);
+                    max_qsize = std::max(max_qsize, M->h_reads[r].len);
+                    pool_cap += 3ull * M->h_reads[r].len + 4096;
+                }
+                win_gpu.push_back(gi);
+            }
+            groups.push_back(g);
+            i = j;
+        }
+    }
+    const uint32_t n_win = (uint32_t)wins.size();
+    if (first) *first = E->hsp_first.data();
+    if (n_win == 0) { if (hsps) *hsps = E->hsps.data(); return LESVGPU_OK; }
+    if (n_win >= (1u << 24)) { ctx->err = "more than 2^24 windows in one batch"; return LESVGPU_E_ARG; }
+
+    cudaEvent_t* ev = ctx->ev;
+    CK(E->d_wins.reserve(n_win));
+    CK(E->d_win_count.reserve(n_win + 1)); CK(E->d_win_off.reserve(n_win + 1));
+    CK(E->d_counters.reserve(8));
+    CK(E->d_cand_cnt.reserve(n_win)); CK(E->d_cand_info.reserve(3 * (size_t)kMaxCandPerWindow * n_win));
+    CK(E->d_outs.reserve((size_t)kMaxCandPerWindow * n_win));
+    CK(cudaEventRecord(ev[0], s));
+    CK(cudaMemcpyAsync(E->d_wins.p, wins.data(), sizeof(WinDev) * n_win, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(E->d_counters.p, 0, sizeof(uint32_t) * 8, s));
+    CK(cudaMemsetAsync(E->d_win_count.p, 0, sizeof(uint32_t) * (n_win + 1), s));
+
+    // ---- MEM-stage seeds ----------------------------------------------------------------------------
+    uint32_t Pmax = 1;
+    while (Pmax < max_words) Pmax <<= 1;
+    const uint32_t smem_words = std::min<uint32_t>(Pmax, 16384);
+    const size_t smem_bytes = (size_t)smem_words * 12;
+    int dev_sms = ctx->n_sm;
+    const int ctas = (int)std::min<uint32_t>(n_win, (uint32_t)dev_sms * (smem_bytes > 100 * 1024 ? 1 : smem_bytes > 50 * 1024 ? 2 : 4));
+    size_t gstride = 0;
+    if (Pmax > smem_words) { gstride = (size_t)Pmax * 3 / 2 + 8; CK(E->d_gscratch.reserve(gstride * ctas)); }
+    uint64_t seed_cap = 0;
+    for (const WinDev& W : wins) seed_cap += 2ull * W.n_words + 64;
+    uint32_t n_seeds = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (seed_cap >= 0xFFFFFFF0ull) { ctx->err = "too many MEM-stage seeds in one batch"; return LESVGPU_E_NOMEM; }
+        CK(E->d_keys0.reserve(seed_cap)); CK(E->d_keys1.reserve(seed_cap));
+        CK(cudaMemsetAsync(E->d_counters.p, 0, sizeof(uint32_t) * 8, s));
+        CK(cudaFuncSetAttribute(ihf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        ihf_kernel<<<ctas, kIhfThreads, smem_bytes, s>>>(E->d_wins.p, n_win, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, word, stride,
+                                                         smem_words, E->d_gscratch.p, gstride, E->d_keys0.p, (uint32_t)seed_cap,
+                                                         E->d_counters.p, E->d_win_count.p, E->d_counters.p + 1);
+        CK(cudaMemcpyAsync(&n_seeds, E->d_counters.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        if (n_seeds <= seed_cap) break;
+        seed_cap = (uint64_t)n_seeds + 1024;           // rare: repeats; run again with room for everything
+        if (attempt == 1) { ctx->err = "MEM-stage seed buffer overflow"; return LESVGPU_E_NOMEM; }
+    }
+    CK(cudaEventRecord(ev[1], s));
+    CK(E->d_tmp.reserve(std::max(radix_tmp_words(n_seeds), scan_tmp_words((size_t)n_win + 1))));
+    const int where = radix_sort_pairs(E->d_keys0.p, nullptr, E->d_keys1.p, nullptr, n_seeds, 0, 40 + std::max(1, bitlen(n_win - 1)),
+                                       E->d_tmp.p, s);
+    const uint64_t* seed_keys = where ? E->d_keys1.p : E->d_keys0.p;
+    exclusive_scan_u32(E->d_win_count.p, E->d_win_off.p, n_win, nullptr, E->d_tmp.p, s);
+    CK(cudaEventRecord(ev[2], s));
+
+    // ---- chaining inside each window ------------------------------------------------------------------
+    CK(E->d_seeds.reserve(n_seeds)); CK(E->d_f.reserve(n_seeds)); CK(E->d_p.reserve(n_seeds)); CK(E->d_t.reserve(n_seeds));
+    CK(E->d_v.reserve(n_seeds)); CK(E->d_u.reserve(n_seeds)); CK(E->d_hs_w.reserve(n_seeds)); CK(E->d_hs_r.reserve(n_seeds));
+    ChainBufs cb{E->d_seeds.p, E->d_f.p, E->d_p.p, E->d_t.p, E->d_v.p, E->d_u.p};
+    ihf_chain_kernel<<<nblk(n_win, 64), 64, 0, s>>>(seed_keys, E->d_win_off.p, E->d_win_count.p, n_win, word, memsc_score, cb,
+                                                    E->d_hs_w.p, E->d_hs_r.p, E->d_cand_info.p, E->d_cand_cnt.p);
+    std::vector<int> cand_cnt(n_win);
+    CK(cudaMemcpyAsync(cand_cnt.data(), E->d_cand_cnt.p, sizeof(int) * n_win, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+
+    // ---- base-level alignment of every candidate --------------------------------------------------------
+    std::vector<int> cand_list;
+    for (uint32_t w = 0; w < n_win; ++w)
+        for (int k = 0; k < cand_cnt[w]; ++k) cand_list.push_back(kMaxCandPerWindow * (int)w + k);
+    const uint32_t n_cand = (uint32_t)cand_list.size();
+    std::vector<CandOut> outs((size_t)kMaxCandPerWindow * n_win);
+    if (n_cand) {
+        const size_t cells = 52500;                       // traceback mode of edlib holds < 1 MB = 52,428 block-columns
+        const size_t peq_words = 4 * ((size_t)max_qsize / 64 + 2);
+        const size_t ops_cap = (size_t)(3.5 * max_qsize) + 2048;
+        const uint32_t n_threads = std::min<uint32_t>((n_cand + kTraceThreadsPerBlock - 1) / kTraceThreadsPerBlock * kTraceThreadsPerBlock,
+                                                      (uint32_t)dev_sms * kTraceThreadsPerBlock);
+        CK(E->d_P.reserve(cells * n_threads)); CK(E->d_M.reserve(cells * n_threads)); CK(E->d_score.reserve(cells * n_threads));
+        CK(E->d_peq.reserve(peq_words * n_threads));
+        CK(E->d_ops.reserve(ops_cap * n_threads)); CK(E->d_blk.reserve((size_t)lesvtb::kBlkOpsCap * n_threads));
+        const unsigned long long mem_cap = 4ull * n_seeds + 64ull * n_cand + 1024;
+        CK(E->d_mems.reserve(mem_cap));
+        CK(E->d_pool.reserve(pool_cap)); CK(E->d_pool_counter.reserve(2));
+        CK(E->d_cand_list.reserve(n_cand));
+        CK(cudaMemcpyAsync(E->d_cand_list.p, cand_list.data(), sizeof(int) * n_cand, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(E->d_pool_counter.p, 0, 2 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(E->d_counters.p + 2, 0, 4, s));
+        if (!E->d_trim.p) {
+            std::vector<int16_t> tt(65536);
+            lesvtb::dalign_tables(tt.data(), tt.data() + 32768, &E->path_ave);
+            CK(E->d_trim.reserve(65536));
+            CK(cudaMemcpyAsync(E->d_trim.p, tt.data(), sizeof(int16_t) * 65536, cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        TraceBufs tb;
+        tb.trim_table = E->d_trim.p; tb.trim_score = E->d_trim.p + 32768; tb.path_ave = E->path_ave;
+        tb.P = E->d_P.p; tb.M = E->d_M.p; tb.score = E->d_score.p; tb.peq = E->d_peq.p; tb.cells = cells; tb.peq_words = peq_words;
+        tb.ops = E->d_ops.p; tb.ops_cap = ops_cap; tb.blk = E->d_blk.p; tb.mem_pool = E->d_mems.p; tb.mem_cap = mem_cap; tb.mem_counter = E->d_pool_counter.p + 1;
+        tb.pool = E->d_pool.p; tb.pool_cap = pool_cap; tb.pool_counter = E->d_pool_counter.p;
+        trace_kernel<<<n_threads / kTraceThreadsPerBlock, kTraceThreadsPerBlock, 0, s>>>(
+            E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_hs_w.p,
+            E->d_hs_r.p, word, min_align, opts->perc_identity, opts->skip_overhang ? 0 : 1, tb, E->d_outs.p, E->d_counters.p + 2);
+        CK(cudaEventRecord(ev[4], s));
+        CK(cudaMemcpyAsync(outs.data(), E->d_outs.p, sizeof(CandOut) * outs.size(), cudaMemcpyDeviceToHost, s));
+        unsigned long long pool_used = 0;
+        CK(cudaMemcpyAsync(&pool_used, E->d_pool_counter.p, sizeof pool_used, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        if (pool_used > pool_cap) { ctx->err = "alignment pool overflow"; return LESVGPU_E_NOMEM; }
+        if (ops_pool && opts->want_ops) {
+            E->ops_host.resize(pool_used);
+            if (pool_used) CK(cudaMemcpyAsync(E->ops_host.data(), E->d_pool.p, pool_used, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaEventRecord(ev[5], s));
+        CK(cudaStreamSynchronize(s));
+        cudaEventElapsedTime(&E->tm.trace_ms, ev[3], ev[4]);
+        cudaEventElapsedTime(&E->tm.d2h_ms, ev[4], ev[5]);
+        E->tm.d2h_bytes = sizeof(CandOut) * outs.size() + E->ops_host.size();
+    }
+    cudaEventElapsedTime(&E->tm.ihf_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&E->tm.sort_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&E->tm.chain_ms, ev[2], ev[3]);
+    E->tm.n_windows = n_win; E->tm.n_seeds = n_seeds; E->tm.n_candidates = n_cand;
+
+    // ---- host: the reference's sequential selection over the computed candidates --------------------------
+    size_t gi = 0;
+    for (int r = 0; r < nr; ++r) {
+        const int qsize = (int)M->h_reads[r].len;
+        for (; gi < groups.size() && groups[gi].read == r; ++gi) {
+            const Group& g = groups[gi];
+            std::vector<lesvgpu_hsp> list;
+            for (int x = 0; x < g.count && x < max_hsps + 2 && (int)list.size() < max_hsps; ++x) {
+                const int gw = win_gpu[g.first + x];
+                if (gw < 0) continue;                   // contained window
+                const lesvgpu_subseq_hit& h = sorted[g.first + x];
+                for (int k = 0; k < cand_cnt[gw]; ++k) {
+                    const CandOut& o = outs[(size_t)kMaxCandPerWindow * gw + k];
+                    if (o.n_mems == 0) continue;
+                    if (o.status < 0 && o.status != lesvtb::kNeedsHirschberg) {
+                        ctx->err = "alignment scratch overflow (status " + std::to_string(o.status) + ")";
+                        return LESVGPU_E_NOMEM;
+                    }
+                    // chain_seed_list_is_contained, hbn_extend_subseq_hit.c:64-100
+                    bool contained = false;
+                    {
+                        const int E200 = 200;
+                        const int qbeg = o.mem_qbeg, qend = o.mem_qend;
+                        const int sbeg = o.mem_sbeg + (int)h.sfrom, send = o.mem_send + (int)h.sfrom;
+                        for (const lesvgpu_hsp& p : list) {
+                            if (p.qdir != h.qdir) continue;
+                            if (qbeg + E200 >= p.qoff && qend <= p.qend + E200 && sbeg + E200 >= p.soff && send <= p.send + E200) { contained = true; break; }
+                        }
+                    }
+                    if (contained) continue;
+                    if (o.status == lesvtb::kNeedsHirschberg) { ++E->tm.n_unsupported; continue; }
+                    if (o.status != lesvtb::kOk) continue;
+                    lesvgpu_hsp p;
+                    p.qid = qfrom + r; p.qdir = h.qdir; p.qoff = o.qoff; p.qend = o.qend; p.qsize = qsize;
+                    p.sid = h.sid; p.soff = o.soff + (int)h.sfrom; p.send = o.send + (int)h.sfrom;
+                    p.ssize = (int64_t)M->sseqs[h.sid].seq_size;
+                    p.aln_len = o.aln_len; p.n_match = o.n_match;
+                    p.chain_score = o.chain_score; p.ddf_score = h.score;
+                    p.ops_off = (size_t)o.ops_off;
+                    p.flags = o.flags;
+                    list.push_back(p);
+                    if ((int)list.size() == max_hsps) break;
+                }
+            }
+            if (list.empty()) continue;
+            // remove_contained_hsp, hbn_extend_subseq_hit.c:102-128
+            lesvsort::introsort(list.data(), list.size(), HspScoreGt());
+            std::vector<char> dead(list.size(), 0);
+            for (size_t i = 0; i < list.size(); ++i) {
+                if (dead[i]) continue;
+                for (size_t j = i + 1; j < list.size(); ++j) {
+                    if (dead[j] || list[j].qdir != list[i].qdir) continue;
+                    const int E200 = 200;
+                    if (list[j].qoff + E200 >= list[i].qoff && list[j].qend <= list[i].qend + E200 &&
+                        list[j].soff + E200 >= list[i].soff && list[j].send <= list[i].send + E200) dead[j] = 1;
+                }
+            }
+            for (size_t i = 0; i < list.size(); ++i) if (!dead[i]) E->hsps.push_back(list[i]);
+        }
+        E->hsp_first[r + 1] = (int)E->hsps.size();
+    }
+    if (hsps) *hsps = E->hsps.data();
+    if (ops_pool && opts->want_ops) *ops_pool = E->ops_host.data();
+    return LESVGPU_OK;
+}
+
+extern "C" void lesvgpu_map_last_extend_timing(const lesvgpu_ctx* ctx, lesvgpu_extend_timing* t)
+{
+    if (ctx && ctx->map && ctx->map->ext && t) *t = ctx->map->ext->tm;
+}

@@ -21,9 +21,8 @@
 //     [qfrom, qto), i.e. what the reference does with -num_threads 1;
 //   - seeds with equal subject offset enter the chaining in ascending query offset (the reference
 //     leaves that order to an unstable sort, sort_sr_hit_seeds.cpp:53-56).
-#include "ctx_internal.cuh"
+#include "map_state.cuh"
 #include "gpu_prims.cuh"
-#include "chain_core.cuh"
 
 #include <algorithm>
 #include <array>
@@ -33,31 +32,7 @@ using namespace lesvmap;
 
 namespace {
 
-constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr int kSeedBlock = 300, kSeedSkip = 200;      // kSeedingSeqSize / kSeedingSeqStride, hbn_word_finder.c:8-9
-
-struct IndexDev {
-    const uint64_t* off;         // offset_list
-    const uint64_t* dir_hash;
-    const uint32_t* dir_start;   // n_dir + 1
-    const uint32_t* bucket;      // 2^bb + 1
-    uint32_t* qcount;            // per directory entry: query k-mers of the current batch that hit it
-    uint32_t n_dir;
-    int k, bucket_shift;         // bucket = hash >> bucket_shift
-};
-
-struct ReadDev {
-    uint64_t off;                // residue index of the read's first base inside the uploaded bytes
-    uint32_t len;
-    uint32_t nk;                 // sampled k-mers per strand
-    uint32_t km_base;            // index of the read's first forward k-mer; reverse ones follow at +nk
-};
-
-struct DdfHit {                  // what fill_init_hit_info leaves of a chain (chain_and_extend_kmer_matches.c:75-95)
-    int score, qbeg, qend;
-    int seg;
-    long long sbeg, send;
-};
 
 __device__ __forceinline__ uint64_t load_kmer(const uint8_t* __restrict__ pac, uint64_t pos, int k)
 {
@@ -296,36 +271,10 @@ template <class T> cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((voi
 // ---------------------------------------------------------------------------------------------
 // state
 // ---------------------------------------------------------------------------------------------
-struct lesvmap_state {
-    int k = 0, w = 0, max_occ = 0;
-    std::vector<lesvgpu_seq> sseqs;
-    uint64_t total_res = 0;            // end of the last contig
-    int soff_bits = 1;
-    uint64_t n_off = 0; uint32_t n_dir = 0; int bucket_bits = 0;
-    DevBuf<uint64_t> d_seq_off, d_off, d_dir_hash;
-    DevBuf<uint32_t> d_dir_start, d_bucket, d_qcount;
-    // batch buffers
-    DevBuf<uint8_t> d_qpac;
-    DevBuf<ReadDev> d_reads;
-    DevBuf<uint32_t> d_slot, d_mcnt, d_tmp, d_flag, d_segid, d_seg_start, d_seg_info, d_counter;
-    DevBuf<uint64_t> d_k0, d_v0, d_k1, d_v1;
-    DevBuf<lesvchain::Seed> d_seeds;
-    DevBuf<int> d_f, d_p, d_t, d_v;
-    DevBuf<lesvchain::IntPair> d_u;
-    DevBuf<DdfHit> d_hits;
-    // results of the last batch
-    int sorted_in = 0; uint32_t n_match = 0, n_seg = 0, n_kmer = 0;
-    std::vector<lesvgpu_subseq_hit> windows;
-    std::vector<int> win_first;
-    std::vector<lesvgpu_kmer_match> matches_host;
-    std::vector<lesvgpu_init_hit> init_hits;
-    std::vector<int> hit_first;
-    lesvgpu_map_timing tm = {};
-};
-
 void lesvmap_state_free(lesvmap_state* m)
 {
     if (!m) return;
+    if (m->ext) lesvmap_ext_free(m->ext);
     m->d_seq_off.release(); m->d_off.release(); m->d_dir_hash.release(); m->d_dir_start.release();
     m->d_bucket.release(); m->d_qcount.release(); m->d_qpac.release(); m->d_reads.release(); m->d_slot.release();
     m->d_mcnt.release(); m->d_tmp.release(); m->d_flag.release(); m->d_segid.release(); m->d_seg_start.release();
@@ -603,7 +552,9 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
     const uint64_t byte0 = qseqs[qfrom].seq_offset >> 2;
     const uint64_t byte1 = (qseqs[qto - 1].seq_offset + qseqs[qto - 1].seq_size + 3) >> 2;
     const size_t nbytes = (size_t)(byte1 - byte0);
-    std::vector<ReadDev> reads(nr);
+    std::vector<ReadDev>& reads = M->h_reads;
+    reads.assign(nr, ReadDev{});
+    M->qfrom = qfrom;
     uint64_t nkm = 0; uint32_t max_read_bytes = 0;
     for (int i = 0; i < nr; ++i) {
         const lesvgpu_seq& q = qseqs[qfrom + i];

@@ -19,9 +19,13 @@
 // smallest target prefix with the minimal distance (edlib.cpp:640-661 keeps positions in ascending
 // order and edlibAlign reports the first), accepted if <= k.
 //
-// Not restated yet (the candidate gets status kNeedsHirschberg / the overhang step is skipped and
-// flagged): edlib's Hirschberg path, taken when 20 B x blocks x columns + 8 B x columns >= 1 MB
-// (edlib.cpp:1175-1177), and the DALIGNER overhang extension (hbn_traceback.c:170-311).
+// Large problems (20 B x blocks x columns + 8 B x columns >= 1 MB, edlib.cpp:1175-1177) take edlib's
+// Hirschberg route (obtainAlignmentHirschberg, :1218-1383): split the target in the middle, pick the
+// FIRST query row whose forward + reverse scores add up to the distance, recurse; restated below with
+// an explicit stack.  The overhang step (hbn_traceback.c:170-311, 517-532) runs DALIGNER's adaptive
+// forward wave (Local_Alignment -> forward_wave, algo/align.c:386-1046) from the alignment's end to
+// find how far the overhang aligns, then edlib_nw over that range; the wave is restated without its
+// trace-point bookkeeping (only the end point and the difference count are consumed, dalign.c:88-107).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -47,6 +51,9 @@ struct Scratch {
     uint64_t* peq;          // [4][blocks]
     size_t cap_cells;       // block-columns that fit P/M/score
     size_t cap_peq;         // u64 words in peq
+    const int16_t* trim_table;   // DALIGNER TABLE / SCORE (New_Align_Spec, align.c:253-296), 32768 entries each
+    const int16_t* trim_score;
+    int path_ave;
 };
 constexpr int kBlkOpsCap = 4096;   // ops of one SHW block: <= 1123 + 1459 columns (get_next_sequence_block)
 
@@ -143,16 +150,93 @@ TRC_HD inline bool needs_hirschberg(int n, int m)
     return 20ll * nb * m + 8ll * m >= 1024 * 1024;
 }
 
+// Last column of the NW matrix of Q[0..n) x T[0..cols): D[i] = D(i, cols), i = 0..n.  Rolling columns:
+// uses sc.P[0..nb), sc.M[0..nb), sc.peq.
+template <class FQ, class FT>
+TRC_HD inline bool myers_last_column(FQ Q, int n, FT T, int cols, Scratch& sc, int* D)
+{
+    const int nb = (n + 63) >> 6;
+    if ((size_t)nb > sc.cap_cells || (size_t)4 * nb > sc.cap_peq) return false;
+    for (int x = 0; x < 4 * nb; ++x) sc.peq[x] = 0;
+    for (int i = 0; i < n; ++i) sc.peq[(size_t)Q(i) * nb + (i >> 6)] |= 1ull << (i & 63);
+    if (n & 63) {
+        const uint64_t pad = ~0ull << (n & 63);
+        for (int c = 0; c < 4; ++c) sc.peq[(size_t)c * nb + nb - 1] |= pad;
+    }
+    for (int b = 0; b < nb; ++b) { sc.P[b] = ~0ull; sc.M[b] = 0ull; }
+    for (int j = 0; j < cols; ++j) {
+        const uint64_t* eq = sc.peq + (size_t)T(j) * nb;
+        int hout = 1;
+        for (int b = 0; b < nb; ++b) hout = myers_block(sc.P[b], sc.M[b], eq[b], hout, sc.P[b], sc.M[b]);
+    }
+    D[0] = cols;
+    for (int i = 1; i <= n; ++i) {
+        const int b = (i - 1) >> 6, pos = (i - 1) & 63;
+        D[i] = D[i - 1] + (int)((sc.P[b] >> pos) & 1) - (int)((sc.M[b] >> pos) & 1);
+    }
+    return true;
+}
+
+// obtainAlignment (edlib.cpp:1148-1216) for Q[0..n) x T[0..m) with known distance `best`.
+template <class FQ, class FT>
+TRC_HD inline int obtain_alignment(FQ Q, int n, FT T, int m, int best, Scratch& sc, uint8_t* out, size_t out_cap)
+{
+    struct Frame { int q0, n, t0, m, best; };
+    Frame stack[48];
+    int top = 0;
+    size_t len = 0;
+    stack[top++] = Frame{0, n, 0, m, best};
+    while (top > 0) {
+        const Frame f = stack[--top];
+        if (len + (size_t)f.n + (size_t)f.m > out_cap) return kOpsOverflow;
+        if (f.n == 0 || f.m == 0) {                  // :1154-1161
+            for (int x = 0; x < f.n + f.m; ++x) out[len++] = f.n == 0 ? kOpDel : kOpIns;
+            continue;
+        }
+        auto fq = [&](int i) { return Q(f.q0 + i); };
+        auto ft = [&](int j) { return T(f.t0 + j); };
+        if (!needs_hirschberg(f.n, f.m)) {
+            int nb;
+            if (!myers_fill(fq, f.n, ft, f.m, sc, &nb)) return kScratchOverflow;
+            len += (size_t)myers_walk(sc, nb, f.n, f.m, out + len);
+            continue;
+        }
+        // obtainAlignmentHirschberg (:1218-1383)
+        if (2 * ((size_t)f.n + 1) > sc.cap_cells || top + 2 > 48) return kScratchOverflow;
+        const int lhw = f.m / 2, rhw = f.m - lhw;
+        int* L = sc.score;                            // L[i] = cost of Q[0..i) against the left half
+        int* R = sc.score + f.n + 1;                  // R[i] = cost of the LAST i bases against the right half
+        if (!myers_last_column(fq, f.n, ft, lhw, sc, L)) return kScratchOverflow;
+        auto rq = [&](int i) { return Q(f.q0 + f.n - 1 - i); };
+        auto rt = [&](int j) { return T(f.t0 + f.m - 1 - j); };
+        if (!myers_last_column(rq, f.n, rt, rhw, sc, R)) return kScratchOverflow;
+        int row = -2, ls = 0, rs = 0;
+        for (int r = 0; r <= f.n - 2; ++r)            // first interior row whose halves add up (:1300-1310)
+            if (L[r + 1] + R[f.n - r - 1] == f.best) { row = r; ls = L[r + 1]; rs = R[f.n - r - 1]; break; }
+        if (row == -2 && lhw + R[f.n] == f.best) { row = -1; ls = lhw; rs = R[f.n]; }            // :1312-1319
+        if (row == -2 && L[f.n] + rhw == f.best) { row = f.n - 1; ls = L[f.n]; rs = rhw; }        // :1320-1328
+        if (row == -2) return kNoAlign;
+        const int ul_h = row + 1;
+        stack[top++] = Frame{f.q0 + ul_h, f.n - ul_h, f.t0 + lhw, rhw, rs};     // lower right, emitted second
+        stack[top++] = Frame{f.q0, ul_h, f.t0, lhw, ls};                        // upper left first
+    }
+    return (int)len;
+}
+
 // edlib_nw (edlib_wrapper.c:32-111).  Returns ops appended (>= 0) or a negative Status.
 template <class FQ, class FT>
 TRC_HD inline int nw_path(FQ Q, int n, FT T, int m, Scratch& sc, uint8_t* out, size_t out_cap)
 {
     if (n == 0 || m == 0) return 0;                  // :43: "return 1" with both strings empty
     if ((size_t)n + (size_t)m > out_cap) return kOpsOverflow;
-    if (needs_hirschberg(n, m)) return kNeedsHirschberg;
-    int nb;
-    if (!myers_fill(Q, n, T, m, sc, &nb)) return kScratchOverflow;
-    return myers_walk(sc, nb, n, m, out);            // tolerance 0.5*max, then max: never fails (:58-72)
+    if (!needs_hirschberg(n, m)) {
+        int nb;
+        if (!myers_fill(Q, n, T, m, sc, &nb)) return kScratchOverflow;
+        return myers_walk(sc, nb, n, m, out);        // tolerance 0.5*max, then max: never fails (:58-72)
+    }
+    if ((size_t)n + 1 > sc.cap_cells) return kScratchOverflow;
+    if (!myers_last_column(Q, n, T, m, sc, sc.score)) return kScratchOverflow;
+    return obtain_alignment(Q, n, T, m, sc.score[n], sc, out, out_cap);
 }
 
 // edlib_shw (edlib_wrapper.c:114-190): 1 + ops in out, *tend = target bases consumed; 0 = no alignment
@@ -171,7 +255,7 @@ TRC_HD inline int shw_path(FQ Q, int n, FT T, int m, Scratch& sc, uint8_t* out, 
         if (v <= k && (best < 0 || v < best)) { best = v; bj = j; }
     }
     if (best < 0) return 0;
-    if (needs_hirschberg(n, bj)) return kNeedsHirschberg;
+    if (needs_hirschberg(n, bj)) return kNeedsHirschberg;     // cannot happen: blocks are <= 1459 x 1459
     *n_ops = myers_walk(sc, nb, n, bj, out);
     *tend = bj;
     return 1;
@@ -196,8 +280,11 @@ TRC_HD inline int extract_mems(FQ Q, FS S, const int* seed_w, const int* seed_r,
             int y = x;
             while (y < ml) { if (Q(ri) != S(wi)) break; ++ri; ++wi; ++y; }
             if (y - x >= word_size) {
-                if (n >= cap) return -1;
-                mems[n].len = y - x; mems[n].q = ri - (y - x); mems[n].s = wi - (y - x); ++n;
+                if (mems) {                            // mems == nullptr: count only
+                    if (n >= cap) return -1;
+                    mems[n].len = y - x; mems[n].q = ri - (y - x); mems[n].s = wi - (y - x);
+                }
+                ++n;
             }
             x = y;
         }
@@ -231,6 +318,154 @@ TRC_HD inline int trace_points(const Mem* seeds, int n, Mem* ts)
     return nt;
 }
 
+// ---- DALIGNER forward wave (align.c:386-1046) without trace points ---------------------------------
+constexpr int kTrimLen = 15, kPathLen = 60, kTrimMlag = 200, kWaveLag = 30;
+constexpr uint64_t kPathTop = 0x1000000000000000ull, kPathInt = 0x0fffffffffffffffull;
+constexpr int kTrimMask = 0x7fff;
+constexpr int kWaveHalf = 6000;                      // diagonals kept on either side of the start
+
+// New_Align_Spec(1 - 0.35, 100, {.25,.25,.25,.25}, 1) (dalign.c:16, align.c:253-296): tables and ave_path.
+// Host only; the device gets the filled tables.
+inline void dalign_tables(int16_t* table, int16_t* score, int* path_ave)
+{
+    const double ave_corr = 1.0 - 0.35, bias_factor = 1.000;     // match = .5 -> bias index 9
+    *path_ave = (int)(kPathLen * (1. - bias_factor * (1. - ave_corr)));
+    const int mscore = (int)(1000 * bias_factor * (1. - ave_corr)), dscore = 1000 - mscore;
+    // set_table (:246-259) unrolled: prefix bits are consumed most significant first
+    for (int prefix = 0; prefix <= kTrimMask; ++prefix) {
+        int sc = 0, mx = 0;
+        for (int bit = kTrimLen - 1; bit >= 0; --bit) {
+            if (sc > mx) mx = sc;
+            sc += ((prefix >> bit) & 1) ? mscore : -dscore;
+        }
+        table[prefix] = (int16_t)(sc - mx);
+        score[prefix] = (int16_t)sc;
+    }
+}
+
+// A(i), B(j): base codes, 4 outside [0, len) (the sentinels dalign_align puts around the copies).
+// Start at (0, 0) on diagonal 0.  V/M: 2*kWaveHalf+3 ints each, T: as many u64.  Returns false if the
+// wave leaves the diagonal window.
+template <class FA, class FB>
+TRC_HD inline bool dalign_forward(FA A, FB B, const Scratch& sc, int* Vb, int* Mb, uint64_t* Tb,
+                                  int* aepos, int* bepos, int* diffs)
+{
+    const int16_t* TABLE = sc.trim_table;
+    const int16_t* SCORE = sc.trim_score;
+    const int PATH_AVE = sc.path_ave;
+    int* V = Vb + kWaveHalf + 1; int* M = Mb + kWaveHalf + 1; uint64_t* T = Tb + kWaveHalf + 1;
+    const int IMAX = 0x7fffffff;
+    int hgh = 0, low = 0, dif = 0;
+    int more = 1, aclip = IMAX, bclip = -IMAX;
+    const int mida = 0;
+    int besta = mida, trima = mida, morea = mida, lasta = mida;
+    int besty = 0, trimy = 0, morey = 0;
+    int trimd = 0, mored = 0, morem = -1;
+    {
+        const int k = 0;
+        int y = 0;
+        for (;;) {
+            const int c = B(y);
+            if (c == 4) { more = 0; if (bclip < k) bclip = k; break; }
+            const int d = A(y + k);
+            if (c != d) { if (d == 4) { more = 0; aclip = k; } break; }
+            y += 1;
+        }
+        const int c = (y << 1) + k;
+        if (c > besta) { besta = trima = lasta = c; besty = trimy = y; }
+        V[k] = c; T[k] = kPathInt; M[k] = kPathLen;
+    }
+    auto clip_fix = [&]() {
+        if (B(besty) != 4 && A(besta - besty) != 4) more = 1;
+        if (hgh >= aclip) {
+            hgh = aclip - 1;
+            if (morem <= M[aclip]) { morem = M[aclip]; morea = V[aclip]; morey = (morea - aclip) / 2; mored = dif; }
+        }
+        if (low <= bclip) {
+            low = bclip + 1;
+            if (morem <= M[bclip]) { morem = M[bclip]; morea = V[bclip]; morey = (morea - bclip) / 2; mored = dif; }
+        }
+        aclip = IMAX; bclip = -IMAX;
+    };
+    if (more == 0) clip_fix();
+    while (more && lasta >= besta - kTrimMlag) {
+        low -= 1; hgh += 1;
+        if (low <= -kWaveHalf || hgh >= kWaveHalf) return false;
+        V[low] = -1;
+        int am = -1;
+        V[hgh] = -1;
+        dif += 1;
+        int ac = -1, ap;
+        V[hgh + 1] = V[low - 1] = -1;
+        uint64_t t = kPathInt;
+        int n = kPathLen;
+        for (int k = hgh; k >= low; --k) {
+            int c, m;
+            uint64_t b;
+            ap = ac; ac = am; am = V[k - 1];
+            if (ac < am) {
+                if (am < ap) { c = ap + 1; m = n; b = t; }
+                else { c = am + 1; m = M[k - 1]; b = T[k - 1]; }
+            } else {
+                if (ac < ap) { c = ap + 1; m = n; b = t; }
+                else { c = ac + 2; m = M[k]; b = T[k]; }
+            }
+            if ((b & kPathTop) != 0) m -= 1;
+            b <<= 1;
+            int y = (c - k) >> 1;
+            for (;;) {
+                const int cb = B(y);
+                if (cb == 4) { more = 0; if (bclip < k) bclip = k; break; }
+                const int d = A(y + k);
+                if (cb != d) { if (d == 4) { more = 0; aclip = k; } break; }
+                y += 1;
+                if ((b & kPathTop) == 0) m += 1;
+                b = (b << 1) | 1;
+            }
+            c = (y << 1) + k;
+            if (c > besta) {
+                besta = c; besty = y;
+                if (m >= PATH_AVE) {
+                    lasta = c;
+                    if (TABLE[b & kTrimMask] >= 0)
+                        if (TABLE[(b >> kTrimLen) & kTrimMask] + SCORE[b & kTrimMask] >= 0) { trima = c; trimy = y; trimd = dif; }
+                }
+            }
+            t = T[k]; n = M[k];
+            V[k] = c; T[k] = b; M[k] = m;
+        }
+        if (more == 0) clip_fix();
+        const int lim = besta - kWaveLag;
+        while (hgh >= low) {
+            if (V[hgh] < lim) hgh -= 1;
+            else { while (V[low] < lim) low += 1; break; }
+        }
+    }
+    int trimx;
+    if (morem >= 0) { trimx = morea - morey; trimy = morey; trimd = mored; }     // REACH = 1
+    else trimx = trima - trimy;
+    *aepos = trimx; *bepos = trimy; *diffs = trimd;
+    return true;
+}
+
+// overhang_extend (hbn_traceback.c:170-212): how far do Q and S align from (0,0) (dalign_align with
+// min_align_size 1, min_ident_perc 0.65), then edlib_nw over that range.  Returns ops written, 0 = the
+// reference's "return 0", < 0 = Status.
+template <class FQ, class FS>
+TRC_HD inline int overhang_extend(FQ Q, int qlen, FS S, int slen, Scratch& sc, uint8_t* out, size_t out_cap)
+{
+    if (sc.cap_cells < (size_t)(4 * kWaveHalf + 8)) return kScratchOverflow;
+    int* V = sc.score; int* M = sc.score + 2 * kWaveHalf + 4;
+    auto A = [&](int i) -> int { return (i >= 0 && i < qlen) ? (int)Q(i) : 4; };
+    auto B = [&](int j) -> int { return (j >= 0 && j < slen) ? (int)S(j) : 4; };
+    int qe = 0, se = 0, diffs = 0;
+    if (!dalign_forward(A, B, sc, V, M, sc.P, &qe, &se, &diffs)) return kScratchOverflow;
+    if (!(qe >= 1 && se >= 1)) return 0;                                  // dalign.c:92-94
+    const double ident = 100.0 - 200.0 * diffs / (qe + se);
+    if (!(ident >= 0.65)) return 0;
+    return nw_path(Q, qe, S, se, sc, out, out_cap);
+}
+
 // ---- the alignment under construction -----------------------------------------------------------
 struct Aln {
     uint8_t* ops; size_t cap;
@@ -243,7 +478,7 @@ struct Result {
     int qoff, qend, soff, send;
     int aln_len, n_match;
     size_t ops_beg;         // where the final ops start inside the candidate's ops buffer
-    int overhang_left, overhang_right;   // 1 = the reference would have tried the DALIGNER overhang step here
+    int overhang_left, overhang_right;   // 1 = the overhang step (left_extend / right_extend) ran its wave here
 };
 
 constexpr int kMatLen = 8, kMaxOverHang = 3000, kExtendBlock = 1024;
@@ -317,7 +552,7 @@ TRC_HD inline int extend(FQ Q, int qsize, FT T, int tsize, Scratch& sc, Emit emi
 template <class FQ, class FS>
 TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems, int n_mems, Mem* ts_buf,
                                Scratch& sc, uint8_t* ops, size_t cap, size_t front, uint8_t* blk,
-                               int min_align_size, double min_ident_perc)
+                               int min_align_size, double min_ident_perc, bool process_over_hang)
 {
     Result R;
     R.status = kNoAlign; R.qoff = R.qend = R.soff = R.send = 0; R.aln_len = 0; R.n_match = 0; R.ops_beg = 0;
@@ -421,13 +656,63 @@ TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems
         qend += qe; send += te;
     }
     if (beg == end) return R;
-    // overhang step (:517-532) not restated: flag where the reference would have run it
-    {
-        const int ls = qoff < soff ? qoff : soff;
-        R.overhang_left = ls > 0 && ls <= kMaxOverHang;
-        const int qrs = qsize - qend, srs = ssize - send;
-        const int rs = qrs < srs ? qrs : srs;
-        R.overhang_right = rs > 0 && rs <= kMaxOverHang;
+    // overhang step (:517-532, left_extend :214-266, right_extend :268-311)
+    if (process_over_hang) {
+        {
+            int qls = qoff, sls = soff;
+            const int ls = qls < sls ? qls : sls;
+            if (ls > 0 && ls <= kMaxOverHang) {
+                R.overhang_left = 1;
+                qls += kMatLen; sls += kMatLen;
+                auto fq = [&](int x) { return Q(qls - 1 - x); };
+                auto fs = [&](int x) { return S(sls - 1 - x); };
+                // the new columns replace the first kMatLen ones; they are written backwards in front of them
+                uint8_t* tmp = ops + end;                              // scratch room behind the alignment
+                const int r = overhang_extend(fq, qls, fs, sls, sc, tmp, cap - end);
+                if (r < 0) { R.status = r; return R; }
+                if (r > 0) {
+                    beg += kMatLen; qoff += kMatLen; soff += kMatLen;
+                    if ((size_t)r > beg) { R.status = kOpsOverflow; return R; }
+                    int qi = 0, si = 0;
+                    for (int x = 0; x < r; ++x) {
+                        const uint8_t op = tmp[x];
+                        ops[--beg] = op;
+                        if (op != kOpDel) ++qi;
+                        if (op != kOpIns) ++si;
+                    }
+                    qoff -= qi; soff -= si;
+                }
+            }
+        }
+        {
+            int qrs = qsize - qend, srs = ssize - send;
+            const int rs = qrs < srs ? qrs : srs;
+            if (rs > 0 && rs <= kMaxOverHang) {
+                R.overhang_right = 1;
+                qrs += kMatLen; srs += kMatLen;
+                const int q0 = qsize - qrs, s0 = ssize - srs;
+                auto fq = [&](int x) { return Q(q0 + x); };
+                auto fs = [&](int x) { return S(s0 + x); };
+                if (end < (size_t)kMatLen + beg) { R.status = kNoAlign; return R; }
+                uint8_t* dst = ops + end - kMatLen;
+                // the first kMatLen columns of the result re-align the last kMatLen ones: compute aside, then copy
+                uint8_t* tmp = ops + end;
+                const int r = overhang_extend(fq, qrs, fs, srs, sc, tmp, cap - end);
+                if (r < 0) { R.status = r; return R; }
+                if (r > 0) {
+                    qend -= kMatLen; send -= kMatLen; end -= kMatLen;
+                    int qi = 0, si = 0;
+                    for (int x = 0; x < r; ++x) {
+                        const uint8_t op = tmp[x];
+                        dst[x] = op;
+                        if (op != kOpDel) ++qi;
+                        if (op != kOpIns) ++si;
+                    }
+                    end += (size_t)r;
+                    qend += qi; send += si;
+                }
+            }
+        }
     }
     // calc_ident_perc (hbn_traceback_aux.c:4-19)
     int n_match = 0;

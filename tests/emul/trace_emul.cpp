@@ -11,11 +11,15 @@ namespace {
 struct Bufs {
     std::vector<uint64_t> P, M, peq;
     std::vector<int> score;
+    std::vector<int16_t> tt, ts;
     Scratch sc;
     explicit Bufs(size_t cells = 60000, size_t peq_words = 1 << 16) : P(cells), M(cells), peq(peq_words), score(cells)
     {
         sc.P = P.data(); sc.M = M.data(); sc.score = score.data(); sc.peq = peq.data();
         sc.cap_cells = cells; sc.cap_peq = peq_words;
+        tt.resize(32768); ts.resize(32768);
+        dalign_tables(tt.data(), ts.data(), &sc.path_ave);
+        sc.trim_table = tt.data(); sc.trim_score = ts.data();
     }
 };
 }
@@ -40,7 +44,7 @@ extern "C" int lesv_emul_mems(const uint8_t* read, const uint8_t* window, const 
 // res[0..8) = status, qoff, qend, soff, send, aln_len, n_match, overhang flags (left | right << 1);
 // ops_out receives the final ops (aln_len bytes)
 extern "C" void lesv_emul_traceback(const uint8_t* read, int qsize, const uint8_t* window, int ssize,
-                                    const int* mems3, int n_mems, int min_align_size, double min_ident,
+                                    const int* mems3, int n_mems, int min_align_size, double min_ident, int over_hang,
                                     int* res, uint8_t* ops_out)
 {
     Bufs B;
@@ -51,7 +55,7 @@ extern "C" void lesv_emul_traceback(const uint8_t* read, int qsize, const uint8_
     std::vector<uint8_t> ops(cap), blk(kBlkOpsCap);
     const Result R = traceback([&](int i) { return read[i]; }, qsize, [&](int j) { return window[j]; }, ssize,
                                mems.data(), n_mems, ts.data(), B.sc, ops.data(), cap, front < cap / 2 ? front : cap / 2,
-                               blk.data(), min_align_size, min_ident);
+                               blk.data(), min_align_size, min_ident, over_hang != 0);
     res[0] = R.status; res[1] = R.qoff; res[2] = R.qend; res[3] = R.soff; res[4] = R.send; res[5] = R.aln_len;
     res[6] = R.n_match; res[7] = R.overhang_left | (R.overhang_right << 1);
     if (R.status == kOk || R.aln_len > 0) memcpy(ops_out, ops.data() + R.ops_beg, (size_t)R.aln_len);

@@ -19,7 +19,7 @@ def emul():
     if "l" not in _e:
         _e["l"] = C.CDLL(os.path.join(H.ROOT, "tests", "emul", "libtrace_emul.so"))
         _e["l"].lesv_emul_traceback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                                C.c_double, C.c_void_p, C.c_void_p]
+                                                C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     return _e["l"]
 
 
@@ -85,6 +85,29 @@ def test_nw_path_equals_edlib():
         assert (a, b) == (ra, rb), (it, len(q), len(t))
 
 
+def test_nw_path_hirschberg_equals_edlib():
+    """Problems past edlib's 1 MB traceback limit go through its Hirschberg recursion."""
+    rng = np.random.default_rng(9)
+    lib = emul()
+    for it in range(14):
+        n = int(rng.integers(1900, 6000))
+        q = rng.integers(0, 4, n, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, float(rng.uniform(0.05, 0.3)), rng))
+        if it % 3 == 1:       # unrelated middle part
+            k = n // 3
+            t = np.ascontiguousarray(np.concatenate([t[:k], rng.integers(0, 4, 2500, dtype=np.uint8), t[k + 2000:]]))
+        if it % 3 == 2:       # low complexity: many co-optimal splits
+            q = rng.integers(0, 2, n, dtype=np.uint8)
+            t = np.ascontiguousarray(mutate(q, 0.2, rng) & 1)
+        assert 20 * ((len(q) + 63) // 64) * len(t) + 8 * len(t) >= 1 << 20
+        ops = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
+        cnt = lib.lesv_emul_nw(H._ptr(q), len(q), H._ptr(t), len(t), H._ptr(ops), len(ops))
+        assert cnt > 0, cnt
+        a, b, i, j = ops_to_strings(ops[:cnt], q, t)
+        ra, rb = ref_nw(q, t)
+        assert (a, b) == (ra, rb), (it, len(q), len(t))
+
+
 class RefMapper:
     """InitHitFindData + HbnTracebackData of the reference, driven like s_hbn_extend_subject_subseq_hit_list."""
 
@@ -123,8 +146,9 @@ class RefMapper:
             out.append((h.score, seeds, mems, sl))
         return out
 
-    def traceback(self, query, window, sl):
-        r = self.lib.hbn_traceback(self.tb, H._ptr(query), len(query), H._ptr(window), len(window), sl.a, int(sl.n), 100, 0.0, 0)
+    def traceback(self, query, window, sl, over_hang=0):
+        r = self.lib.hbn_traceback(self.tb, H._ptr(query), len(query), H._ptr(window), len(window), sl.a, int(sl.n), 100, 0.0,
+                                   over_hang)
         f = (C.c_int * 8).from_address(self.tb)
         qas = C.c_void_p.from_address(self.tb + 184).value
         qae = C.c_void_p.from_address(self.tb + 192).value
@@ -133,13 +157,13 @@ class RefMapper:
         return r, (f[0], f[1], f[3], f[4]), C.string_at(qas, n).decode() if n > 0 else "", C.string_at(sas, n).decode() if n > 0 else ""
 
 
-def emul_traceback(query, window, mems):
+def emul_traceback(query, window, mems, over_hang=0):
     lib = emul()
     m3 = np.ascontiguousarray(np.array(mems, dtype=np.int32).reshape(-1))
     res = np.zeros(8, dtype=np.int32)
     ops = np.zeros(3 * len(query) + 2 * len(window) + 4096, dtype=np.uint8)
     lib.lesv_emul_traceback(H._ptr(query), len(query), H._ptr(window), len(window), H._ptr(m3), len(mems), 100, 0.0,
-                            H._ptr(res), H._ptr(ops))
+                            over_hang, H._ptr(res), H._ptr(ops))
     return res, ops[:res[5]]
 
 
@@ -152,8 +176,8 @@ def emul_mems(query, window, seeds, cap):
     return [tuple(int(x) for x in out[3 * i:3 * i + 3]) for i in range(n)]
 
 
-@pytest.mark.parametrize("seed", [0, 1])
-def test_mems_and_traceback_equal_reference(seed):
+@pytest.mark.parametrize("seed,over_hang", [(0, 0), (1, 0), (2, 1), (3, 1)])
+def test_mems_and_traceback_equal_reference(seed, over_hang):
     rng = np.random.default_rng(40 + seed)
     R = RefMapper()
     n_ok = n_flag = 0
@@ -180,8 +204,8 @@ def test_mems_and_traceback_equal_reference(seed):
             assert emul_mems(query, window, seeds, len(mems) + 8) == mems, (it, "mems")
             if not mems:
                 continue
-            r, coords, qas, sas = R.traceback(query, window, sl)
-            res, ops = emul_traceback(query, window, mems)
+            r, coords, qas, sas = R.traceback(query, window, sl, over_hang)
+            res, ops = emul_traceback(query, window, mems, over_hang)
             assert res[0] in (0, 1), (it, res)
             assert int(res[0]) == int(r), (it, res, r)
             if r:
@@ -191,3 +215,4 @@ def test_mems_and_traceback_equal_reference(seed):
                 n_ok += 1
                 n_flag += int(res[7] != 0)
     assert n_ok >= 50
+    assert not over_hang or n_flag >= 20       # the overhang step really ran
