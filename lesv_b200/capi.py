@@ -315,12 +315,13 @@ def map_last_timing(ctx: "Context") -> MapTiming:
 
 
 def map_batch(ctx: "Context", query_pac, q_offsets, q_sizes, qfrom, qto, hitlist_size=3, max_hsps=5, want_ops=False,
-              min_ddfs=3):
+              min_ddfs=3, skip_overhang=False):
     """chain_and_extend for the reads [qfrom, qto): per read a list of dicts (HSP fields; `ops` = alignment
     columns as a uint8 array when want_ops)."""
     _bind_map(ctx.lib)
     query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
-    opts = MapOpts(min_ddfs=min_ddfs, hitlist_size=hitlist_size, max_hsps=max_hsps, want_ops=1 if want_ops else 0)
+    opts = MapOpts(min_ddfs=min_ddfs, hitlist_size=hitlist_size, max_hsps=max_hsps, want_ops=1 if want_ops else 0,
+                   skip_overhang=1 if skip_overhang else 0)
     h, first, pool = C.POINTER(Hsp)(), C.POINTER(C.c_int)(), C.POINTER(C.c_uint8)()
     rc = ctx.lib.lesvgpu_map_batch(ctx.h, query_pac.ctypes.data, _seq_array(q_offsets, q_sizes), qfrom, qto, C.byref(opts),
                                    C.byref(h), C.byref(first), C.byref(pool))

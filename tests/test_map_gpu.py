@@ -100,3 +100,67 @@ def test_candidates_against_fresh_reference_run(ctx, tmp_path, case):
         n += len(got)
     assert n >= Q.num_seqs // 2
     shutil.rmtree(work, ignore_errors=True)
+
+
+# ---- full mapping (lesvgpu_map_batch): HSPs and CIGARs -----------------------------------------------
+def m4_lines(res, Q, S):
+    """Format HSP dicts the way print_one_m4_result does with -cigar (mecat_results.c:27-62, 256-280;
+    note the role swap of print_cigar_core: a gap in the reference string prints as D)."""
+    lines = []
+    for i, lst in enumerate(res):
+        for h in lst:
+            qoff, qend = h["qoff"], h["qend"]
+            if h["qdir"] == 1:                      # dump_m4_hits, chain_and_extend_kmer_matches.c:325-330
+                qoff, qend = h["qsize"] - h["qend"], h["qsize"] - h["qoff"]
+            ident = 100.0 * h["n_match"] / h["aln_len"]
+            score = 8 * h["aln_len"] - h["n_match"]
+            ops, cg, a = h["ops"], [], 0
+            while a < len(ops):
+                b = a
+                while b < len(ops) and ops[b] == ops[a]:
+                    b += 1
+                cg.append(f"{b - a}{'MDI'[ops[a]]}")
+                a = b
+            lines.append(f"{Q.name(h['qid'])}\t{S.name(h['sid'])}\t{ident:g}\t{score}\t{h['qdir']}\t{qoff}\t{qend}\t{h['qsize']}"
+                         f"\t0\t{h['soff']}\t{h['send']}\t{h['ssize']}\tcg:Z:{''.join(cg)}\n")
+    return sorted(lines)
+
+
+def test_map_batch_equals_golden_m4_with_cigars(ctx):
+    from lesv_b200 import capi
+    S, Q = _load(ctx, os.path.join(GOLD, "db"))
+    res = capi.map_batch(ctx, Q.pac, Q.seq_offset, Q.seq_size, 0, Q.num_seqs, hitlist_size=5, max_hsps=10, want_ops=True)
+    exp = open(os.path.join(GOLD, "map.cigar.m4")).readlines()
+    got = m4_lines(res, Q, S)
+    assert len(exp) > 150
+    assert got == exp
+    tm = capi.map_last_extend_timing(ctx)
+    assert tm.n_unsupported == 0
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(H.ROOT, "oracle", "_ref", "bin", "qx2map")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["reads10k", "contigs5_svs", "skip_overhang"])
+def test_map_batch_against_fresh_reference_run(ctx, tmp_path, case):
+    import refmap
+    from lesv_b200 import capi, synth
+    work = str(tmp_path)
+    extra = []
+    if case == "reads10k":
+        synth.make_dataset(work, ref_len=1_000_000, n_reads=60, read_len=10000, n_events=20, seed=41)
+    elif case == "contigs5_svs":
+        synth.make_dataset(work, ref_len=1_500_000, n_reads=50, read_len=20000, n_events=30, seed=42, n_contigs=5,
+                           err_lo=0.08, err_hi=0.16)
+    else:
+        extra = ["-skip_overhang"]
+        synth.make_dataset(work, ref_len=600_000, n_reads=40, read_len=6000, n_events=10, seed=43, n_contigs=2)
+    refmap.run_qx2map(work, ["-cigar", "-max_target_seqs", "5", "-max_hsps", "10", "-db_dir", "db", "-keep_db"] + extra, "map.m4")
+    exp = sorted(open(os.path.join(work, "map.m4")).readlines())
+    S, Q = _load(ctx, os.path.join(work, "db"))
+    _bind = capi._bind_map(ctx.lib)
+    opts_skip = case == "skip_overhang"
+    res = capi.map_batch(ctx, Q.pac, Q.seq_offset, Q.seq_size, 0, Q.num_seqs, hitlist_size=5, max_hsps=10, want_ops=True,
+                         skip_overhang=opts_skip)
+    got = m4_lines(res, Q, S)
+    assert len(exp) >= Q.num_seqs // 2
+    assert got == exp
+    shutil.rmtree(work, ignore_errors=True)
