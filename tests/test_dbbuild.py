@@ -1,0 +1,66 @@
+"""The packed-database builder of the GPU qx2map driver (lesv_b200/host/lesv_dbbuild.hpp) against the
+reference's build_db (src/corelib/build_db.c): every file byte-identical, including ambiguous runs,
+lower case, gzip input and multi-volume splitting."""
+import filecmp
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+REFBIN = os.path.join(H.ROOT, "oracle", "_ref", "bin", "qx2map")
+pytestmark = pytest.mark.skipif(not os.path.exists(REFBIN), reason="oracle/_ref not built")
+
+
+def test_database_files_equal_reference(tmp_path):
+    rng = np.random.default_rng(3)
+    work = str(tmp_path)
+
+    def seq(n):
+        s = rng.integers(0, 4, n)
+        return "".join("ACGT"[x] for x in s)
+
+    reads = []
+    for i in range(40):
+        s = seq(int(rng.integers(600, 4000)))
+        if i % 5 == 1:
+            s = s[:100] + "N" * int(rng.integers(1, 30)) + s[100:300] + "RRYYN" + s[300:]
+        if i % 5 == 2:
+            s = s.lower()
+        reads.append((f"read{i} some description {i}", s))
+    with gzip.open(os.path.join(work, "reads.fa.gz"), "wt") as f:
+        for n, s in reads:
+            f.write(f">{n}\n")
+            for k in range(0, len(s), 70):
+                f.write(s[k:k + 70] + "\n")
+    with open(os.path.join(work, "ref.fa"), "w") as f:
+        for c in range(3):
+            f.write(f">chr{c}\n{seq(30000 + c)}\n")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    with open(os.path.join(work, "out.m4"), "wb") as out, open(os.path.join(work, "log"), "wb") as log:
+        subprocess.run([REFBIN, "-db_dir", "db_ref", "-keep_db", "-max_query_vol_res", "20k", "-max_subject_vol_res", "50k",
+                        "-num_threads", "1", "reads.fa.gz", "ref.fa"], cwd=work, check=True, stdout=out, stderr=log, env=env)
+    subprocess.run(["make", "-s", "-C", os.path.join(H.ROOT, "tests", "emul"), "dbbuild_tool"], check=True)
+    tool = os.path.join(H.ROOT, "tests", "emul", "dbbuild_tool")
+    os.makedirs(os.path.join(work, "db_ours"))
+    subprocess.run([tool, "reads.fa.gz", "db_ours", "query", "0", str(2**31 - 1), "20000"], cwd=work, check=True)
+    subprocess.run([tool, "ref.fa", "db_ours", "subject", "0", str(2**31 - 1), "50000"], cwd=work, check=True)
+    n = 0
+    for title in ("query", "subject"):
+        for ext in ("pac", "hdr", "seq_info", "ambig", "volume_info.bin", "volume_info.txt", "hbndb_is_built"):
+            a = os.path.join(work, "db_ref", f"{title}.{ext}")
+            b = os.path.join(work, "db_ours", f"{title}.{ext}")
+            if ext == "ambig":          # CAmbigSubseq{size_t; char; int}: the reference leaves the 3 padding bytes uninitialised
+                ra = np.fromfile(a, dtype=np.uint8).reshape(-1, 16)
+                rb = np.fromfile(b, dtype=np.uint8).reshape(-1, 16)
+                keep = [0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 14, 15]
+                assert ra.shape == rb.shape and np.array_equal(ra[:, keep], rb[:, keep]), title
+            else:
+                assert filecmp.cmp(a, b, shallow=False), (title, ext)
+            n += 1
+    assert n == 14
+    assert os.path.getsize(os.path.join(work, "db_ref", "query.volume_info.bin")) > 3 * 64      # several volumes
+    assert os.path.getsize(os.path.join(work, "db_ref", "query.ambig")) > 0
