@@ -49,6 +49,18 @@ struct Reader {
     std::vector<uint8_t> pac;
     std::vector<size_t> read_offset;     // residue offset + 1 (raw_read_offset_array)
 
+    void open_names(const std::string& db_dir, const std::string& title)      // headers only (qx2m4x)
+    {
+        const std::string base = db_dir + "/" + title + ".";
+        auto vi = read_file(base + "volume_info.bin", 0, sizeof(DbInfo));
+        if (vi.size() != sizeof(DbInfo)) die("bad volume_info.bin in " + db_dir);
+        memcpy(&info, vi.data(), sizeof(DbInfo));
+        auto si = read_file(base + "seq_info", 0, sizeof(SeqInfo) * (size_t)info.num_seqs);
+        seqs.resize(info.num_seqs);
+        memcpy(seqs.data(), si.data(), si.size());
+        auto h = read_file(base + "hdr", 0, info.hdr_offset_to);
+        names.assign(h.begin(), h.end());
+    }
     void open(const std::string& db_dir, const std::string& title)
     {
         const std::string base = db_dir + "/" + title + ".";

@@ -1,0 +1,123 @@
+"""The drop-in tools chained the way lesv.sh chains the reference's (src/scripts/lesv.sh:105-172):
+    qx2map -> qx2m4x -> qx2svr -> qx2svsig
+all four from lesv_b200/bin, against the committed golden run of the unmodified reference
+(tests/golden/svsig_small) and, when oracle/_ref travelled to the box, a fresh reference run with several
+query volumes and contigs.  qx2m4x alone (host I/O only) is checked without a GPU."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+GOLD = os.path.join(H.ROOT, "tests", "golden", "svsig_small")
+BIN = os.path.join(H.ROOT, "lesv_b200", "bin")
+REF_BIN = os.path.join(H.ROOT, "oracle", "_ref", "bin")
+
+
+def _m4x(path):
+    """M4Record[] without the 4 trailing padding bytes (the reference writes them uninitialised, m4x.cpp:53-58)."""
+    raw = np.fromfile(path, dtype=np.uint8).reshape(-1, 56)[:, :52]
+    return sorted(bytes(r) for r in raw)
+
+
+def _lines(path):
+    with open(path) as f:
+        return f.readlines()
+
+
+def test_qx2m4x_equals_reference_records(tmp_path):
+    subprocess.run(["make", "-s", "-C", os.path.join(H.ROOT, "lesv_b200", "csrc"), "../bin/qx2m4x"], check=True)
+    db = str(tmp_path / "db")
+    shutil.copytree(os.path.join(GOLD, "db"), db)
+    br = os.path.join(db, "backup_results")
+    name = "stagebackup_results_Q00000000_D00000000"
+    os.rename(os.path.join(br, name + ".m4x"), os.path.join(br, "expected.m4x"))
+    shutil.copy(os.path.join(GOLD, "map.m4"), os.path.join(br, name))
+    subprocess.run([os.path.join(BIN, "qx2m4x"), db], check=True, stderr=subprocess.DEVNULL)
+    got, exp = _m4x(os.path.join(br, name + ".m4x")), _m4x(os.path.join(br, "expected.m4x"))
+    assert len(exp) == 60 and got == exp
+    # a 13-column (-cigar) file must be refused like the reference's hbn_assert does (m4x.cpp:18)
+    with open(os.path.join(br, name), "a") as f:
+        f.write(_lines(os.path.join(GOLD, "map.m4"))[0].rstrip("\n") + "\tcg:Z:10M\n")
+    assert subprocess.run([os.path.join(BIN, "qx2m4x"), db], stderr=subprocess.DEVNULL).returncode != 0
+
+
+def _run_ours(work, map_args, threads="4"):
+    env = dict(os.environ)
+    with open(os.path.join(work, "gpu.map.m4"), "wb") as f, open(os.path.join(work, "gpu.log"), "ab") as log:
+        subprocess.run([os.path.join(BIN, "qx2map")] + map_args + ["-db_dir", "db_gpu", "-keep_db", "-num_threads", threads,
+                        "split.fa", "ref.fa"], cwd=work, check=True, stdout=f, stderr=log, env=env)
+        subprocess.run([os.path.join(BIN, "qx2m4x"), "db_gpu"], cwd=work, check=True, stderr=log)
+        subprocess.run([os.path.join(BIN, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", threads], cwd=work, check=True, stderr=log)
+        subprocess.run([os.path.join(BIN, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", threads], cwd=work, check=True, stderr=log)
+
+
+def _compare_pipeline(work, ref_db, ref_m4, ref_svr, ref_svsig):
+    assert sorted(_lines(os.path.join(work, "gpu.map.m4"))) == sorted(_lines(ref_m4))
+    n = 0
+    br = os.path.join(ref_db, "backup_results")
+    for f in sorted(os.listdir(br)):
+        if f.endswith(".m4x"):
+            exp = _m4x(os.path.join(br, f))
+            assert _m4x(os.path.join(work, "db_gpu", "backup_results", f)) == exp, f
+            n += len(exp)
+    for f in sorted(os.listdir(ref_svr)):
+        if f.endswith(".sv_read"):
+            a, b = _lines(os.path.join(ref_svr, f)), _lines(os.path.join(work, "svr_gpu", f))
+            assert (a == b) if f.startswith("subject_") else (sorted(a) == sorted(b)), f
+    n_sig = 0
+    for f in sorted(os.listdir(ref_svsig)):
+        if f.endswith(".sv_signature"):
+            ie, de = H.load_sv_signatures(os.path.join(ref_svsig, f))
+            ig, dg = H.load_sv_signatures(os.path.join(work, "svsig_gpu", f))
+            assert ie == ig and de == dg, f
+            n_sig += len(ie) + len(de)
+    return n, n_sig
+
+
+@pytest.mark.gpu
+def test_four_tools_reproduce_the_golden_run(tmp_path):
+    work = str(tmp_path)
+    shutil.copy(os.path.join(GOLD, "reads.fa"), os.path.join(work, "split.fa"))      # 4 kb reads: qx2splitseq is the identity
+    shutil.copy(os.path.join(GOLD, "ref.fa"), os.path.join(work, "ref.fa"))
+    _run_ours(work, ["-max_target_seqs", "5", "-max_hsps", "10"])
+    n, n_sig = _compare_pipeline(work, os.path.join(GOLD, "db"), os.path.join(GOLD, "map.m4"), os.path.join(GOLD, "svr"),
+                                 os.path.join(GOLD, "svsig"))
+    assert n == 60 and n_sig >= 5
+    # resume: a second run finds the .mapped sentinels and only re-emits the backup files (hbn_job_control.c:31-92)
+    first = _lines(os.path.join(work, "gpu.map.m4"))
+    with open(os.path.join(work, "again.m4"), "wb") as f:
+        subprocess.run([os.path.join(BIN, "qx2map"), "-max_target_seqs", "5", "-max_hsps", "10", "-db_dir", "db_gpu", "-keep_db",
+                        "split.fa", "ref.fa"], cwd=work, check=True, stdout=f, stderr=subprocess.DEVNULL)
+    assert _lines(os.path.join(work, "again.m4")) == first
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2map")), reason="oracle/_ref not built")
+def test_four_tools_against_fresh_reference_run_with_volumes(tmp_path):
+    """3 contigs, 150 x 12 kb reads at 10-15 %, planted 40 bp-3 kb INS/DEL, query database cut into volumes of
+    <= 400 kb and mapped in batches of 150 kb (the -max_query_vol_res / -query_batch_size surface)."""
+    sys.path.insert(0, os.path.join(H.ROOT, "tests", "golden"))
+    from lesv_b200 import synth
+    work = str(tmp_path)
+    synth.make_dataset(work, ref_len=900_000, n_reads=150, read_len=12000, n_events=18, seed=77, n_contigs=3,
+                       err_lo=0.10, err_hi=0.15, event_sizes=(40, 60, 100, 300, 1000, 3000))
+    shutil.copy(os.path.join(work, "reads.fa"), os.path.join(work, "split.fa"))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    args = ["-max_target_seqs", "5", "-max_hsps", "10", "-max_query_vol_res", "400k", "-query_batch_size", "150k"]
+    t = str(os.cpu_count() or 4)
+    with open(os.path.join(work, "ref.map.m4"), "wb") as f, open(os.path.join(work, "ref.log"), "ab") as log:
+        subprocess.run([os.path.join(REF_BIN, "qx2map")] + args + ["-db_dir", "db", "-keep_db", "-num_threads", "1", "split.fa", "ref.fa"],
+                       cwd=work, check=True, stdout=f, stderr=log, env=env)
+        subprocess.run([os.path.join(REF_BIN, "qx2m4x"), "db"], cwd=work, check=True, stdout=log, stderr=log, env=env)
+        subprocess.run([os.path.join(REF_BIN, "qx2svr"), "svr", "db", "3000", "70.0", "300", t], cwd=work, check=True, stdout=log, stderr=log, env=env)
+        subprocess.run([os.path.join(REF_BIN, "qx2svsig"), "svsig", "svr", "db", "40", t], cwd=work, check=True, stdout=log, stderr=log, env=env)
+    _run_ours(work, args)
+    n, n_sig = _compare_pipeline(work, os.path.join(work, "db"), os.path.join(work, "ref.map.m4"), os.path.join(work, "svr"),
+                                 os.path.join(work, "svsig"))
+    assert n >= 140 and n_sig >= 10
+    assert len([f for f in os.listdir(os.path.join(work, "db_gpu", "backup_results")) if f.endswith(".m4x")]) >= 4
