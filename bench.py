@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the lesv hot path on B200 (contract: see the task statement).
 
-Metric (BASELINE.json): GCUPS of the banded dual-affine DP (cells as ksw_extd2_sse counts them,
-reference src/algo/ksw2_extd2_sse.c:124-138) and aligned bases/s, per B200, on the SV-signature
-stage (qx2svsig) that consumes the mapper's alignments -- ~90 % of the reference's CPU time on
-this path.  Workload = BASELINE.json configs[1] shape: 50 kb subreads at 10-15 %
-ONT-like error against a 50 Mbp synthetic contig with planted 40 bp-10 kb INS/DEL; one *step* is
-one lesvgpu_svsig_batch call (the reference-facing C ABI; discover_func's body) over a batch of
-SvReads with HOST buffers.
+Metric (BASELINE.json): aligned bases/s and GCUPS per B200 on configs[1] -- 50 kb subreads at 10-15 %
+ONT-like error against a 50 Mbp synthetic contig with planted 40 bp-10 kb INS/DEL, "mapping + SV
+signatures on 1 B200".  One *step* takes one batch of reads through the whole hot path, calling the
+reference-facing C ABI (include/lesvgpu.h) with HOST buffers exactly as the drop-in tools do:
 
-  value      whole-job GCUPS with inputs resident (pack + DP/traceback kernels, CUDA events)
-  e2e        the same through the C ABI including H2D of the reads' .pac bytes and D2H of results
-  roofline   integer-issue roofline of ksw_dp_kernel, plus the HBM view
-  cpu_baseline / --impl reference : the reference's own nw_ksw2_extd2 (oracle/_ref/libhbn_ref.so,
-             compiled from the unmodified sources) on all host cores, bounded sample
+    lesvgpu_map_batch    qx2map   : seeding, chaining, candidate windows, MEM stage, edlib/DALIGNER alignment
+    (m4 text round trip) qx2m4x   : identity through its 6-significant-digit text, reverse-strand flip
+    lesvgpu_svr_batch    qx2svr   : one trusted placement per read (ksw2 re-alignment where HSPs compete/split)
+    lesvgpu_svsig_batch  qx2svsig : banded dual-affine DP + traceback + signature scan per placed read
+
+The subject .pac and its k-mer index are resident (built once per reference, outside the step, like the
+reference's per-volume build_lookup_table; the build time is reported as index_build_ms).
+
+  value      aligned read bases (sum of qend-qoff over emitted HSPs) / summed CUDA-event time of the GPU work
+             of all stages (inputs resident; host<->device copies and host logic excluded)
+  e2e        the same bases / wall time of the step: H2D of the packed reads, all host logic, D2H of results
+  gcups      DP cells (ksw_extd2_sse's count, reference src/algo/ksw2_extd2_sse.c:124-138) of the qx2svr +
+             qx2svsig alignments / their kernel time
+  roofline   integer-issue roofline of ksw_dp_kernel, the dominant kernel, plus the HBM view
+  cpu_baseline / --impl reference : the UNMODIFIED reference tools (oracle/_ref/bin, compiled from
+             /root/reference/src) on all host cores over a bounded sample of the same workload
 """
 from __future__ import annotations
 
@@ -21,8 +29,11 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,8 +47,9 @@ from lesv_b200 import synth  # noqa: E402
 READ_LEN = 50000
 REF_LEN = 50_000_000
 MIN_INDEL = 40
-OPS_PER_CELL = 46            # SURVEY.md §8d: scalar formulation of ksw2_extd2_sse.c:31-58,227-265,318-349
+OPS_PER_CELL = 46            # SURVEY.md 8d: scalar formulation of ksw2_extd2_sse.c:31-58,227-265,318-349
 LANES_PACKED = 2             # two DP cells per 32-bit integer instruction (16-bit lanes)
+METRIC = "aligned bases/s (qx2map + qx2svr + qx2svsig stages, C2)"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -57,49 +69,37 @@ def pack_pac(seqs):
     return pac.astype(np.uint8), np.asarray(offs, dtype=np.int64)
 
 
-def make_workload(n_reads: int, seed: int, read_len: int = READ_LEN, ref_len: int = REF_LEN, sv_frac: float = 0.2):
-    """C2-shaped SvRead batch: (reference contig, reads, SvRead tuples)."""
+def make_genomes(seed: int, ref_len: int = REF_LEN):
+    """(reference contig, sample genome): the sample carries INS/DEL of 40 bp-10 kb (log-uniform), ~1 per 250 kb."""
     rng = np.random.default_rng(seed)
     ref = synth.random_codes(ref_len, rng)
-    reads, svreads, pairs = [], [], []
-    for i in range(n_reads):
-        s = int(rng.integers(0, ref_len - read_len - 12000))
-        tgt_len = read_len
-        sample = ref[s:s + tgt_len]
-        sv = 0
-        if rng.random() < sv_frac:                   # ~1 event per 250 kb of read
-            size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
-            pos = int(rng.integers(2000, read_len - 2000))
-            if rng.random() < 0.5:                   # insertion in the sample
-                sample = np.concatenate([sample[:pos], synth.random_codes(size, rng), sample[pos:]])
-                sv = size
-            else:                                    # deletion in the sample: the window on the reference grows
-                tgt_len = read_len + size
-                sample = np.concatenate([ref[s:s + pos], ref[s + pos + size:s + tgt_len]])
-                sv = size
-        err = float(rng.uniform(0.10, 0.15))
-        read = synth.mutate(sample, err, rng)
-        qdir = int(rng.integers(0, 2))
-        fwd = synth.revcomp_codes(read) if qdir else read
-        qlen = len(read)
-        # identity as the mapper would report it (matches / alignment columns), 6 significant digits
-        cols = len(sample) * (1 + 0.3 * err) + sv
-        ident = float(f"{100.0 * len(sample) * (1 - 0.7 * err) / cols:.6g}")
-        dist = int((qlen + tgt_len) * (100.0 - ident) / 200.0)       # find_sv_reads.c:49
-        reads.append(np.ascontiguousarray(fwd))
-        svreads.append((i, 0, qdir, 0, qlen, qlen, s, s + tgt_len, dist))
-        pairs.append((np.ascontiguousarray(read), s, tgt_len, dist))
-    return ref, reads, svreads, pairs
+    n_events = max(1, ref_len // 250_000)
+    slot = ref_len // (n_events + 1)
+    pieces, prev = [], 0
+    for i in range(n_events):
+        pos = slot * (i + 1) + int(rng.integers(-slot // 8, slot // 8 + 1))
+        size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
+        pieces.append(ref[prev:pos])
+        if rng.random() < 0.5:
+            pieces.append(synth.random_codes(size, rng))         # insertion in the sample
+            prev = pos
+        else:
+            prev = pos + size                                     # deletion from the sample
+    pieces.append(ref[prev:])
+    return ref, np.concatenate(pieces)
 
 
-def band_of(qn, sn, dist):
-    """discover_func's band policy (find_sv_signature.c:272-316)."""
-    w = int(dist * 1.2)
-    if w == 0:
-        w = int(max(qn, sn) * 0.1)
-    if abs(qn - sn) > w:
-        w = max(qn, sn)
-    return w
+def make_reads(sample, n_reads: int, seed: int, read_len: int = READ_LEN):
+    """n_reads subreads of the sample genome, 10-15 % error (0.4 sub / 0.3 ins / 0.3 del), random strand."""
+    rng = np.random.default_rng(seed)
+    reads = []
+    for _ in range(n_reads):
+        s = int(rng.integers(0, len(sample) - read_len))
+        r = synth.mutate(sample[s:s + read_len], float(rng.uniform(0.10, 0.15)), rng)
+        if rng.integers(0, 2):
+            r = synth.revcomp_codes(r)
+        reads.append(np.ascontiguousarray(r))
+    return reads
 
 
 # ---------------------------------------------------------------------------------------------
@@ -146,81 +146,78 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the compiled reference's nw_ksw2_extd2 on all host cores
+# reference arm / cpu baseline: the unmodified reference tools on the host cores
 # ---------------------------------------------------------------------------------------------
-class KString(C.Structure):
-    _fields_ = [("l", C.c_size_t), ("m", C.c_size_t), ("s", C.c_void_p)]
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
-def _cpu_lib():
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "libhbn_ref.so")
-    if os.path.exists(ref_so):
-        lib = C.CDLL(ref_so)
-        lib.Ksw2DataNew.restype = C.c_void_p
-        lib.ksw2_extd2_set_params.argtypes = [C.c_void_p]
-        lib.nw_ksw2_extd2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
-        return "reference", lib
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
-    return "port", C.CDLL(os.path.join(ROOT, "oracle", "liblesv_oracle.so"))
+def reference_pipeline(ref, reads, cores: int):
+    """qx2map -> qx2m4x -> qx2svr -> qx2svsig of the compiled reference (oracle/_ref/bin) on `reads`.
+    Returns a dict of seconds per stage, aligned bases and signature count.  The mapping time is the
+    reference's own 'mapping query ...' timer (hbn_align_one_volume.c:124,141): database packing and the
+    index build are one-off costs per reference and are reported separately."""
+    work = tempfile.mkdtemp(prefix="lesv_ref_")
+    try:
+        synth.write_fasta(os.path.join(work, "ref.fa"), ["chr1"], [ref], width=0)
+        synth.write_fasta(os.path.join(work, "reads.fa"), [f"read{i}" for i in range(len(reads))], reads, width=0)
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        t = str(cores)
+        res = {}
+
+        def run(name, cmd, stdout=None):
+            t0 = time.perf_counter()
+            with open(os.path.join(work, name + ".log"), "wb") as log:
+                subprocess.run(cmd, cwd=work, check=True, env=env, stdout=stdout or log, stderr=log)
+            res[name + "_wall_s"] = time.perf_counter() - t0
+
+        with open(os.path.join(work, "map.m4"), "wb") as f:
+            run("qx2map", [os.path.join(REF_BIN, "qx2map"), "-max_target_seqs", "5", "-max_hsps", "10", "-db_dir", "db",
+                           "-keep_db", "-num_threads", t, "reads.fa", "ref.fa"], stdout=f)
+        log = open(os.path.join(work, "qx2map.log"), errors="replace").read()
+        res["map_s"] = sum(float(x) for x in re.findall(r"'mapping query [0-9 -]+' takes ([0-9.]+) secs", log))
+        if res["map_s"] <= 0:
+            res["map_s"] = res["qx2map_wall_s"]
+        run("qx2m4x", [os.path.join(REF_BIN, "qx2m4x"), "db"])
+        run("qx2svr", [os.path.join(REF_BIN, "qx2svr"), "svr", "db", "3000", "70.0", "300", t])
+        run("qx2svsig", [os.path.join(REF_BIN, "qx2svsig"), "svsig", "svr", "db", str(MIN_INDEL), t])
+        bases = 0
+        with open(os.path.join(work, "map.m4")) as f:
+            for line in f:
+                c = line.split("\t")
+                bases += int(c[6]) - int(c[5])
+        n_sig = 0
+        for fn in os.listdir(os.path.join(work, "svsig")):
+            if fn.endswith(".sv_signature"):
+                n_sig += sum(1 for _ in open(os.path.join(work, "svsig", fn)))
+        res["aligned_bases"] = bases
+        res["signatures"] = n_sig
+        res["path_s"] = res["map_s"] + res["qx2svr_wall_s"] + res["qx2svsig_wall_s"]
+        return res
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
-def cpu_align_pairs(kind, lib, jobs, n_threads):
-    """jobs: list of (query codes, target codes, band). Runs them on n_threads host threads
-    (ctypes releases the GIL). Returns wall seconds."""
-    it = iter(range(len(jobs)))
-    lock = threading.Lock()
-
-    def worker():
-        if kind == "reference":
-            data = lib.Ksw2DataNew()
-            lib.ksw2_extd2_set_params(data)
-            qa, sa = KString(), KString()
-            ints = [C.c_int() for _ in range(4)]
-            ident = C.c_double()
-        while True:
-            with lock:
-                i = next(it, None)
-            if i is None:
-                return
-            q, t, w = jobs[i]
-            if kind == "reference":
-                lib.nw_ksw2_extd2(data, 0, q.ctypes.data, 0, len(q), len(q), 0, t.ctypes.data, 0, len(t), len(t), 0,
-                                  C.c_double(0.0), w, *[C.addressof(x) for x in ints], C.addressof(ident),
-                                  C.addressof(qa), C.addressof(sa))
-            else:
-                outs = [C.c_int() for _ in range(4)]
-                ident2, n = C.c_double(), C.c_int()
-                pa, ps = C.c_void_p(), C.c_void_p()
-                lib.lesv_oracle_nw_ksw2_extd2(q.ctypes.data, 0, len(q), t.ctypes.data, 0, len(t), C.c_double(0.0), w,
-                                              *[C.byref(x) for x in outs], C.byref(ident2), C.byref(pa), C.byref(ps), C.byref(n))
-
-    ths = [threading.Thread(target=worker) for _ in range(n_threads)]
-    t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
-    return time.perf_counter() - t0
-
-
-def cpu_jobs_from(ref, pairs, k):
-    jobs = []
-    for read, s, tl, dist in pairs[:k]:
-        t = np.ascontiguousarray(ref[s:s + tl])
-        jobs.append((read, t, band_of(len(read), tl, dist)))
-    return jobs
+def cpu_baseline(ref, reads, cores):
+    if not os.path.exists(os.path.join(REF_BIN, "qx2map")):
+        return None
+    r = reference_pipeline(ref, reads, cores)
+    return {"value": r["aligned_bases"] / r["path_s"], "unit": "bases/s", "cores": cores, "kind": "reference",
+            "sample": f"{len(reads)} reads of the same workload through oracle/_ref/bin qx2map, qx2svr, qx2svsig on {cores} threads: "
+                      f"mapping {r['map_s']:.2f} s (the tool's own timer, without database/index build; whole qx2map "
+                      f"{r['qx2map_wall_s']:.2f} s), qx2svr {r['qx2svr_wall_s']:.2f} s, qx2svsig {r['qx2svsig_wall_s']:.2f} s",
+            "stages_s": {"map": r["map_s"], "svr": r["qx2svr_wall_s"], "svsig": r["qx2svsig_wall_s"]},
+            "signatures": r["signatures"]}
 
 
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=1184)
-    ap.add_argument("--no-sv", action="store_true", help="profiling aid: no planted INS/DEL (no cluster launches)")
+    ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -229,35 +226,36 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    config = {"workload": "C2: 50 Mbp synthetic contig, 50 kb subreads at 10-15 % error, planted 40 bp-10 kb INS/DEL; "
-                          "qx2svsig stage (banded dual-affine DP + traceback + signature scan)",
-              "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN, "min_indel": MIN_INDEL,
-              "l2": "inputs and traceback per step far exceed the 126 MB L2", "seed": args.seed}
+    config = {"workload": "C2: 50 Mbp synthetic contig, 50 kb subreads at 10-15 % error sampled from a genome with planted "
+                          "40 bp-10 kb INS/DEL (~1 per 250 kb); mapping + SvRead selection + SV signatures "
+                          "(-max_target_seqs 5 -max_hsps 10, SVR 3000/70.0/300, min indel 40)",
+              "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN, "ref_len": args.ref_len,
+              "l2": "each step streams new candidate windows and > 100 GB of traceback: far beyond the 126 MB L2",
+              "seed": args.seed}
 
-    # ---- reference arm: the reference's own CPU implementation on the host cores ------------------
+    # ---- reference arm: the reference's own CPU tools on the host cores --------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
-        kind, lib = _cpu_lib()
-        n_sample = max(cores, 8)
-        ref, reads, svreads, pairs = make_workload(n_sample, args.seed, ref_len=4_000_000)
-        jobs = cpu_jobs_from(ref, pairs, n_sample)
-        from lesv_b200 import capi
-        cells = sum(capi.ksw_cells(len(q), len(t), w)[0] for q, t, w in jobs)
-        bases = sum(len(q) for q, _, _ in jobs)
-        for _ in range(min(args.warmup, 1)):
-            cpu_align_pairs(kind, lib, jobs[:cores], cores)
-        times = [cpu_align_pairs(kind, lib, jobs, cores) for _ in range(max(1, min(args.steps, 3)))]
-        sec = sum(times) / len(times)
-        gcups = cells / sec / 1e9
-        line = {"impl": "reference", "metric": "GCUPS (banded dual-affine DP cells/s, qx2svsig stage)", "value": gcups,
-                "unit": "GCUPS", "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        ref, sample = make_genomes(args.seed, args.ref_len)
+        n_sample = max(4 * cores, 16)
+        K = max(1, min(args.steps, 2))
+        vals = []
+        base = None
+        for k in range(K):
+            base = cpu_baseline(ref, make_reads(sample, n_sample, args.seed + 77 + k), cores)
+            if base is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin is missing (make -C oracle ref needs /root/reference)"}))
+                return
+            vals.append(base)
+        v = sum(b["value"] for b in vals) / len(vals)
+        sec = sum(sum(b["stages_s"].values()) for b in vals) / len(vals)
+        base = dict(vals[-1], value=v)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus, "steps": K, "warmup": 0,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8", "data": "synthetic", "config": config,
-                "aligned_bases_per_s": bases / sec,
-                "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
-                                 "sample": f"{n_sample} reads of the same workload, nw_ksw2_extd2 on {cores} threads"},
-                "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "dtype": "int8", "data": "synthetic", "config": dict(config, reads_per_step_per_gpu=n_sample),
+                "cpu_baseline": base,
+                "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
@@ -271,22 +269,44 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ref, reads, svreads, pairs = make_workload(args.reads_per_step, args.seed + 1000 * rank,
-                                               sv_frac=0.0 if args.no_sv else 0.2)
+    ref, sample = make_genomes(args.seed, args.ref_len)                          # replicated on every GPU
+    reads = make_reads(sample, args.reads_per_step, args.seed + 1000 * (rank + 1))   # this rank's shard
     subject_pac, _ = pack_pac([ref])
     query_pac, qoffs = pack_pac(reads)
+    qsizes = np.array([len(r) for r in reads], dtype=np.int64)
     read_offset = (qoffs + 1).astype(np.uint64)
-    bands = [band_of(r[4] - r[3], r[7] - r[6], r[8]) for r in svreads]
-    cells = sum(capi.ksw_cells(r[4] - r[3], r[7] - r[6], w)[0] for r, w in zip(svreads, bands))
-    bases = sum(r[4] - r[3] for r in svreads)
-    tb_bytes = cells                                   # 1 traceback byte per cell, written once
+    seq_arr = capi._seq_array(qoffs, qsizes)
+    nq = len(reads)
 
     ctx = capi.Context(local_rank)
+    lib = ctx.lib
+    lib.lesvgpu_launch_count.restype = C.c_uint64
     capi.subject_load(ctx, subject_pac)
+    t0 = time.perf_counter()
+    capi.index_build(ctx, [0], [len(ref)], 15, 10, 200)
+    index_ms = (time.perf_counter() - t0) * 1e3
 
     def step():
-        per, sigs = capi.svsig_batch(ctx, query_pac, read_offset, 0, len(ref), svreads, MIN_INDEL)
-        return per, sigs, ctx.timing()
+        """one batch through the path; returns per-stage device ms, byte counts, work counts"""
+        h = capi.map_batch_raw(ctx, query_pac, seq_arr, 0, nq, hitlist_size=5, max_hsps=10)
+        mt, et = capi.map_last_timing(ctx), capi.map_last_extend_timing(ctx)
+        m4 = capi.hsps_to_m4(h)
+        svr, st = capi.svr_batch(ctx, query_pac, read_offset, [0], [len(ref)], m4, 3000, 70.0, 300)
+        t_svr = ctx.timing() if (st.n_refine_jobs or st.n_chain_jobs) else capi.Timing()
+        status, n_sig = capi.svsig_batch_raw(ctx, query_pac, read_offset, 0, len(ref), svr, MIN_INDEL)
+        t_sig = ctx.timing()
+        dev = {"map_seed_chain": mt.lookup_ms + mt.emit_ms + mt.sort_ms + mt.chain_ms,
+               "map_extend": et.ihf_ms + et.sort_ms + et.chain_ms + et.trace_ms,
+               "svr": t_svr.pack_ms + t_svr.dp_ms + t_svr.scan_ms,
+               "svsig": t_sig.pack_ms + t_sig.dp_ms + t_sig.scan_ms}
+        return {"dev": dev, "dp_ms": t_svr.dp_ms + t_sig.dp_ms, "sig_dp_ms": t_sig.dp_ms, "sig_cells": int(t_sig.dp_cells),
+                "cells": int(t_svr.dp_cells) + int(t_sig.dp_cells), "dp_launches": t_svr.dp_launches + t_sig.dp_launches,
+                "sig_launches": t_sig.dp_launches,
+                "h2d": int(mt.h2d_bytes + t_svr.h2d_bytes + t_sig.h2d_bytes),
+                "d2h": int(mt.d2h_bytes + et.d2h_bytes + t_svr.d2h_bytes + t_sig.d2h_bytes),
+                "bases": int((h["qend"] - h["qoff"]).sum()), "hsps": len(h), "sv_reads": len(svr),
+                "reads_ok": int((status == 1).sum()), "signatures": n_sig,
+                "svr_jobs": int(st.n_refine_jobs + st.n_chain_jobs)}
 
     def barrier():
         if world > 1:
@@ -296,37 +316,34 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    dev_ms = e2e_ms = dp_ms = 0.0
-    launches = dp_launches = 0
-    h2d = d2h = 0
-    n_sig = 0
+    acc = None
+    launches0 = lib.lesvgpu_launch_count()
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            per, sigs, tm = step()
-            dev_ms += tm.pack_ms + tm.dp_ms + tm.scan_ms
-            e2e_ms += tm.h2d_ms + tm.pack_ms + tm.dp_ms + tm.scan_ms + tm.d2h_ms
-            dp_ms += tm.dp_ms
-            launches += tm.kernel_launches
-            dp_launches += tm.dp_launches
-            h2d, d2h = tm.h2d_bytes, tm.d2h_bytes
-            n_sig = len(sigs)
+            r = step()
+            if acc is None:
+                acc = r
+            else:
+                for k in ("dp_ms", "sig_dp_ms", "sig_cells", "cells", "dp_launches", "sig_launches", "bases"):
+                    acc[k] += r[k]
+                for k in acc["dev"]:
+                    acc["dev"][k] += r["dev"][k]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-    n_ok = sum(1 for i in range(len(svreads)) if per[i].status == 1)
+    launches = lib.lesvgpu_launch_count() - launches0
+    dev_ms = sum(acc["dev"].values())
 
-    stats = torch.tensor([dev_ms, e2e_ms, wall_ms, dp_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(cells), float(bases)], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(acc["bases"]), float(acc["cells"]), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, wall_ms, dp_ms_max = [float(x) for x in stats.tolist()]
-    all_cells, all_bases = [float(x) for x in tot.tolist()]
+    dev_ms_max, wall_ms_max = [float(x) for x in stats.tolist()]
+    all_bases, all_cells, all_launches = [float(x) for x in tot.tolist()]
 
     if rank == 0:
         K = args.steps
-        value = all_cells * K / (dev_ms / 1e3) / 1e9
-        e2e_val = all_cells * K / (wall_ms / 1e3) / 1e9
         clocks = clk.summary()
         peaks = {}
         try:
@@ -336,38 +353,39 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         f_mhz = clocks["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        int_peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9      # GCUPS, SURVEY.md §8d
-        kern_gcups = cells * K / (dp_ms / 1e3) / 1e9                                # rank 0's kernel
+        int_peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9      # GCUPS, SURVEY.md 8d
+        kern_gcups = acc["sig_cells"] / (acc["sig_dp_ms"] / 1e3) / 1e9               # rank 0's qx2svsig DP kernel launches
         line = {
-            "metric": "GCUPS (banded dual-affine DP cells/s, qx2svsig stage)", "value": value, "unit": "GCUPS",
-            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms / K,
+            "metric": METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": config,
-            "aligned_bases_per_s": all_bases * K / (dev_ms / 1e3),
-            "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "device_event_value": all_cells * K / (e2e_ms / 1e3) / 1e9, "wall_ms_per_step": wall_ms / K,
-                    "aligned_bases_per_s": all_bases * K / (wall_ms / 1e3)},
-            "gpu_launches": int(launches),
+            "gcups": all_cells / (acc["dp_ms"] / 1e3) / 1e9 if world == 1 else None,
+            "e2e": {"value": all_bases / (wall_ms_max / 1e3), "unit": "bases/s", "h2d_bytes_per_step": r["h2d"],
+                    "d2h_bytes_per_step": r["d2h"], "wall_ms_per_step": wall_ms_max / K},
+            "gpu_launches": int(all_launches),
             "clocks": clocks,
+            "stages_ms_per_step": {k: v / K for k, v in acc["dev"].items()},
+            "stage_throughput": {"map_bases_per_s": acc["bases"] / ((acc["dev"]["map_seed_chain"] + acc["dev"]["map_extend"]) / 1e3),
+                                 "svr_svsig_gcups": acc["cells"] / (acc["dp_ms"] / 1e3) / 1e9},
             "roofline": {"bound": "int-issue", "kernel": "ksw_dp_kernel", "achieved": kern_gcups, "peak": int_peak,
                          "unit": "GCUPS", "frac": kern_gcups / int_peak,
                          "peak_def": f"{n_sm} SMs x 128 lanes x {f_mhz:.0f} MHz (median under load) / {OPS_PER_CELL} ops per cell x "
                                      f"{LANES_PACKED} cells per 32-bit op (SURVEY.md 8d)",
-                         "avg_launch_ms": dp_ms / max(1, dp_launches), "launches": int(dp_launches),
+                         "avg_launch_ms": acc["sig_dp_ms"] / max(1, acc["sig_launches"]), "launches": int(acc["sig_launches"]),
+                         "launch_note": "the launch classes of one batch run concurrently on side streams; achieved = cells of the "
+                                        "qx2svsig batch / CUDA-event time around all of its ksw_dp_kernel launches",
                          "traffic": None,
-                         "hbm": {"achieved": tb_bytes * K / (dp_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": tb_bytes * K / (dp_ms / 1e3) / 1e9 / hbm_peak,
+                         "hbm": {"achieved": kern_gcups, "peak": hbm_peak, "unit": "GB/s", "frac": kern_gcups / hbm_peak,
                                  "note": "1 traceback byte per DP cell, written once (of measured copy bandwidth)"}},
-            "reads_ok": n_ok, "signatures_per_step": n_sig,
+            "index_build_ms": index_ms,
+            "per_step": {k: r[k] for k in ("hsps", "sv_reads", "svr_jobs", "reads_ok", "signatures")},
         }
         if not args.no_cpu_baseline and world == 1:
-            kind, lib = _cpu_lib()
-            n_sample = max(cores, 8)
-            jobs = cpu_jobs_from(ref, pairs, n_sample)
-            c_cells = sum(capi.ksw_cells(len(q), len(t), w)[0] for q, t, w in jobs)
-            sec = cpu_align_pairs(kind, lib, jobs, cores)
-            line["cpu_baseline"] = {"value": c_cells / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
-                                    "sample": f"first {n_sample} reads of the step, nw_ksw2_extd2 on {cores} threads, {sec:.1f} s"}
+            n_sample = max(4 * cores, 16)
+            base = cpu_baseline(ref, reads[:n_sample], cores)
+            if base is not None:
+                line["cpu_baseline"] = base
         print(json.dumps(line))
     ctx.close()
     if world > 1:

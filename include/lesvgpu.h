@@ -48,8 +48,11 @@ typedef struct {
     int   dp_launches;       /* ksw_dp_kernel launches inside dp_ms                     */
     int   kernel_launches;   /* all kernels launched by the call                        */
     size_t h2d_bytes, d2h_bytes;
+    uint64_t dp_cells;       /* DP cells of all ksw_extd2 invocations of the call (lesvgpu_ksw_cells), failed-then-retried ones included */
 } lesvgpu_timing;
 void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t);
+/* Kernels this process has launched through the library so far (all contexts, all stages). */
+uint64_t lesvgpu_launch_count(void);
 
 /* ---- pairwise dual-affine banded global alignment ------------------------------------------
  * Stands in for
@@ -158,6 +161,43 @@ typedef struct {
 int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
                                const lesvgpu_refine_job* jobs, int n, lesvgpu_refine_result* results);
 
+typedef struct {            /* CSeqInfo.seq_offset / .seq_size, corelib/seqdb.h:20-27 */
+    uint64_t seq_offset;
+    uint64_t seq_size;
+} lesvgpu_seq;
+
+/* ---- qx2svr: one trusted placement per read ------------------------------------------------------
+ * lesvgpu_svr_batch stands in, over the M4Record array of one query volume, for the worker loop
+ *   thread_func -> get_next_m4a -> process_one_m4_list(M4Record* m4a, int m4c, vec_sv_read*, ...)
+ *                                                       app/necat2sv/find_sv_reads.c:750-760, 728-747, 705-725
+ * with min_seq_size / min_ident_perc / max_overhang = the tool's SVR_MIN_SEQ_SIZE, SVR_MIN_SVE_PERC_IDENTITY,
+ * SVR_MAX_OVERHANG arguments (:909-922).  Records of one read must be consecutive (qx2map writes them so).
+ * The selection logic runs on the host, its alignments (calc_m4_eff_perc_identity :130-164, s_chain_dual_m4s
+ * :341-430) on the GPU through lesvgpu_align_refine_batch.  *reads is library-owned, ordered by query id.
+ * lesvgpu_last_timing afterwards holds the sum over the alignment batches. */
+typedef struct {            /* M4Record, corelib/m4_record.h:11-24 (56 bytes with tail padding) */
+    int qid, qdir, qoff, qend, qsize;
+    int sid, sdir, soff, send, ssize;
+    double ident_perc;
+    int score;
+    int pad_;
+} lesvgpu_m4;
+
+typedef struct {
+    int min_seq_size;
+    double min_ident_perc;
+    int max_overhang;
+} lesvgpu_svr_opts;
+
+typedef struct {
+    size_t n_m4, n_refine_jobs, n_chain_jobs;
+} lesvgpu_svr_stats;
+
+int lesvgpu_svr_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
+                      const lesvgpu_seq* subject_seqs, int n_subject, const lesvgpu_m4* m4, size_t n_m4,
+                      const lesvgpu_svr_opts* opts, const char* trf_mask,
+                      const lesvgpu_svread** reads, int* n_reads, lesvgpu_svr_stats* stats);
+
 /* ---- qx2map, candidate stage: index, seeding, chaining, candidate windows ----------------------
  * lesvgpu_index_build stands in for
  *   LookupTable* build_lookup_table(const text_t* db, int kmer_size, int window_size,
@@ -168,11 +208,6 @@ int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const
  * The index stays in HBM; lesvgpu_index_export copies it out in the reference's layout
  * (LookupTable.offset_list, LktblKmerInfo{hash, offset_list_idx, cnt}) for parity checks.
  */
-typedef struct {            /* CSeqInfo.seq_offset / .seq_size, corelib/seqdb.h:20-27 */
-    uint64_t seq_offset;
-    uint64_t seq_size;
-} lesvgpu_seq;
-
 int lesvgpu_index_build(lesvgpu_ctx* ctx, const lesvgpu_seq* subject_seqs, int nseq,
                         int kmer_size, int kmer_window, int max_kmer_occ);
 int lesvgpu_index_stats(const lesvgpu_ctx* ctx, uint64_t* n_offsets, uint64_t* n_distinct);

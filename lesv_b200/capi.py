@@ -29,7 +29,8 @@ class KswResult(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("pack_ms", C.c_float), ("dp_ms", C.c_float),
                 ("scan_ms", C.c_float), ("d2h_ms", C.c_float), ("dp_launches", C.c_int),
-                ("kernel_launches", C.c_int), ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t)]
+                ("kernel_launches", C.c_int), ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t),
+                ("dp_cells", C.c_uint64)]
 
 
 _lib = None
@@ -183,6 +184,96 @@ def svsig_batch(ctx: "Context", query_pac: np.ndarray, query_read_offset: np.nda
     if rc != OK:
         raise RuntimeError(f"lesvgpu_svsig_batch failed ({rc}): {ctx.error()}")
     return per, [sigs[i].astuple() for i in range(n_sigs.value)]
+
+
+# ---- qx2svr (include/lesvgpu.h: lesvgpu_svr_batch) ------------------------------------------------------
+M4_DTYPE = np.dtype([(n, np.int32) for n in ("qid", "qdir", "qoff", "qend", "qsize", "sid", "sdir", "soff", "send", "ssize")] +
+                    [("ident_perc", np.float64), ("score", np.int32), ("pad_", np.int32)])          # M4Record, 56 bytes
+SVREAD_DTYPE = np.dtype([(n, np.int32) for n in ("query_id", "subject_id", "qdir", "qoff", "qend", "qsize", "soff", "send", "dist")])
+HSP_DTYPE = np.dtype([(n, np.int32) for n in ("qid", "qdir", "qoff", "qend", "qsize", "sid", "soff", "send")] +
+                     [("ssize", np.int64)] + [(n, np.int32) for n in ("aln_len", "n_match", "chain_score", "ddf_score")] +
+                     [("ops_off", np.uint64), ("flags", np.int32), ("pad_", np.int32)])            # lesvgpu_hsp, 72 bytes
+
+
+class SvrOpts(C.Structure):
+    _fields_ = [("min_seq_size", C.c_int), ("min_ident_perc", C.c_double), ("max_overhang", C.c_int)]
+
+
+class SvrStats(C.Structure):
+    _fields_ = [("n_m4", C.c_size_t), ("n_refine_jobs", C.c_size_t), ("n_chain_jobs", C.c_size_t)]
+
+
+def svr_batch(ctx: "Context", query_pac, query_read_offset, s_offsets, s_sizes, m4: np.ndarray, min_seq_size=3000,
+              min_ident=70.0, max_overhang=300, trf_mask=None):
+    """process_one_m4_list over the M4Record array (M4_DTYPE) of one query volume -> (SvRead array (SVREAD_DTYPE), stats)."""
+    lib = ctx.lib
+    lib.lesvgpu_svr_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Seq), C.c_int, C.c_void_p, C.c_size_t,
+                                      C.POINTER(SvrOpts), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(SvrStats)]
+    assert m4.dtype == M4_DTYPE and M4_DTYPE.itemsize == 56
+    m4 = np.ascontiguousarray(m4)
+    query_pac = np.ascontiguousarray(query_pac, dtype=np.uint8)
+    offs = np.ascontiguousarray(query_read_offset, dtype=np.uint64)
+    trf = None if trf_mask is None else np.ascontiguousarray(trf_mask, dtype=np.uint8)
+    opts = SvrOpts(min_seq_size, min_ident, max_overhang)
+    out, n, st = C.c_void_p(), C.c_int(), SvrStats()
+    rc = lib.lesvgpu_svr_batch(ctx.h, query_pac.ctypes.data, offs.ctypes.data, _seq_array(s_offsets, s_sizes), len(s_offsets),
+                               m4.ctypes.data, len(m4), C.byref(opts), None if trf is None else trf.ctypes.data,
+                               C.byref(out), C.byref(n), C.byref(st))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_svr_batch failed ({rc}): {ctx.error()}")
+    if n.value == 0:
+        return np.zeros(0, dtype=SVREAD_DTYPE), st
+    buf = (C.c_char * (n.value * SVREAD_DTYPE.itemsize)).from_address(out.value)
+    return np.frombuffer(buf, dtype=SVREAD_DTYPE).copy(), st
+
+
+def svsig_batch_raw(ctx: "Context", query_pac, query_read_offset, subject_seq_offset, subject_size, reads: np.ndarray,
+                    min_indel: int):
+    """lesvgpu_svsig_batch over a SVREAD_DTYPE array; returns (status array, n_signatures) without per-record Python work."""
+    _bind_svsig(ctx.lib)
+    reads = np.ascontiguousarray(reads)
+    assert reads.dtype == SVREAD_DTYPE
+    n = len(reads)
+    per = (SvSigRead * max(1, n))()
+    sigs, n_sigs = C.POINTER(SvSig)(), C.c_int()
+    rc = ctx.lib.lesvgpu_svsig_batch(ctx.h, query_pac.ctypes.data, query_read_offset.ctypes.data, subject_seq_offset, subject_size,
+                                     C.cast(reads.ctypes.data, C.POINTER(SvRead)), n, min_indel, None, per, C.byref(sigs), C.byref(n_sigs))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_svsig_batch failed ({rc}): {ctx.error()}")
+    status = np.frombuffer(per, dtype=np.int32).reshape(-1, 9)[:n, 0].copy()
+    return status, n_sigs.value
+
+
+def map_batch_raw(ctx: "Context", query_pac, seq_arr, qfrom, qto, hitlist_size=3, max_hsps=5):
+    """lesvgpu_map_batch -> HSP array (HSP_DTYPE); seq_arr from _seq_array()."""
+    _bind_map(ctx.lib)
+    opts = MapOpts(min_ddfs=3, hitlist_size=hitlist_size, max_hsps=max_hsps, want_ops=0)
+    h, first, pool = C.POINTER(Hsp)(), C.POINTER(C.c_int)(), C.POINTER(C.c_uint8)()
+    rc = ctx.lib.lesvgpu_map_batch(ctx.h, query_pac.ctypes.data, seq_arr, qfrom, qto, C.byref(opts), C.byref(h), C.byref(first),
+                                   C.byref(pool))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_map_batch failed ({rc}): {ctx.error()}")
+    n = first[qto - qfrom]
+    if n == 0:
+        return np.zeros(0, dtype=HSP_DTYPE)
+    assert C.sizeof(Hsp) == HSP_DTYPE.itemsize
+    buf = (C.c_char * (n * HSP_DTYPE.itemsize)).from_address(C.addressof(h.contents))
+    return np.frombuffer(buf, dtype=HSP_DTYPE).copy()
+
+
+def hsps_to_m4(h: np.ndarray) -> np.ndarray:
+    """What qx2map prints and qx2m4x parses back (print_one_m4_result, mecat_results.c:256-280; m4x.cpp:13-31):
+    reverse-strand query coordinates flipped, identity through its 6-significant-digit text."""
+    m = np.zeros(len(h), dtype=M4_DTYPE)
+    rev = h["qdir"] == 1
+    m["qid"], m["qdir"], m["qsize"] = h["qid"], h["qdir"], h["qsize"]
+    m["qoff"] = np.where(rev, h["qsize"] - h["qend"], h["qoff"])
+    m["qend"] = np.where(rev, h["qsize"] - h["qoff"], h["qend"])
+    m["sid"], m["soff"], m["send"], m["ssize"] = h["sid"], h["soff"], h["send"], h["ssize"]
+    ident = 100.0 * h["n_match"] / np.maximum(h["aln_len"], 1)
+    m["ident_perc"] = [float("%g" % x) for x in ident]
+    m["score"] = 8 * h["aln_len"] - h["n_match"]
+    return m
 
 
 # ---- qx2map candidate stage (include/lesvgpu.h: lesvgpu_index_build .. lesvgpu_map_candidates) --------

@@ -76,6 +76,7 @@ struct lesvgpu_ctx {
     PinBuf<lesvksw::KswOut> h_outs;
     PinBuf<lesvksw::KswGapRun> h_runs;
     std::vector<lesvgpu_svsig> sigs;
+    std::vector<lesvgpu_svread> svreads;          // result of lesvgpu_svr_batch
     lesvmap_state* map = nullptr;                 // index + scratch of the mapping stages
 };
 

@@ -1,6 +1,8 @@
 // gpu_prims.cu -- exclusive scan and stable LSD radix sort (see gpu_prims.cuh).
 #include "gpu_prims.cuh"
 
+unsigned long long g_lesv_launches = 0;
+
 namespace lesvmap {
 
 // ---------------------------------------------------------------------------------------------
@@ -84,13 +86,13 @@ void exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_
     }
     const size_t nb = (n + kScanTile - 1) / kScanTile;
     uint32_t* sums = d_tmp;
-    scan_local_kernel<<<(unsigned)nb, kScanThreads, 0, s>>>(d_in, d_out, n, sums);
+    scan_local_kernel<<<(unsigned)nb, kScanThreads, 0, s>>>(d_in, d_out, n, sums); ++g_lesv_launches;
     if (nb == 1) {
         if (d_total) cudaMemcpyAsync(d_total, sums, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
         return;
     }
     exclusive_scan_u32(sums, sums, nb, d_total, d_tmp + ((nb + 63) & ~(size_t)63), s);
-    scan_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_out, n, sums);
+    scan_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_out, n, sums); ++g_lesv_launches;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,9 +191,9 @@ int radix_sort_pairs(uint64_t* k0, uint64_t* v0, uint64_t* k1, uint64_t* v1, siz
         const uint32_t mask = (1u << bits) - 1u;
         uint64_t* ki = cur ? k1 : k0; uint64_t* vi = cur ? v1 : v0;
         uint64_t* ko = cur ? k0 : k1; uint64_t* vo = cur ? v0 : v1;
-        rs_hist_kernel<<<nblk, kRsThreads, 0, s>>>(ki, n, lo, mask, hist, nblk);
+        rs_hist_kernel<<<nblk, kRsThreads, 0, s>>>(ki, n, lo, mask, hist, nblk); ++g_lesv_launches;
         exclusive_scan_u32(hist, offs, (size_t)nblk * 256, nullptr, stmp, s);
-        rs_scatter_kernel<<<nblk, kRsThreads, 0, s>>>(ki, vi, ko, vo, n, lo, mask, offs, nblk);
+        rs_scatter_kernel<<<nblk, kRsThreads, 0, s>>>(ki, vi, ko, vo, n, lo, mask, offs, nblk); ++g_lesv_launches;
         cur ^= 1;
     }
     return cur;

@@ -9,6 +9,9 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+// kernels launched by the mapper stages of this process (lesvgpu_launch_count, include/lesvgpu.h)
+extern unsigned long long g_lesv_launches;
+
 namespace lesvmap {
 
 // out[i] = sum_{j<i} in[j]; returns nothing, the grand total lands in *d_total (may be null).

@@ -5,6 +5,7 @@
 // counts the DP kernel is instantiated for, each bin is sorted by decreasing traceback size and
 // pulled by persistent CTAs, and every CTA reuses one traceback arena in HBM.
 #include "ctx_internal.cuh"
+#include "gpu_prims.cuh"
 #include "ksw_core.cuh"
 
 #include <algorithm>
@@ -63,6 +64,7 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     delete ctx;
 }
 
+extern "C" uint64_t lesvgpu_launch_count(void) { return g_lesv_launches; }
 extern "C" const char* lesvgpu_last_error(const lesvgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t) { if (ctx && t) *t = ctx->timing; }
 
@@ -292,8 +294,10 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     T.scan_ms = 0.f;                                  // the scan runs inside the traceback walk
     T.dp_launches = (int)launches.size();
     T.kernel_launches = 1 + (int)launches.size();
+    g_lesv_launches += (unsigned long long)T.kernel_launches;
     T.h2d_bytes = raw_bytes + sizeof(KswJob) * nj + sizeof(int) * nj;
     T.d2h_bytes = d2h;
+    for (const KswJob& J : jobs) { int ok = 0; T.dp_cells += (uint64_t)lesvgpu_ksw_cells(J.qlen, J.tlen, J.w, &ok); }
     return LESVGPU_OK;
 }
 

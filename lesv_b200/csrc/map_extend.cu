@@ -460,7 +460,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         CK(cudaFuncSetAttribute(ihf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         ihf_kernel<<<ctas, kIhfThreads, smem_bytes, s>>>(E->d_wins.p, n_win, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, word, stride,
                                                          smem_words, E->d_gscratch.p, gstride, E->d_keys0.p, (uint32_t)seed_cap,
-                                                         E->d_counters.p, E->d_win_count.p, E->d_counters.p + 1);
+                                                         E->d_counters.p, E->d_win_count.p, E->d_counters.p + 1); ++g_lesv_launches;
         CK(cudaMemcpyAsync(&n_seeds, E->d_counters.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
@@ -481,7 +481,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
     CK(E->d_v.reserve(n_seeds)); CK(E->d_u.reserve(n_seeds)); CK(E->d_hs_w.reserve(n_seeds)); CK(E->d_hs_r.reserve(n_seeds));
     ChainBufs cb{E->d_seeds.p, E->d_f.p, E->d_p.p, E->d_t.p, E->d_v.p, E->d_u.p};
     ihf_chain_kernel<<<nblk(n_win, 64), 64, 0, s>>>(seed_keys, E->d_win_off.p, E->d_win_count.p, n_win, word, memsc_score, cb,
-                                                    E->d_hs_w.p, E->d_hs_r.p, E->d_cand_info.p, E->d_cand_cnt.p);
+                                                    E->d_hs_w.p, E->d_hs_r.p, E->d_cand_info.p, E->d_cand_cnt.p); ++g_lesv_launches;
     std::vector<int> cand_cnt(n_win);
     CK(cudaMemcpyAsync(cand_cnt.data(), E->d_cand_cnt.p, sizeof(int) * n_win, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ev[3], s));
@@ -524,7 +524,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         tb.pool = E->d_pool.p; tb.pool_cap = pool_cap; tb.pool_counter = E->d_pool_counter.p;
         trace_kernel<<<n_threads / kTraceThreadsPerBlock, kTraceThreadsPerBlock, 0, s>>>(
             E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_hs_w.p,
-            E->d_hs_r.p, word, min_align, opts->perc_identity, opts->skip_overhang ? 0 : 1, tb, E->d_outs.p, E->d_counters.p + 2);
+            E->d_hs_r.p, word, min_align, opts->perc_identity, opts->skip_overhang ? 0 : 1, tb, E->d_outs.p, E->d_counters.p + 2); ++g_lesv_launches;
         CK(cudaEventRecord(ev[4], s));
         CK(cudaMemcpyAsync(outs.data(), E->d_outs.p, sizeof(CandOut) * outs.size(), cudaMemcpyDeviceToHost, s));
         unsigned long long pool_used = 0;

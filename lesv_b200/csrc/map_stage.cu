@@ -330,16 +330,16 @@ extern "C" int lesvgpu_index_build(lesvgpu_ctx* ctx, const lesvgpu_seq* seqs, in
         CKI(dmalloc(&tmp, std::max(radix_tmp_words(nk), scan_tmp_words(nk))));
         CKI(dmalloc(&flag, nk)); CKI(dmalloc(&rid, nk)); CKI(dmalloc(&d_tot, 4));
         CKI(cudaMemcpyAsync(d_pre, pre.data(), sizeof(uint64_t) * (nseq + 1), cudaMemcpyHostToDevice, s));
-        index_extract_kernel<<<nblocks(nk, 256), 256, 0, s>>>(ctx->d_subject.p, M->d_seq_off.p, d_pre, nseq, kmer_size, kmer_window, nk, k0, v0);
+        index_extract_kernel<<<nblocks(nk, 256), 256, 0, s>>>(ctx->d_subject.p, M->d_seq_off.p, d_pre, nseq, kmer_size, kmer_window, nk, k0, v0); ++g_lesv_launches;
         const int where = radix_sort_pairs(k0, v0, k1, v1, nk, 0, 2 * kmer_size, tmp, s);
         uint64_t* K = where ? k1 : k0; uint64_t* V = where ? v1 : v0;
-        run_flag_kernel<<<nblocks(nk, 256), 256, 0, s>>>(K, nk, flag);
+        run_flag_kernel<<<nblocks(nk, 256), 256, 0, s>>>(K, nk, flag); ++g_lesv_launches;
         exclusive_scan_u32(flag, rid, nk, d_tot, tmp, s);
         CKI(cudaMemcpyAsync(&n_runs, d_tot, 4, cudaMemcpyDeviceToHost, s));
         CKI(cudaStreamSynchronize(s));
         CKI(dmalloc(&run_start, (size_t)n_runs + 1)); CKI(dmalloc(&kept_len, (size_t)n_runs + 1)); CKI(dmalloc(&kept_flag, (size_t)n_runs + 1));
-        run_start_kernel<<<nblocks(nk, 256), 256, 0, s>>>(flag, rid, nk, run_start);
-        run_keep_kernel<<<nblocks(n_runs, 256), 256, 0, s>>>(run_start, n_runs, (uint32_t)nk, (uint32_t)max_kmer_occ, kept_len, kept_flag);
+        run_start_kernel<<<nblocks(nk, 256), 256, 0, s>>>(flag, rid, nk, run_start); ++g_lesv_launches;
+        run_keep_kernel<<<nblocks(n_runs, 256), 256, 0, s>>>(run_start, n_runs, (uint32_t)nk, (uint32_t)max_kmer_occ, kept_len, kept_flag); ++g_lesv_launches;
         // exclusive scans in place: kept_len -> new_start, kept_flag -> new_idx (kept_flag is needed afterwards: copy first)
         uint32_t* keep_copy = nullptr;
         CKI(dmalloc(&keep_copy, (size_t)n_runs));
@@ -355,7 +355,7 @@ extern "C" int lesvgpu_index_build(lesvgpu_ctx* ctx, const lesvgpu_seq* seqs, in
         if (e3 == cudaSuccess) e3 = M->d_dir_start.reserve((size_t)M->n_dir + 2);
         if (e3 != cudaSuccess) { cudaFree(keep_copy); CKI(e3); }
         index_compact_kernel<<<nblocks(nk, 256), 256, 0, s>>>(K, V, nk, flag, rid, run_start, keep_copy, kept_len, kept_flag,
-                                                              M->d_off.p, M->d_dir_hash.p, M->d_dir_start.p);
+                                                              M->d_off.p, M->d_dir_hash.p, M->d_dir_start.p); ++g_lesv_launches;
         const uint32_t end = (uint32_t)M->n_off;
         cudaMemcpyAsync(M->d_dir_start.p + M->n_dir, &end, 4, cudaMemcpyHostToDevice, s);
         cudaStreamSynchronize(s);
@@ -377,7 +377,7 @@ extern "C" int lesvgpu_index_build(lesvgpu_ctx* ctx, const lesvgpu_seq* seqs, in
         cudaError_t e = dmalloc(&stmp, scan_tmp_words(nb));
         if (e != cudaSuccess) { cudaFree(cnt); CKI(e); }
         cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * nb, s);
-        if (M->n_dir) bucket_count_kernel<<<nblocks(M->n_dir, 256), 256, 0, s>>>(M->d_dir_hash.p, M->n_dir, 2 * kmer_size - bb, cnt);
+        if (M->n_dir) { bucket_count_kernel<<<nblocks(M->n_dir, 256), 256, 0, s>>>(M->d_dir_hash.p, M->n_dir, 2 * kmer_size - bb, cnt); ++g_lesv_launches; }
         exclusive_scan_u32(cnt, M->d_bucket.p, nb, nullptr, stmp, s);
         cudaMemsetAsync(M->d_qcount.p, 0, sizeof(uint32_t) * ((size_t)M->n_dir + 1), s);
         e = cudaStreamSynchronize(s);
@@ -588,8 +588,8 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
     uint32_t n_match = 0;
     if (nkm) {
         seed_kernel<0><<<2 * nr, 256, smem_cap, s>>>(M->d_qpac.p, M->d_reads.p, ix, smem_cap, M->d_slot.p, nullptr,
-                                                    (uint32_t)M->max_occ, M->soff_bits, nullptr, nullptr);
-        match_count_kernel<<<nblocks(nkm, 256), 256, 0, s>>>(M->d_slot.p, (uint32_t)nkm, ix, (uint32_t)M->max_occ, M->d_mcnt.p);
+                                                    (uint32_t)M->max_occ, M->soff_bits, nullptr, nullptr); ++g_lesv_launches;
+        match_count_kernel<<<nblocks(nkm, 256), 256, 0, s>>>(M->d_slot.p, (uint32_t)nkm, ix, (uint32_t)M->max_occ, M->d_mcnt.p); ++g_lesv_launches;
         exclusive_scan_u32(M->d_mcnt.p, M->d_mcnt.p, nkm, M->d_counter.p, M->d_tmp.p, s);
         CK(cudaMemcpyAsync(&n_match, M->d_counter.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -604,8 +604,8 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
         CK(M->d_k0.reserve(n_match)); CK(M->d_v0.reserve(n_match)); CK(M->d_k1.reserve(n_match)); CK(M->d_v1.reserve(n_match));
         CK(M->d_tmp.reserve(std::max(radix_tmp_words(n_match), scan_tmp_words((size_t)n_match + 1))));
         seed_kernel<1><<<2 * nr, 256, 0, s>>>(M->d_qpac.p, M->d_reads.p, ix, 0, M->d_slot.p, M->d_mcnt.p,
-                                              (uint32_t)M->max_occ, M->soff_bits, M->d_k0.p, M->d_v0.p);
-        qcount_reset_kernel<<<nblocks(nkm, 256), 256, 0, s>>>(M->d_slot.p, (uint32_t)nkm, M->d_qcount.p);
+                                              (uint32_t)M->max_occ, M->soff_bits, M->d_k0.p, M->d_v0.p); ++g_lesv_launches;
+        qcount_reset_kernel<<<nblocks(nkm, 256), 256, 0, s>>>(M->d_slot.p, (uint32_t)nkm, M->d_qcount.p); ++g_lesv_launches;
         CK(cudaEventRecord(ev[3], s));
         M->sorted_in = radix_sort_pairs(M->d_k0.p, M->d_v0.p, M->d_k1.p, M->d_v1.p, n_match, 0, M->soff_bits + ctx_bits, M->d_tmp.p, s);
         CK(cudaEventRecord(ev[4], s));
@@ -613,14 +613,14 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
         const uint64_t* V = M->sorted_in ? M->d_v1.p : M->d_v0.p;
         // segments
         CK(M->d_flag.reserve(n_match)); CK(M->d_segid.reserve(n_match));
-        seg_flag_kernel<<<nblocks(n_match, 256), 256, 0, s>>>(K, n_match, M->soff_bits, M->d_seq_off.p, (int)M->sseqs.size(), M->d_flag.p);
+        seg_flag_kernel<<<nblocks(n_match, 256), 256, 0, s>>>(K, n_match, M->soff_bits, M->d_seq_off.p, (int)M->sseqs.size(), M->d_flag.p); ++g_lesv_launches;
         exclusive_scan_u32(M->d_flag.p, M->d_segid.p, n_match, M->d_counter.p, M->d_tmp.p, s);
         CK(cudaMemcpyAsync(&n_seg, M->d_counter.p, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         M->n_seg = n_seg;
         if (n_seg > 0x3FFFFFF) { ctx->err = "more than 2^26 segments in one batch"; return LESVGPU_E_ARG; }
         CK(M->d_seg_start.reserve((size_t)n_seg + 1)); CK(M->d_seg_info.reserve(2 * (size_t)n_seg));
-        run_start_kernel<<<nblocks(n_match, 256), 256, 0, s>>>(M->d_flag.p, M->d_segid.p, n_match, M->d_seg_start.p);
+        run_start_kernel<<<nblocks(n_match, 256), 256, 0, s>>>(M->d_flag.p, M->d_segid.p, n_match, M->d_seg_start.p); ++g_lesv_launches;
         // chaining
         CK(M->d_seeds.reserve(n_match)); CK(M->d_f.reserve(n_match)); CK(M->d_p.reserve(n_match));
         CK(M->d_t.reserve(n_match)); CK(M->d_v.reserve(n_match)); CK(M->d_u.reserve(n_match));
@@ -631,7 +631,7 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
         ChainScratch sc{M->d_seeds.p, M->d_f.p, M->d_p.p, M->d_t.p, M->d_v.p, M->d_u.p};
         chain_kernel<<<nblocks(n_seg, 128), 128, 0, s>>>(K, V, M->d_seg_start.p, n_seg, n_match, M->soff_bits, M->d_seq_off.p,
                                                          (int)M->sseqs.size(), k, min_cnt, min_score, sc, M->d_hits.p, hit_cap,
-                                                         M->d_counter.p + 1, M->d_seg_info.p);
+                                                         M->d_counter.p + 1, M->d_seg_info.p); ++g_lesv_launches;
         CK(cudaEventRecord(ev[5], s));
         CK(cudaMemcpyAsync(&n_hits, M->d_counter.p + 1, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
