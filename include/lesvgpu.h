@@ -282,6 +282,9 @@ typedef struct {
     uint64_t n_unsupported;        /* candidates dropped because a step is not available on the GPU (0 today) */
     uint64_t n_overhang_skipped;   /* reserved (0)                                                             */
     size_t d2h_bytes;
+    float prep_ms, gap_ms, finish_ms;   /* inside trace_ms: MEMs + trace seeds, the edlib_nw gap alignments, assembly + end extension */
+    uint64_t n_gap_jobs;                /* gaps between trace seeds (one edlib_nw each) */
+    uint64_t n_gaps_class[4];           /* by size class: 1 block x <=128 columns, <=256, <=512 block-columns, larger / Hirschberg */
 } lesvgpu_extend_timing;
 
 /* lesvgpu_map_batch stands in, for the reads [qfrom, qto) of a query volume, for
@@ -303,6 +306,12 @@ int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac, const les
 int lesvgpu_map_last_init_hits(const lesvgpu_ctx* ctx, const lesvgpu_init_hit** hits, const int** first);
 int lesvgpu_map_last_matches(lesvgpu_ctx* ctx, int qfrom, const lesvgpu_kmer_match** matches, size_t* n);
 void lesvgpu_map_last_timing(const lesvgpu_ctx* ctx, lesvgpu_map_timing* t);
+
+/* Test hook: the warp-cooperative edlib_nw of the mapper's extension stage on one pair (residues 0..3):
+ * alignment columns as in lesvgpu_hsp.ops_off's pool (0 = both, 1 = query base over '-', 2 = '-' over target base),
+ * the output of edlib_nw (algo/edlib_wrapper.c:32-111).  ops_out: n + m bytes. */
+int lesvgpu_debug_edlib_nw(lesvgpu_ctx* ctx, const uint8_t* query, int n, const uint8_t* target, int m,
+                           uint8_t* ops_out, int* n_ops);
 
 /* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
  * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */

@@ -297,7 +297,8 @@ class Hsp(C.Structure):
 class ExtendTiming(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ihf_ms", "sort_ms", "chain_ms", "trace_ms", "d2h_ms")] + \
                [(n, C.c_uint64) for n in ("n_windows", "n_seeds", "n_candidates", "n_unsupported", "n_overhang_skipped")] + \
-               [("d2h_bytes", C.c_size_t)]
+               [("d2h_bytes", C.c_size_t)] + [(n, C.c_float) for n in ("prep_ms", "gap_ms", "finish_ms")] + \
+               [("n_gap_jobs", C.c_uint64), ("n_gaps_class", C.c_uint64 * 4)]
 
 
 class SubseqHit(C.Structure):

@@ -21,6 +21,7 @@
 #include "map_state.cuh"
 #include "gpu_prims.cuh"
 #include "trace_core.cuh"
+#include "trace_warp.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -217,81 +218,318 @@ ihf_chain_kernel(const uint64_t* __restrict__ seed_keys, const uint32_t* __restr
     cand_cnt[w] = nc;
 }
 
-struct TraceBufs {
+// ---- base-level alignment, three kernels ---------------------------------------------------------------
+// hbn_traceback spends its time in ~1 edlib_nw call per 40 bp (the gaps between trace seeds), and those calls
+// do not depend on each other.  So:
+//   trace_prep_kernel    one thread per candidate: MEMs, trace seeds, one GapJob per gap, queued by size class
+//   gap_small_kernel<C>  one thread per gap, Myers columns in (hardware-interleaved) local memory
+//   gap_big_kernel       the few gaps that need more than kSmallCells2 block-columns or edlib's Hirschberg
+//                        route: persistent threads with 1 MB slabs in HBM
+//   trace_finish_kernel  one thread per candidate: stitches seeds and gap alignments, trims, extends the ends
+//                        (edlib_extend), overhang step, identity -- trace_core.cuh's traceback_ts unchanged.
+struct GapJob {
+    int qa, n, sa, m;            // edlib_nw(Q[qa, qa+n), S[sa, sa+m))
+    uint32_t cand;               // index into cand_list
+    int len;                     // ops written (or a negative lesvtb::Status)
+    unsigned long long slot;     // first op in the slot pool (n + m bytes reserved)
+};
+
+struct CandPrep {
+    int n_mems, tsc, status;
+    uint32_t job_first;
+    unsigned long long mem_off;  // mems at mem_pool + mem_off, trace seeds right behind them
+};
+
+constexpr int kGapClasses = 4;                         // 3 local-memory classes + the big one
+constexpr int kSmallCells0 = 128, kSmallCells1 = 256, kSmallCells2 = 512;
+
+struct PrepBufs {
+    lesvtb::Mem* mem_pool; unsigned long long mem_cap; unsigned long long* mem_counter;
+    GapJob* jobs; uint32_t jobs_cap; uint32_t* job_counter;
+    unsigned long long slot_cap; unsigned long long* slot_counter;
+    uint32_t* queue[kGapClasses]; uint32_t* queue_count;        // queue_count[kGapClasses]
+};
+
+__device__ __forceinline__ int gap_class(int n, int m)
+{
+    const int nb = (n + 63) >> 6;
+    const long long cells = (long long)nb * m;
+    if (nb == 1 && m <= kSmallCells0) return 0;
+    if (nb <= 2 && cells <= kSmallCells1) return 1;
+    if (nb <= 8 && cells <= kSmallCells2) return 2;
+    return 3;
+}
+
+__global__ void __launch_bounds__(32)
+trace_prep_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
+                  const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, uint32_t n_cand,
+                  const int* __restrict__ cand_info, const int* __restrict__ hs_w, const int* __restrict__ hs_r, int word,
+                  PrepBufs pb, CandPrep* __restrict__ preps)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_cand) return;
+    const int c = cand_list[x];                       // = 3 * window + rank
+    const WinDev W = wins[c / kMaxCandPerWindow];
+    const ReadDev rd = reads[W.read];
+    const int* ci = cand_info + 3 * (size_t)c;
+    const int seed_off = ci[1], seed_cnt = ci[2];
+    auto Q = [&](int i) -> uint32_t {
+        return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)i)) : pac_code(qpac, rd.off + (uint32_t)i);
+    };
+    auto S = [&](int j) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)j); };
+    CandPrep P;
+    P.n_mems = 0; P.tsc = 0; P.status = lesvtb::kOk; P.job_first = 0; P.mem_off = 0;
+    // MEMs between the chain's seeds can outnumber the seeds: count, then take room from the pool
+    int n_mems = lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, (lesvtb::Mem*)nullptr, 0);
+    if (n_mems > 0) {
+        const unsigned long long need = 2ull * (unsigned)n_mems + 2;
+        const unsigned long long off = atomicAdd(pb.mem_counter, need);
+        if (off + need > pb.mem_cap) { P.status = lesvtb::kScratchOverflow; n_mems = 0; }
+        else {
+            lesvtb::Mem* mems = pb.mem_pool + off;
+            lesvtb::Mem* ts = mems + n_mems;
+            lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, mems, n_mems);
+            P.mem_off = off;
+            P.tsc = lesvtb::trace_points(mems, n_mems, ts);
+            const int n_jobs = P.tsc - 1;
+            unsigned long long bytes = 0;
+            lesvtb::enumerate_gaps(ts, P.tsc, [&](int, int, int n, int, int m) { bytes += (unsigned)(n + m); });
+            if (n_jobs > 0) {
+                const uint32_t j0 = atomicAdd(pb.job_counter, (uint32_t)n_jobs);
+                const unsigned long long s0 = atomicAdd(pb.slot_counter, bytes);
+                if ((unsigned long long)j0 + (unsigned)n_jobs > pb.jobs_cap || s0 + bytes > pb.slot_cap) P.status = lesvtb::kScratchOverflow;
+                else {
+                    P.job_first = j0;
+                    unsigned long long slot = s0;
+                    lesvtb::enumerate_gaps(ts, P.tsc, [&](int i, int qa, int n, int sa, int m) {
+                        GapJob J;
+                        J.qa = qa; J.n = n; J.sa = sa; J.m = m; J.cand = x; J.len = 0; J.slot = slot;
+                        slot += (unsigned)(n + m);
+                        pb.jobs[j0 + i] = J;
+                        if (n > 0 && m > 0) {                      // edlib_wrapper.c:43: nothing to align otherwise
+                            const int cls = gap_class(n, m);
+                            pb.queue[cls][atomicAdd(&pb.queue_count[cls], 1u)] = j0 + (uint32_t)i;
+                        }
+                    });
+                }
+            }
+        }
+    }
+    P.n_mems = n_mems;
+    preps[x] = P;
+}
+
+template <int CELLS, int CLS>
+__global__ void __launch_bounds__(128)
+gap_small_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
+                 const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, GapJob* __restrict__ jobs,
+                 const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queue_count, uint8_t* __restrict__ slots)
+{
+    uint64_t Pc[CELLS], Mc[CELLS], peq[4 * 8];
+    int score[CELLS];
+    lesvtb::Scratch sc;
+    sc.P = Pc; sc.M = Mc; sc.score = score; sc.peq = peq; sc.cap_cells = CELLS; sc.cap_peq = 32;
+    sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
+    const uint32_t n_jobs = queue_count[CLS];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_jobs; j += gridDim.x * blockDim.x) {
+        GapJob& J = jobs[queue[j]];
+        const WinDev W = wins[cand_list[J.cand] / kMaxCandPerWindow];
+        const ReadDev rd = reads[W.read];
+        const int qa = J.qa, sa = J.sa;
+        auto fq = [&](int i) -> uint32_t {
+            return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)(qa + i))) : pac_code(qpac, rd.off + (uint32_t)(qa + i));
+        };
+        auto fs = [&](int i) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)(sa + i)); };
+        J.len = lesvtb::nw_path(fq, J.n, fs, J.m, sc, slots + J.slot, (size_t)(J.n + J.m));
+    }
+}
+
+struct SlabBufs {
     uint64_t* P; uint64_t* M; int* score; uint64_t* peq;     // per thread slab
     size_t cells, peq_words;
+};
+
+// One warp per gap (trace_warp.cuh), persistent warps with a 1 MB slab each.
+__global__ void __launch_bounds__(128)
+gap_big_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
+               const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, GapJob* __restrict__ jobs,
+               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queue_count, uint8_t* __restrict__ slots,
+               SlabBufs sb, int8_t* __restrict__ carry_pool, size_t carry_stride, uint32_t* __restrict__ work_counter)
+{
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    lesvtb::Scratch sc;
+    sc.P = sb.P + warp * sb.cells; sc.M = sb.M + warp * sb.cells; sc.score = sb.score + warp * sb.cells;
+    sc.peq = nullptr; sc.cap_cells = sb.cells; sc.cap_peq = 0;
+    sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
+    int8_t* carry = carry_pool + warp * carry_stride;
+    const uint32_t n_jobs = queue_count[kGapClasses - 1];
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(work_counter, 1u);
+        j = __shfl_sync(0xFFFFFFFFu, j, 0);
+        if (j >= n_jobs) break;
+        GapJob& J = jobs[queue[j]];
+        const WinDev W = wins[cand_list[J.cand] / kMaxCandPerWindow];
+        const ReadDev rd = reads[W.read];
+        const int qa = J.qa, sa = J.sa, n = J.n, m = J.m;
+        auto fq = [&](int i) -> uint32_t {
+            return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)(qa + i))) : pac_code(qpac, rd.off + (uint32_t)(qa + i));
+        };
+        auto fs = [&](int i) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)(sa + i)); };
+        const int r = lesvtw::nw_path_warp(fq, n, fs, m, sc, carry, slots + J.slot, (size_t)(n + m));
+        if (lane == 0) J.len = r;
+        __syncwarp();
+    }
+}
+
+struct TraceBufs {
+    SlabBufs sb;
     uint8_t* ops; size_t ops_cap;                             // per thread working ops
     uint8_t* blk;                                             // per thread kBlkOpsCap
-    lesvtb::Mem* mem_pool; unsigned long long mem_cap; unsigned long long* mem_counter;   // MEMs + trace seeds of a candidate
+    const lesvtb::Mem* mem_pool;
+    const GapJob* jobs; const uint8_t* slots;
     uint8_t* pool; unsigned long long pool_cap; unsigned long long* pool_counter;
     const int16_t* trim_table; const int16_t* trim_score; int path_ave;
 };
 
-// Persistent threads, one alignment candidate at a time per thread (trace_core.cuh).
-__global__ void __launch_bounds__(kTraceThreadsPerBlock)
-trace_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
-             const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, uint32_t n_cand,
-             const int* __restrict__ cand_info, const int* __restrict__ hs_w, const int* __restrict__ hs_r, int word,
-             int min_align_size, double min_ident, int over_hang, TraceBufs tb, CandOut* __restrict__ outs,
-             uint32_t* __restrict__ work_counter)
+// Persistent warps, one alignment candidate at a time per warp.  The lanes stitch seeds and gap alignments
+// (prefix sum over the gap lengths), lane 0 runs the sequential end game (trace_core.cuh: finish_ends), the lanes
+// count the matches (calc_ident_perc) and copy the columns into the result pool.
+__global__ void __launch_bounds__(128)
+trace_finish_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
+                    const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, uint32_t n_cand,
+                    const int* __restrict__ cand_info, const CandPrep* __restrict__ preps,
+                    int min_align_size, double min_ident, int over_hang, TraceBufs tb, CandOut* __restrict__ outs,
+                    uint32_t* __restrict__ work_counter)
 {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     lesvtb::Scratch sc;
-    sc.P = tb.P + slot * tb.cells; sc.M = tb.M + slot * tb.cells; sc.score = tb.score + slot * tb.cells;
-    sc.peq = tb.peq + slot * tb.peq_words; sc.cap_cells = tb.cells; sc.cap_peq = tb.peq_words;
+    sc.P = tb.sb.P + warp * tb.sb.cells; sc.M = tb.sb.M + warp * tb.sb.cells; sc.score = tb.sb.score + warp * tb.sb.cells;
+    sc.peq = tb.sb.peq + warp * tb.sb.peq_words; sc.cap_cells = tb.sb.cells; sc.cap_peq = tb.sb.peq_words;
     sc.trim_table = tb.trim_table; sc.trim_score = tb.trim_score; sc.path_ave = tb.path_ave;
-    uint8_t* ops = tb.ops + slot * tb.ops_cap;
-    uint8_t* blk = tb.blk + slot * lesvtb::kBlkOpsCap;
+    uint8_t* ops = tb.ops + warp * tb.ops_cap;
+    uint8_t* blk = tb.blk + warp * lesvtb::kBlkOpsCap;
+    const size_t cap = tb.ops_cap;
     for (;;) {
-        const uint32_t x = atomicAdd(work_counter, 1u);
+        uint32_t x = 0;
+        if (lane == 0) x = atomicAdd(work_counter, 1u);
+        x = __shfl_sync(kFull, x, 0);
         if (x >= n_cand) break;
-        const int c = cand_list[x];                       // = 3 * window + rank
+        const int c = cand_list[x];
         const WinDev W = wins[c / kMaxCandPerWindow];
         const ReadDev rd = reads[W.read];
-        const int* ci = cand_info + 3 * (size_t)c;
-        const int seed_off = ci[1], seed_cnt = ci[2];
+        const CandPrep P = preps[x];
         auto Q = [&](int i) -> uint32_t {
             return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)i)) : pac_code(qpac, rd.off + (uint32_t)i);
         };
         auto S = [&](int j) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)j); };
         CandOut o;
         memset(&o, 0, sizeof o);
-        o.chain_score = ci[0];
-        // MEMs between the chain's seeds can outnumber the seeds: count, then take room from the pool
-        int n_mems = lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, (lesvtb::Mem*)nullptr, 0);
-        lesvtb::Mem* mems = nullptr;
-        lesvtb::Mem* ts = nullptr;
-        if (n_mems > 0) {
-            const unsigned long long need = 2ull * (unsigned)n_mems + 2;
-            const unsigned long long off = atomicAdd(tb.mem_counter, need);
-            if (off + need > tb.mem_cap) n_mems = -1;
-            else {
-                mems = tb.mem_pool + off; ts = mems + n_mems;
-                lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, mems, n_mems);
-            }
-        }
-        o.n_mems = n_mems;
-        if (n_mems > 0) {
+        o.chain_score = cand_info[3 * (size_t)c];
+        o.n_mems = P.status == lesvtb::kOk ? P.n_mems : -1;
+        if (P.status != lesvtb::kOk) o.status = P.status;
+        else if (P.n_mems > 0) {
+            const lesvtb::Mem* mems = tb.mem_pool + P.mem_off;
+            const lesvtb::Mem* ts = mems + P.n_mems;
+            const int n_mems = P.n_mems, tsc = P.tsc, n_gaps = P.tsc - 1;
             o.mem_qbeg = mems[0].q; o.mem_sbeg = mems[0].s;
             o.mem_qend = mems[n_mems - 1].q + mems[n_mems - 1].len; o.mem_send = mems[n_mems - 1].s + mems[n_mems - 1].len;
             const int q0 = mems[0].q, s0 = mems[0].s;
             size_t front = (size_t)q0 + (size_t)s0 + 8;
             const size_t alt = (size_t)(2.5 * q0) + 512;
             if (alt < front) front = alt;
-            if (front > tb.ops_cap / 2) front = tb.ops_cap / 2;
-            const lesvtb::Result R = lesvtb::traceback(Q, (int)rd.len, S, (int)W.wlen, mems, n_mems, ts, sc, ops, tb.ops_cap, front,
-                                                       blk, min_align_size, min_ident, over_hang != 0);
-            o.status = R.status; o.qoff = R.qoff; o.qend = R.qend; o.soff = R.soff; o.send = R.send;
-            o.aln_len = R.aln_len; o.n_match = R.n_match; o.flags = R.overhang_left | (R.overhang_right << 1);
-            if (R.status == lesvtb::kOk) {
-                const unsigned long long off = atomicAdd(tb.pool_counter, (unsigned long long)R.aln_len);
-                o.ops_off = off;
-                if (off + (unsigned long long)R.aln_len <= tb.pool_cap)
-                    for (int a = 0; a < R.aln_len; ++a) tb.pool[off + a] = ops[R.ops_beg + a];
-                else o.status = lesvtb::kOpsOverflow;
+            if (front > cap / 2) front = cap / 2;
+            // ---- stitch (hbn_traceback.c:338-390): first seed, then gap i and seed i+1 for every gap ----------
+            const int E = 10, E2 = 20;
+            const lesvtb::Mem first = ts[0], last = ts[tsc - 1];
+            int head = first.len > E2 ? first.len - E : 0;
+            if (n_gaps == 0) head += first.len > E2 ? E : first.len;
+            int err = 0;
+            size_t pos = front;
+            if (pos + (size_t)head > cap) err = lesvtb::kOpsOverflow;
+            else {
+                for (int a = lane; a < head; a += 32) ops[pos + a] = lesvtb::kOpDiag;
+                pos += (size_t)head;
             }
-        } else if (n_mems < 0) o.status = lesvtb::kScratchOverflow;
-        outs[c] = o;
+            const GapJob* jobs = tb.jobs + P.job_first;
+            for (int base = 0; base < n_gaps && err == 0; base += 32) {
+                const int i = base + lane;
+                int glen = 0, dafter = 0, my_err = 0;
+                unsigned long long slot = 0;
+                if (i < n_gaps) {
+                    const GapJob J = jobs[i];
+                    glen = J.len; slot = J.slot;
+                    if (glen < 0) { my_err = glen; glen = 0; }
+                    const lesvtb::Mem sj = ts[i + 1];
+                    dafter = sj.len > E2 ? sj.len - 2 * E : 0;
+                    if (i == n_gaps - 1) dafter += sj.len > E2 ? E : sj.len - sj.len / 2;
+                }
+                const int tot = glen + dafter;
+                int incl = tot;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += v; }
+                const int warp_tot = __shfl_sync(kFull, incl, 31);
+                const unsigned errs = __ballot_sync(kFull, my_err != 0);
+                if (errs) { err = __shfl_sync(kFull, my_err, __ffs(errs) - 1); break; }
+                if (pos + (size_t)warp_tot > cap) { err = lesvtb::kOpsOverflow; break; }
+                uint8_t* dst = ops + pos + (size_t)(incl - tot);
+                const uint8_t* src = tb.slots + slot;
+                for (int a = 0; a < glen; ++a) dst[a] = src[a];
+                for (int a = 0; a < dafter; ++a) dst[glen + a] = lesvtb::kOpDiag;
+                pos += (size_t)warp_tot;
+            }
+            __syncwarp();
+            if (err) o.status = err;
+            else {
+                // ---- trim, extend, overhang: sequential, lane 0 ------------------------------------------------
+                lesvtb::Result R;
+                R.status = lesvtb::kNoAlign; R.qoff = R.qend = R.soff = R.send = 0; R.aln_len = 0; R.n_match = 0; R.ops_beg = 0;
+                R.overhang_left = R.overhang_right = 0;
+                if (lane == 0)
+                    R = lesvtb::finish_ends(Q, (int)rd.len, S, (int)W.wlen, sc, ops, cap, front, pos, first.q, last.q + last.len,
+                                            first.s, last.s + last.len, blk, over_hang != 0);
+                __syncwarp();
+                R.status = __shfl_sync(kFull, R.status, 0);
+                R.qoff = __shfl_sync(kFull, R.qoff, 0); R.qend = __shfl_sync(kFull, R.qend, 0);
+                R.soff = __shfl_sync(kFull, R.soff, 0); R.send = __shfl_sync(kFull, R.send, 0);
+                R.aln_len = __shfl_sync(kFull, R.aln_len, 0);
+                R.ops_beg = (size_t)__shfl_sync(kFull, (unsigned)R.ops_beg, 0);
+                R.overhang_left = __shfl_sync(kFull, R.overhang_left, 0); R.overhang_right = __shfl_sync(kFull, R.overhang_right, 0);
+                if (R.status == lesvtb::kOk) {
+                    // ---- calc_ident_perc: 32 columns per step, positions from ballots -------------------------
+                    int n_match = 0, qb = R.qoff, sb = R.soff;
+                    const uint8_t* al = ops + R.ops_beg;
+                    for (int a = 0; a < R.aln_len; a += 32) {
+                        const bool valid = a + lane < R.aln_len;
+                        const uint8_t op = valid ? al[a + lane] : (uint8_t)255;
+                        const unsigned bq = __ballot_sync(kFull, valid && op != lesvtb::kOpDel);
+                        const unsigned bs = __ballot_sync(kFull, valid && op != lesvtb::kOpIns);
+                        bool same = false;
+                        if (valid && op == lesvtb::kOpDiag) same = Q(qb + __popc(bq & lt_mask)) == S(sb + __popc(bs & lt_mask));
+                        n_match += __popc(__ballot_sync(kFull, same));
+                        qb += __popc(bq); sb += __popc(bs);
+                    }
+                    lesvtb::finalize_stats(R, n_match, min_align_size, min_ident);
+                }
+                o.status = R.status; o.qoff = R.qoff; o.qend = R.qend; o.soff = R.soff; o.send = R.send;
+                o.aln_len = R.aln_len; o.n_match = R.n_match; o.flags = R.overhang_left | (R.overhang_right << 1);
+                if (R.status == lesvtb::kOk) {
+                    unsigned long long off = 0;
+                    if (lane == 0) off = atomicAdd(tb.pool_counter, (unsigned long long)R.aln_len);
+                    off = __shfl_sync(kFull, off, 0);
+                    o.ops_off = off;
+                    if (off + (unsigned long long)R.aln_len <= tb.pool_cap)
+                        for (int a = lane; a < R.aln_len; a += 32) tb.pool[off + a] = ops[R.ops_beg + a];
+                    else o.status = lesvtb::kOpsOverflow;
+                }
+            }
+        }
+        if (lane == 0) outs[c] = o;
+        __syncwarp();
     }
 }
 
@@ -315,6 +553,13 @@ struct lesvmap_ext {
     DevBuf<uint8_t> d_ops, d_blk, d_pool;
     DevBuf<unsigned long long> d_pool_counter;
     DevBuf<CandOut> d_outs;
+    DevBuf<GapJob> d_jobs;
+    DevBuf<uint32_t> d_queue;
+    DevBuf<uint8_t> d_slots;
+    DevBuf<CandPrep> d_preps;
+    DevBuf<int8_t> d_carry;
+    cudaEvent_t ev[4] = {};
+    bool ev_made = false;
     DevBuf<int16_t> d_trim;                  // DALIGNER TABLE | SCORE
     int path_ave = 0;
     std::vector<lesvgpu_hsp> hsps;
@@ -332,6 +577,8 @@ void lesvmap_ext_free(lesvmap_ext* e)
     e->d_score.release(); e->d_seeds.release(); e->d_f.release(); e->d_p.release(); e->d_t.release(); e->d_v.release(); e->d_u.release();
     e->d_mems.release(); e->d_ops.release(); e->d_blk.release(); e->d_pool.release(); e->d_pool_counter.release();
     e->d_outs.release(); e->d_trim.release();
+    e->d_jobs.release(); e->d_queue.release(); e->d_slots.release(); e->d_preps.release(); e->d_carry.release();
+    if (e->ev_made) for (auto& x : e->ev) cudaEventDestroy(x);
     delete e;
 }
 
@@ -498,18 +745,26 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         const size_t cells = 52500;                       // traceback mode of edlib holds < 1 MB = 52,428 block-columns
         const size_t peq_words = 4 * ((size_t)max_qsize / 64 + 2);
         const size_t ops_cap = (size_t)(3.5 * max_qsize) + 2048;
-        const uint32_t n_threads = std::min<uint32_t>((n_cand + kTraceThreadsPerBlock - 1) / kTraceThreadsPerBlock * kTraceThreadsPerBlock,
-                                                      (uint32_t)dev_sms * kTraceThreadsPerBlock);
-        CK(E->d_P.reserve(cells * n_threads)); CK(E->d_M.reserve(cells * n_threads)); CK(E->d_score.reserve(cells * n_threads));
-        CK(E->d_peq.reserve(peq_words * n_threads));
+        const uint32_t n_big_warps = (uint32_t)dev_sms * 8;
+        const uint32_t n_threads = std::min<uint32_t>((n_cand + 3) / 4 * 4, n_big_warps);    // warps of trace_finish_kernel
+        const uint32_t n_slabs = n_big_warps;
+        uint32_t max_wlen = 0;
+        for (const WinDev& W : wins) max_wlen = std::max(max_wlen, W.wlen);
+        CK(E->d_P.reserve(cells * n_slabs)); CK(E->d_M.reserve(cells * n_slabs)); CK(E->d_score.reserve(cells * n_slabs));
+        CK(E->d_peq.reserve(peq_words * n_slabs));
         CK(E->d_ops.reserve(ops_cap * n_threads)); CK(E->d_blk.reserve((size_t)lesvtb::kBlkOpsCap * n_threads));
         const unsigned long long mem_cap = 4ull * n_seeds + 64ull * n_cand + 1024;
+        const uint32_t jobs_cap = (uint32_t)std::min<unsigned long long>(2ull * n_seeds + 8ull * n_cand + 1024, 0xFFFFFFF0ull);
+        unsigned long long slot_cap = 40ull * jobs_cap;
+        for (int c : cand_list) slot_cap += (unsigned long long)M->h_reads[wins[c / kMaxCandPerWindow].read].len + wins[c / kMaxCandPerWindow].wlen;
         CK(E->d_mems.reserve(mem_cap));
-        CK(E->d_pool.reserve(pool_cap)); CK(E->d_pool_counter.reserve(2));
+        CK(E->d_jobs.reserve(jobs_cap)); CK(E->d_queue.reserve((size_t)kGapClasses * jobs_cap)); CK(E->d_slots.reserve(slot_cap));
+        CK(E->d_preps.reserve(n_cand));
+        CK(E->d_pool.reserve(pool_cap)); CK(E->d_pool_counter.reserve(8));
         CK(E->d_cand_list.reserve(n_cand));
         CK(cudaMemcpyAsync(E->d_cand_list.p, cand_list.data(), sizeof(int) * n_cand, cudaMemcpyHostToDevice, s));
-        CK(cudaMemsetAsync(E->d_pool_counter.p, 0, 2 * sizeof(unsigned long long), s));
-        CK(cudaMemsetAsync(E->d_counters.p + 2, 0, 4, s));
+        CK(cudaMemsetAsync(E->d_pool_counter.p, 0, 8 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(E->d_counters.p + 2, 0, 6 * sizeof(uint32_t), s));
         if (!E->d_trim.p) {
             std::vector<int16_t> tt(65536);
             lesvtb::dalign_tables(tt.data(), tt.data() + 32768, &E->path_ave);
@@ -517,14 +772,45 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
             CK(cudaMemcpyAsync(E->d_trim.p, tt.data(), sizeof(int16_t) * 65536, cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
         }
+        if (!E->ev_made) {
+            for (auto& e : E->ev) CK(cudaEventCreate(&e));
+            E->ev_made = true;
+        }
+        // d_pool_counter: [0] alignment pool, [1] MEM pool, [2] slot pool; as uint32 behind them: [6] job counter, [8..11] queue counts
+        uint32_t* c32 = reinterpret_cast<uint32_t*>(E->d_pool_counter.p + 3);
+        PrepBufs pb;
+        pb.mem_pool = E->d_mems.p; pb.mem_cap = mem_cap; pb.mem_counter = E->d_pool_counter.p + 1;
+        pb.jobs = E->d_jobs.p; pb.jobs_cap = jobs_cap; pb.job_counter = c32;
+        pb.slot_cap = slot_cap; pb.slot_counter = E->d_pool_counter.p + 2;
+        for (int k = 0; k < kGapClasses; ++k) pb.queue[k] = E->d_queue.p + (size_t)k * jobs_cap;
+        pb.queue_count = c32 + 2;
+        trace_prep_kernel<<<nblk(n_cand, 32), 32, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand,
+                                                          E->d_cand_info.p, E->d_hs_w.p, E->d_hs_r.p, word, pb, E->d_preps.p); ++g_lesv_launches;
+        CK(cudaEventRecord(E->ev[0], s));
+        const unsigned small_grid = (unsigned)dev_sms * 8;
+        gap_small_kernel<kSmallCells0, 0><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,
+                                                                     E->d_jobs.p, pb.queue[0], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
+        gap_small_kernel<kSmallCells1, 1><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,
+                                                                     E->d_jobs.p, pb.queue[1], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
+        gap_small_kernel<kSmallCells2, 2><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,
+                                                                     E->d_jobs.p, pb.queue[2], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
+        SlabBufs sb;
+        sb.P = E->d_P.p; sb.M = E->d_M.p; sb.score = E->d_score.p; sb.peq = E->d_peq.p; sb.cells = cells; sb.peq_words = peq_words;
+        const size_t carry_stride = ((size_t)max_wlen + 64 + 15) & ~(size_t)15;
+        CK(E->d_carry.reserve(carry_stride * n_big_warps));
+        gap_big_kernel<<<n_big_warps / 4, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
+                                                       pb.queue[3], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
+                                                       E->d_counters.p + 3); ++g_lesv_launches;
+        CK(cudaEventRecord(E->ev[1], s));
         TraceBufs tb;
+        tb.sb = sb;
         tb.trim_table = E->d_trim.p; tb.trim_score = E->d_trim.p + 32768; tb.path_ave = E->path_ave;
-        tb.P = E->d_P.p; tb.M = E->d_M.p; tb.score = E->d_score.p; tb.peq = E->d_peq.p; tb.cells = cells; tb.peq_words = peq_words;
-        tb.ops = E->d_ops.p; tb.ops_cap = ops_cap; tb.blk = E->d_blk.p; tb.mem_pool = E->d_mems.p; tb.mem_cap = mem_cap; tb.mem_counter = E->d_pool_counter.p + 1;
+        tb.ops = E->d_ops.p; tb.ops_cap = ops_cap; tb.blk = E->d_blk.p; tb.mem_pool = E->d_mems.p;
+        tb.jobs = E->d_jobs.p; tb.slots = E->d_slots.p;
         tb.pool = E->d_pool.p; tb.pool_cap = pool_cap; tb.pool_counter = E->d_pool_counter.p;
-        trace_kernel<<<n_threads / kTraceThreadsPerBlock, kTraceThreadsPerBlock, 0, s>>>(
-            E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_hs_w.p,
-            E->d_hs_r.p, word, min_align, opts->perc_identity, opts->skip_overhang ? 0 : 1, tb, E->d_outs.p, E->d_counters.p + 2); ++g_lesv_launches;
+        trace_finish_kernel<<<n_threads / 4, 128, 0, s>>>(
+            E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_preps.p,
+            min_align, opts->perc_identity, opts->skip_overhang ? 0 : 1, tb, E->d_outs.p, E->d_counters.p + 2); ++g_lesv_launches;
         CK(cudaEventRecord(ev[4], s));
         CK(cudaMemcpyAsync(outs.data(), E->d_outs.p, sizeof(CandOut) * outs.size(), cudaMemcpyDeviceToHost, s));
         unsigned long long pool_used = 0;
@@ -539,6 +825,15 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         CK(cudaEventRecord(ev[5], s));
         CK(cudaStreamSynchronize(s));
         cudaEventElapsedTime(&E->tm.trace_ms, ev[3], ev[4]);
+        cudaEventElapsedTime(&E->tm.prep_ms, ev[3], E->ev[0]);
+        cudaEventElapsedTime(&E->tm.gap_ms, E->ev[0], E->ev[1]);
+        cudaEventElapsedTime(&E->tm.finish_ms, E->ev[1], ev[4]);
+        {
+            uint32_t qc[kGapClasses + 2] = {};
+            cudaMemcpy(qc, reinterpret_cast<uint32_t*>(E->d_pool_counter.p + 3), sizeof qc, cudaMemcpyDeviceToHost);
+            E->tm.n_gap_jobs = qc[0];
+            for (int k = 0; k < kGapClasses; ++k) E->tm.n_gaps_class[k] = qc[2 + k];
+        }
         cudaEventElapsedTime(&E->tm.d2h_ms, ev[4], ev[5]);
         E->tm.d2h_bytes = sizeof(CandOut) * outs.size() + E->ops_host.size();
     }
@@ -616,4 +911,41 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
 extern "C" void lesvgpu_map_last_extend_timing(const lesvgpu_ctx* ctx, lesvgpu_extend_timing* t)
 {
     if (ctx && ctx->map && ctx->map->ext && t) *t = ctx->map->ext->tm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test hook: edlib_nw of one pair by one warp (trace_warp.cuh), residues coded 0..3
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(32)
+debug_nw_kernel(const uint8_t* __restrict__ q, int n, const uint8_t* __restrict__ t, int m, SlabBufs sb, int8_t* carry,
+                uint8_t* __restrict__ out, int* __restrict__ n_out)
+{
+    lesvtb::Scratch sc;
+    sc.P = sb.P; sc.M = sb.M; sc.score = sb.score; sc.peq = nullptr; sc.cap_cells = sb.cells; sc.cap_peq = 0;
+    sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
+    auto fq = [&](int i) -> uint32_t { return q[i]; };
+    auto ft = [&](int j) -> uint32_t { return t[j]; };
+    const int r = lesvtw::nw_path_warp(fq, n, ft, m, sc, carry, out, (size_t)(n + m));
+    if (threadIdx.x == 0) *n_out = r;
+}
+}  // namespace
+
+extern "C" int lesvgpu_debug_edlib_nw(lesvgpu_ctx* ctx, const uint8_t* q, int n, const uint8_t* t, int m, uint8_t* ops_out, int* n_ops)
+{
+    if (!ctx || !q || !t || !ops_out || !n_ops || n < 0 || m < 0) return LESVGPU_E_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
+    const size_t cells = std::max<size_t>(52500, 2 * ((size_t)n + 1));
+    DevBuf<uint64_t> P, Mv; DevBuf<int> score; DevBuf<uint8_t> dq, dt, dout; DevBuf<int8_t> carry; DevBuf<int> dn;
+    CK(P.reserve(cells)); CK(Mv.reserve(cells)); CK(score.reserve(cells)); CK(dq.reserve(n + 1)); CK(dt.reserve(m + 1));
+    CK(dout.reserve((size_t)n + m + 1)); CK(carry.reserve(m + 64)); CK(dn.reserve(1));
+    CK(cudaMemcpy(dq.p, q, n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt.p, t, m, cudaMemcpyHostToDevice));
+    SlabBufs sb{P.p, Mv.p, score.p, nullptr, cells, 0};
+    debug_nw_kernel<<<1, 32, 0, ctx->stream>>>(dq.p, n, dt.p, m, sb, carry.p, dout.p, dn.p); ++g_lesv_launches;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(n_ops, dn.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*n_ops > 0) CK(cudaMemcpy(ops_out, dout.p, *n_ops, cudaMemcpyDeviceToHost));
+    P.release(); Mv.release(); score.release(); dq.release(); dt.release(); dout.release(); carry.release(); dn.release();
+    return LESVGPU_OK;
 }

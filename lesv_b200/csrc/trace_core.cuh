@@ -51,6 +51,8 @@ struct Scratch {
     uint64_t* peq;          // [4][blocks]
     size_t cap_cells;       // block-columns that fit P/M/score
     size_t cap_peq;         // u64 words in peq
+    int cols;               // columns of the last myers_fill: cell (column j, block b) sits at b * cols + j, so a walk
+                            // along the diagonal stays inside a few cache lines
     const int16_t* trim_table;   // DALIGNER TABLE / SCORE (New_Align_Spec, align.c:253-296), 32768 entries each
     const int16_t* trim_score;
     int path_ave;
@@ -90,7 +92,7 @@ TRC_HD inline int cell_value(const Scratch& sc, int nb, int j, int i)
     if (j == 0) return i;
     if (i == 0) return j;
     const int b = (i - 1) >> 6, pos = (i - 1) & 63;
-    const size_t x = (size_t)(j - 1) * nb + b;
+    const size_t x = (size_t)b * sc.cols + (j - 1);
     const uint64_t above = pos == 63 ? 0ull : (~0ull << (pos + 1));     // rows below row i inside the block
     return sc.score[x] - popc64(sc.P[x] & above) + popc64(sc.M[x] & above);
 }
@@ -102,6 +104,7 @@ TRC_HD inline bool myers_fill(FQ Q, int n, FT T, int m, Scratch& sc, int* nb_out
     const int nb = (n + 63) >> 6;
     *nb_out = nb;
     if ((size_t)nb * (size_t)m > sc.cap_cells || (size_t)4 * nb > sc.cap_peq) return false;
+    sc.cols = m;
     for (int x = 0; x < 4 * nb; ++x) sc.peq[x] = 0;
     for (int i = 0; i < n; ++i) sc.peq[(size_t)Q(i) * nb + (i >> 6)] |= 1ull << (i & 63);
     if (n & 63) {                                    // rows past the query match anything (buildPeq, :350-353)
@@ -112,9 +115,9 @@ TRC_HD inline bool myers_fill(FQ Q, int n, FT T, int m, Scratch& sc, int* nb_out
         const uint64_t* eq = sc.peq + (size_t)T(j) * nb;
         int hout = 1;
         for (int b = 0; b < nb; ++b) {
-            const size_t x = (size_t)j * nb + b;
-            const uint64_t Pv = j ? sc.P[x - nb] : ~0ull, Mv = j ? sc.M[x - nb] : 0ull;
-            const int prev = j ? sc.score[x - nb] : (b + 1) * 64;
+            const size_t x = (size_t)b * m + j;
+            const uint64_t Pv = j ? sc.P[x - 1] : ~0ull, Mv = j ? sc.M[x - 1] : 0ull;
+            const int prev = j ? sc.score[x - 1] : (b + 1) * 64;
             hout = myers_block(Pv, Mv, eq[b], hout, sc.P[x], sc.M[x]);
             sc.score[x] = prev + hout;
         }
@@ -129,7 +132,7 @@ TRC_HD inline int myers_walk(const Scratch& sc, int nb, int n, int jend, uint8_t
     uint8_t* rev = out;                              // written last-op-first, reversed in place below
     while (i > 0 && j > 0) {
         const int b = (i - 1) >> 6, pos = (i - 1) & 63;
-        const size_t x = (size_t)(j - 1) * nb + b;
+        const size_t x = (size_t)b * sc.cols + (j - 1);
         const int u = cur - (int)((sc.P[x] >> pos) & 1) + (int)((sc.M[x] >> pos) & 1);
         if (u + 1 == cur) { rev[len++] = kOpIns; --i; cur = u; continue; }
         const int l = cell_value(sc, nb, j - 1, i);
@@ -549,17 +552,76 @@ TRC_HD inline int extend(FQ Q, int qsize, FT T, int tsize, Scratch& sc, Emit emi
 // hbn_traceback (hbn_traceback.c:313-544) without the overhang step.  Q: read strand (qsize bases),
 // S: window (ssize bases).  seeds = MEMs in chain order.  ops buffer: cap bytes; `front` = room kept
 // before the first column for the left extension.
+// The gaps between consecutive trace seeds, in the order hbn_traceback aligns them (:351-374):
+// f(i, query start, query bases, window start, window bases) for i = 0 .. tsc-2.  The gaps are independent
+// of each other, so they can be solved anywhere (one GPU thread each) before the alignment is assembled.
+template <class F>
+TRC_HD inline void enumerate_gaps(const Mem* tsa, int tsc, F f)
+{
+    const int E = 10, E2 = 20;
+    int qfrom, sfrom;
+    if (tsa[0].len > E2) { qfrom = tsa[0].q + tsa[0].len - E; sfrom = tsa[0].s + tsa[0].len - E; }
+    else { qfrom = tsa[0].q; sfrom = tsa[0].s; }
+    for (int i = 0; i < tsc - 1; ++i) {
+        const Mem sj = tsa[i + 1];
+        int qto, sto;
+        if (sj.len > E2) { qto = sj.q + E; sto = sj.s + E; }
+        else { qto = sj.q + sj.len / 2; sto = sj.s + sj.len / 2; }
+        f(i, qfrom, qto - qfrom, sfrom, sto - sfrom);
+        qfrom = qto; sfrom = sto;
+        if (sj.len > E2) { qfrom = sj.q + sj.len - E; sfrom = sj.s + sj.len - E; }
+    }
+}
+
+template <class FQ, class FS>
+TRC_HD inline Result finish_ends(FQ Q, int qsize, FS S, int ssize, Scratch& sc, uint8_t* ops, size_t cap, size_t beg, size_t end,
+                                 int qoff, int qend, int soff, int send, uint8_t* blk, bool process_over_hang);
+
+// ident_perc = 100 * matches / columns; accept iff long and similar enough (hbn_traceback.c:534-542)
+TRC_HD inline void finalize_stats(Result& R, int n_match, int min_align_size, double min_ident_perc)
+{
+    R.n_match = n_match;
+    const double ident = 100.0 * n_match / R.aln_len;
+    R.status = (R.aln_len >= min_align_size && ident >= min_ident_perc) ? kOk : kNoAlign;
+}
+
+// hbn_traceback over known trace seeds tsa[0..tsc).  gap(i, qa, n, sa, m, out, cap) delivers the ops of
+// edlib_nw(Q[qa..qa+n), S[sa..sa+m)) for the i-th gap (count, or a negative Status).
+template <class FQ, class FS, class FG>
+TRC_HD inline Result traceback_ts(FQ Q, int qsize, FS S, int ssize, const Mem* tsa, int tsc, FG gap,
+                                  Scratch& sc, uint8_t* ops, size_t cap, size_t front, uint8_t* blk,
+                                  int min_align_size, double min_ident_perc, bool process_over_hang);
+
 template <class FQ, class FS>
 TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems, int n_mems, Mem* ts_buf,
                                Scratch& sc, uint8_t* ops, size_t cap, size_t front, uint8_t* blk,
                                int min_align_size, double min_ident_perc, bool process_over_hang)
 {
+    if (n_mems == 0) {
+        Result R;
+        R.status = kNoAlign; R.qoff = R.qend = R.soff = R.send = 0; R.aln_len = 0; R.n_match = 0; R.ops_beg = 0;
+        R.overhang_left = R.overhang_right = 0;
+        return R;
+    }
+    const int tsc = trace_points(mems, n_mems, ts_buf);
+    auto gap = [&](int, int qa, int n, int sa, int m, uint8_t* out, size_t out_cap) {
+        auto fq = [&](int x) { return Q(qa + x); };
+        auto fs = [&](int x) { return S(sa + x); };
+        return nw_path(fq, n, fs, m, sc, out, out_cap);
+    };
+    return traceback_ts(Q, qsize, S, ssize, ts_buf, tsc, gap, sc, ops, cap, front, blk, min_align_size, min_ident_perc,
+                        process_over_hang);
+}
+
+template <class FQ, class FS, class FG>
+TRC_HD inline Result traceback_ts(FQ Q, int qsize, FS S, int ssize, const Mem* tsa, int tsc, FG gap,
+                                  Scratch& sc, uint8_t* ops, size_t cap, size_t front, uint8_t* blk,
+                                  int min_align_size, double min_ident_perc, bool process_over_hang)
+{
     Result R;
     R.status = kNoAlign; R.qoff = R.qend = R.soff = R.send = 0; R.aln_len = 0; R.n_match = 0; R.ops_beg = 0;
     R.overhang_left = R.overhang_right = 0;
-    if (n_mems == 0) return R;
-    const int tsc = trace_points(mems, n_mems, ts_buf);
-    const Mem* tsa = ts_buf;
+    if (tsc == 0) return R;
     size_t beg = front, end = front;
     const int E = 10, E2 = 20;
     int qfrom, qto, sfrom, sto;
@@ -579,10 +641,7 @@ TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems
         if (sj.len > E2) { qto = sj.q + E; sto = sj.s + E; }
         else { qto = sj.q + sj.len / 2; sto = sj.s + sj.len / 2; }
         {
-            const int qa = qfrom, sa = sfrom;
-            auto fq = [&](int x) { return Q(qa + x); };
-            auto fs = [&](int x) { return S(sa + x); };
-            const int r = nw_path(fq, qto - qfrom, fs, sto - sfrom, sc, ops + end, cap - end);
+            const int r = gap(i, qfrom, qto - qfrom, sfrom, sto - sfrom, ops + end, cap - end);
             if (r < 0) { R.status = r; return R; }
             end += (size_t)r;
         }
@@ -599,7 +658,35 @@ TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems
         TRC_PUSH_DIAG(qto - qfrom);
     }
 #undef TRC_PUSH_DIAG
-    int qoff = tsa[0].q, qend = qto, soff = tsa[0].s, send = sto;
+    R = finish_ends(Q, qsize, S, ssize, sc, ops, cap, beg, end, tsa[0].q, qto, tsa[0].s, sto, blk, process_over_hang);
+    if (R.status != kOk) return R;
+    // calc_ident_perc (hbn_traceback_aux.c:4-19)
+    int n_match = 0;
+    {
+        int qi = R.qoff, si = R.soff;
+        const size_t e = R.ops_beg + (size_t)R.aln_len;
+        for (size_t a = R.ops_beg; a < e; ++a) {
+            const uint8_t op = ops[a];
+            if (op == kOpDiag) { n_match += Q(qi) == S(si); ++qi; ++si; }
+            else if (op == kOpIns) ++qi;
+            else ++si;
+        }
+    }
+    finalize_stats(R, n_match, min_align_size, min_ident_perc);
+    return R;
+}
+
+// Everything hbn_traceback does after the seeds and gaps are stitched (:396-532): trim to the first / last
+// run of kMatLen identical columns, edlib_extend to both sides, the overhang step.  ops[beg, end) holds the
+// stitched columns of Q[qoff, qend) x S[soff, send).  Returns status kOk with coordinates, aln_len and
+// ops_beg set (n_match still 0: see finalize_stats), kNoAlign, or a negative Status.
+template <class FQ, class FS>
+TRC_HD inline Result finish_ends(FQ Q, int qsize, FS S, int ssize, Scratch& sc, uint8_t* ops, size_t cap, size_t beg, size_t end,
+                                 int qoff, int qend, int soff, int send, uint8_t* blk, bool process_over_hang)
+{
+    Result R;
+    R.status = kNoAlign; R.qoff = R.qend = R.soff = R.send = 0; R.aln_len = 0; R.n_match = 0; R.ops_beg = 0;
+    R.overhang_left = R.overhang_right = 0;
 
     // trim to the first / last run of kMatLen identical columns (:396-433)
     {
@@ -714,21 +801,9 @@ TRC_HD inline Result traceback(FQ Q, int qsize, FS S, int ssize, const Mem* mems
             }
         }
     }
-    // calc_ident_perc (hbn_traceback_aux.c:4-19)
-    int n_match = 0;
-    {
-        int qi = qoff, si = soff;
-        for (size_t a = beg; a < end; ++a) {
-            const uint8_t op = ops[a];
-            if (op == kOpDiag) { n_match += Q(qi) == S(si); ++qi; ++si; }
-            else if (op == kOpIns) ++qi;
-            else ++si;
-        }
-    }
     R.qoff = qoff; R.qend = qend; R.soff = soff; R.send = send;
-    R.aln_len = (int)(end - beg); R.n_match = n_match; R.ops_beg = beg;
-    const double ident = 100.0 * n_match / R.aln_len;
-    R.status = (R.aln_len >= min_align_size && ident >= min_ident_perc) ? kOk : kNoAlign;
+    R.aln_len = (int)(end - beg); R.ops_beg = beg;
+    R.status = kOk;
     return R;
 }
 

@@ -262,3 +262,13 @@ def oracle_discover(svr, read_fwd, contig, min_indel):
     out = (OracleSvSig * 64)()
     n = lib.lesv_oracle_discover_one(C.byref(s), _ptr(read_fwd), len(read_fwd), _ptr(contig), len(contig), min_indel, out, 64)
     return n, [tuple(getattr(out[i], f) for f, _ in OracleSvSig._fields_) for i in range(max(n, 0))]
+
+
+def trace_emul():
+    """Host build of trace_core.cuh (tests/emul/trace_emul.cpp): the sequential restatement of edlib_nw etc."""
+    if "t" not in _cache:
+        so = os.path.join(ROOT, "tests", "emul", "libtrace_emul.so")
+        if not os.path.exists(so):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul"), "libtrace_emul.so"], check=True)
+        _cache["t"] = C.CDLL(so)
+    return _cache["t"]

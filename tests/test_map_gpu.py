@@ -164,3 +164,34 @@ def test_map_batch_against_fresh_reference_run(ctx, tmp_path, case):
     assert len(exp) >= Q.num_seqs // 2
     assert got == exp
     shutil.rmtree(work, ignore_errors=True)
+
+
+# ---- warp-cooperative edlib_nw (trace_warp.cuh) against the sequential restatement (validated against edlib on CPU) ----
+def test_warp_edlib_nw_equals_sequential_restatement(ctx):
+    import ctypes as C
+    from lesv_b200.synth import mutate
+    lib = ctx.lib
+    lib.lesvgpu_debug_edlib_nw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    em = H.trace_emul()
+    rng = np.random.default_rng(21)
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 500, 1000, 2047, 2048, 2049, 2100, 3000, 4100, 5000, 9000]
+    n_h = 0
+    for it, n in enumerate(sizes * 2):
+        two = it % 5 == 3                                   # two-letter alphabet: many co-optimal paths and splits
+        q = rng.integers(0, 2 if two else 4, n, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, float(rng.uniform(0.03, 0.3)), rng))
+        if two:
+            t &= 1
+        if it % 4 == 1 and n > 200:                         # a large deletion / unrelated insert inside
+            k = n // 3
+            t = np.ascontiguousarray(np.concatenate([t[:k], rng.integers(0, 4, n // 4, dtype=np.uint8), t[k + n // 5:]]))
+        if len(t) == 0:
+            t = q[:1].copy()
+        n_h += 20 * ((len(q) + 63) // 64) * len(t) + 8 * len(t) >= 1 << 20
+        exp = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
+        ne = em.lesv_emul_nw(H._ptr(q), len(q), H._ptr(t), len(t), H._ptr(exp), len(exp))
+        got = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
+        ng = C.c_int()
+        assert lib.lesvgpu_debug_edlib_nw(ctx.h, H._ptr(q), len(q), H._ptr(t), len(t), H._ptr(got), C.byref(ng)) == 0
+        assert ng.value == ne and np.array_equal(got[:ne], exp[:ne]), (it, len(q), len(t))
+    assert n_h >= 8                                          # Hirschberg route exercised

@@ -10,13 +10,19 @@ n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 read_len = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
 ref_len = int(sys.argv[3]) if len(sys.argv) > 3 else 50_000_000
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+sv = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 
 rng = np.random.default_rng(7)
 ref = synth.random_codes(ref_len, rng)
 reads = []
 for i in range(n_reads):
     s = int(rng.integers(0, ref_len - read_len))
-    r = synth.mutate(ref[s:s + read_len], float(rng.uniform(0.10, 0.15)), rng)
+    seg = ref[s:s + read_len]
+    if sv and i % 5 == 0:                      # every 5th read spans a 40 bp - 10 kb insertion or deletion
+        size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
+        pos = int(rng.integers(2000, read_len - 2000 - size))
+        seg = np.concatenate([seg[:pos], synth.random_codes(size, rng), seg[pos:]]) if i % 10 == 0 else np.concatenate([seg[:pos], seg[pos + size:]])
+    r = synth.mutate(seg, float(rng.uniform(0.10, 0.15)), rng)
     if rng.integers(0, 2):
         r = synth.revcomp_codes(r)
     reads.append(np.ascontiguousarray(r))
@@ -42,4 +48,5 @@ for rep in range(reps):
           f" kmers={mt.n_kmers} matches={mt.n_matches} segs={mt.n_segments} hits={mt.n_hits}", flush=True)
     print("   ext:  " + " ".join(f"{n}={getattr(et, n):.1f}" for n in ("ihf_ms", "sort_ms", "chain_ms", "trace_ms", "d2h_ms")) +
           f" windows={et.n_windows} seeds={et.n_seeds} cands={et.n_candidates} unsupported={et.n_unsupported}", flush=True)
+    print(f"   trace: prep={et.prep_ms:.1f} gap={et.gap_ms:.1f} finish={et.finish_ms:.1f} gaps={et.n_gap_jobs} classes={list(et.n_gaps_class)}", flush=True)
 ctx.close()
