@@ -186,6 +186,10 @@ KSX_HD inline int join_chains(const Params& P, Hit* hits, int nh, Hit* out, int*
     return n_out;
 }
 
+KSX_HD inline int find_candidates_scored(const Params& P, const Seed* seeds, int n,
+                                         int* f, int* p, int* t, int* v, IntPair* u,
+                                         Hit* pre, int* n_pre, Hit* out, int* members);
+
 // chaining_find_candidates, chain_dp.c:273-395.  Scratch f,p,t,v: n ints each; u: n pairs.
 // pre[] (kMaxChains) receives the chains before joining (members[] refers to them), out[] (kMaxJoined)
 // the final hits in the reference's order.  Returns the number of final hits; *n_pre = chains found.
@@ -196,6 +200,16 @@ KSX_HD inline int find_candidates(const Params& P, const Seed* seeds, int n, boo
     *n_pre = 0;
     if (n == 0) return 0;
     score_seeds(P, seeds, n, is_mem, f, p, t, v);
+    return find_candidates_scored(P, seeds, n, f, p, t, v, u, pre, n_pre, out, members);
+}
+
+// chaining_find_candidates after scoring_chain_seeds has filled f, p, v (chain_dp.c:286-395).
+KSX_HD inline int find_candidates_scored(const Params& P, const Seed* seeds, int n,
+                                         int* f, int* p, int* t, int* v, IntPair* u,
+                                         Hit* pre, int* n_pre, Hit* out, int* members)
+{
+    *n_pre = 0;
+    if (n == 0) return 0;
     for (int i = 0; i < n; ++i) t[i] = 0;
     for (int i = 0; i < n; ++i) if (p[i] >= 0) t[p[i]] = 1;
     int n_u = 0;

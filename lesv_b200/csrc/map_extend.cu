@@ -22,6 +22,7 @@
 #include "gpu_prims.cuh"
 #include "trace_core.cuh"
 #include "trace_warp.cuh"
+#include "chain_warp.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -174,30 +175,35 @@ struct ChainBufs {
     lesvchain::IntPair* u;
 };
 
-// One thread per window: chain the sorted seeds (InitHitFindData_FindHits, init_hit_finder.c:387-467),
-// keep the seed lists of the <= 3 best chains.
-__global__ void __launch_bounds__(64)
+// One warp per window: chain the sorted seeds (InitHitFindData_FindHits, init_hit_finder.c:387-467), keep the
+// seed lists of the <= 3 best chains.  The scoring DP runs on the whole warp (chain_warp.cuh), the
+// backtracking on lane 0.
+__global__ void __launch_bounds__(128)
 ihf_chain_kernel(const uint64_t* __restrict__ seed_keys, const uint32_t* __restrict__ win_off, const uint32_t* __restrict__ win_count,
                  uint32_t n_win, int word, int min_score, ChainBufs cb, int* __restrict__ hs_w, int* __restrict__ hs_r,
                  int* __restrict__ cand_info /* per candidate: score, seed_off, seed_cnt */, int* __restrict__ cand_cnt)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (w >= n_win) return;
     const uint32_t a = win_off[w], n = win_count[w];
-    cand_cnt[w] = 0;
-    if (n == 0) return;
+    if (n == 0) { if (lane == 0) cand_cnt[w] = 0; return; }
     lesvchain::Seed* seeds = cb.seeds + a;
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t i = lane; i < n; i += 32) {
         const uint64_t key = seed_keys[a + i];
         seeds[i].q = (int)(key & 0xFFFFF);            // chain "query" = window (roles as in init_hit_finder.c)
         seeds[i].s = (int)((key >> 20) & 0xFFFFF);    // chain "subject" = read
         seeds[i].len = word;
     }
+    __syncwarp();
+    const lesvchain::Params P = lesvchain::make_params(1, min_score);
+    lesvchain::score_seeds_warp(P, seeds, (int)n, false, cb.f + a, cb.p + a, cb.t + a, cb.v + a);
+    if (lane != 0) return;
     lesvchain::Hit pre[lesvchain::kMaxChains], out[lesvchain::kMaxJoined];
     int members[lesvchain::kMaxChains], n_pre = 0;
-    const lesvchain::Params P = lesvchain::make_params(1, min_score);
-    const int nh = lesvchain::find_candidates(P, seeds, (int)n, false, cb.f + a, cb.p + a, cb.t + a, cb.v + a, cb.u + a,
-                                              pre, &n_pre, out, members);
+    const int nh = lesvchain::find_candidates_scored(P, seeds, (int)n, cb.f + a, cb.p + a, cb.t + a, cb.v + a, cb.u + a,
+                                                     pre, &n_pre, out, members);
+    cand_cnt[w] = 0;
     if (nh == 0) return;
     lesvsort::introsort(out, (size_t)nh, lesvchain::HitScoreGt());         // :465, on the already sorted list
     const int* v = cb.v + a;
@@ -240,7 +246,7 @@ struct CandPrep {
     unsigned long long mem_off;  // mems at mem_pool + mem_off, trace seeds right behind them
 };
 
-constexpr int kGapClasses = 4;                         // 3 local-memory classes + the big one
+constexpr int kGapClasses = 5;                         // 3 local-memory classes, big (one warp each), giant (ditto, started first)
 constexpr int kSmallCells0 = 128, kSmallCells1 = 256, kSmallCells2 = 512;
 
 struct PrepBufs {
@@ -257,7 +263,8 @@ __device__ __forceinline__ int gap_class(int n, int m)
     if (nb == 1 && m <= kSmallCells0) return 0;
     if (nb <= 2 && cells <= kSmallCells1) return 1;
     if (nb <= 8 && cells <= kSmallCells2) return 2;
-    return 3;
+    if (cells <= 16384 && !lesvtb::needs_hirschberg(n, m)) return 3;
+    return 4;
 }
 
 __global__ void __launch_bounds__(32)
@@ -353,7 +360,8 @@ struct SlabBufs {
 __global__ void __launch_bounds__(128)
 gap_big_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
                const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, GapJob* __restrict__ jobs,
-               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queue_count, uint8_t* __restrict__ slots,
+               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ giant_queue,
+               const uint32_t* __restrict__ queue_count, uint8_t* __restrict__ slots,
                SlabBufs sb, int8_t* __restrict__ carry_pool, size_t carry_stride, uint32_t* __restrict__ work_counter)
 {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -363,13 +371,13 @@ gap_big_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ read
     sc.peq = nullptr; sc.cap_cells = sb.cells; sc.cap_peq = 0;
     sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
     int8_t* carry = carry_pool + warp * carry_stride;
-    const uint32_t n_jobs = queue_count[kGapClasses - 1];
+    const uint32_t n_giant = queue_count[4], n_jobs = n_giant + queue_count[3];
     for (;;) {
         uint32_t j = 0;
         if (lane == 0) j = atomicAdd(work_counter, 1u);
         j = __shfl_sync(0xFFFFFFFFu, j, 0);
         if (j >= n_jobs) break;
-        GapJob& J = jobs[queue[j]];
+        GapJob& J = jobs[j < n_giant ? giant_queue[j] : queue[j - n_giant]];
         const WinDev W = wins[cand_list[J.cand] / kMaxCandPerWindow];
         const ReadDev rd = reads[W.read];
         const int qa = J.qa, sa = J.sa, n = J.n, m = J.m;
@@ -727,7 +735,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
     CK(E->d_seeds.reserve(n_seeds)); CK(E->d_f.reserve(n_seeds)); CK(E->d_p.reserve(n_seeds)); CK(E->d_t.reserve(n_seeds));
     CK(E->d_v.reserve(n_seeds)); CK(E->d_u.reserve(n_seeds)); CK(E->d_hs_w.reserve(n_seeds)); CK(E->d_hs_r.reserve(n_seeds));
     ChainBufs cb{E->d_seeds.p, E->d_f.p, E->d_p.p, E->d_t.p, E->d_v.p, E->d_u.p};
-    ihf_chain_kernel<<<nblk(n_win, 64), 64, 0, s>>>(seed_keys, E->d_win_off.p, E->d_win_count.p, n_win, word, memsc_score, cb,
+    ihf_chain_kernel<<<nblk((uint64_t)n_win * 32, 128), 128, 0, s>>>(seed_keys, E->d_win_off.p, E->d_win_count.p, n_win, word, memsc_score, cb,
                                                     E->d_hs_w.p, E->d_hs_r.p, E->d_cand_info.p, E->d_cand_cnt.p); ++g_lesv_launches;
     std::vector<int> cand_cnt(n_win);
     CK(cudaMemcpyAsync(cand_cnt.data(), E->d_cand_cnt.p, sizeof(int) * n_win, cudaMemcpyDeviceToHost, s));
@@ -763,7 +771,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         CK(E->d_pool.reserve(pool_cap)); CK(E->d_pool_counter.reserve(8));
         CK(E->d_cand_list.reserve(n_cand));
         CK(cudaMemcpyAsync(E->d_cand_list.p, cand_list.data(), sizeof(int) * n_cand, cudaMemcpyHostToDevice, s));
-        CK(cudaMemsetAsync(E->d_pool_counter.p, 0, 8 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(E->d_pool_counter.p, 0, 8 * sizeof(unsigned long long), s));     // counters, see below
         CK(cudaMemsetAsync(E->d_counters.p + 2, 0, 6 * sizeof(uint32_t), s));
         if (!E->d_trim.p) {
             std::vector<int16_t> tt(65536);
@@ -799,7 +807,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         const size_t carry_stride = ((size_t)max_wlen + 64 + 15) & ~(size_t)15;
         CK(E->d_carry.reserve(carry_stride * n_big_warps));
         gap_big_kernel<<<n_big_warps / 4, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
-                                                       pb.queue[3], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
+                                                       pb.queue[3], pb.queue[4], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
                                                        E->d_counters.p + 3); ++g_lesv_launches;
         CK(cudaEventRecord(E->ev[1], s));
         TraceBufs tb;
@@ -832,7 +840,16 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
             uint32_t qc[kGapClasses + 2] = {};
             cudaMemcpy(qc, reinterpret_cast<uint32_t*>(E->d_pool_counter.p + 3), sizeof qc, cudaMemcpyDeviceToHost);
             E->tm.n_gap_jobs = qc[0];
-            for (int k = 0; k < kGapClasses; ++k) E->tm.n_gaps_class[k] = qc[2 + k];
+            if (getenv("LESV_GAP_DEBUG")) {
+                std::vector<GapJob> hj(qc[0]);
+                cudaMemcpy(hj.data(), E->d_jobs.p, sizeof(GapJob) * qc[0], cudaMemcpyDeviceToHost);
+                std::sort(hj.begin(), hj.end(), [](const GapJob& a, const GapJob& b) { return (long long)a.n * a.m > (long long)b.n * b.m; });
+                fprintf(stderr, "[gap debug] giant=%u big=%u; largest:", qc[6], qc[5]);
+                for (size_t k = 0; k < 12 && k < hj.size(); ++k) fprintf(stderr, " %dx%d", hj[k].n, hj[k].m);
+                fprintf(stderr, "\n");
+            }
+            for (int k = 0; k < 4; ++k) E->tm.n_gaps_class[k] = qc[2 + k];
+            E->tm.n_gaps_class[3] += qc[2 + 4];
         }
         cudaEventElapsedTime(&E->tm.d2h_ms, ev[4], ev[5]);
         E->tm.d2h_bytes = sizeof(CandOut) * outs.size() + E->ops_host.size();
