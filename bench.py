@@ -288,18 +288,24 @@ def main():
 
     def step():
         """one batch through the path; returns per-stage device ms, byte counts, work counts"""
+        w0 = time.perf_counter()
         h = capi.map_batch_raw(ctx, query_pac, seq_arr, 0, nq, hitlist_size=5, max_hsps=10)
+        w1 = time.perf_counter()
         mt, et = capi.map_last_timing(ctx), capi.map_last_extend_timing(ctx)
         m4 = capi.hsps_to_m4(h)
+        w2 = time.perf_counter()
         svr, st = capi.svr_batch(ctx, query_pac, read_offset, [0], [len(ref)], m4, 3000, 70.0, 300)
+        w3 = time.perf_counter()
         t_svr = ctx.timing() if (st.n_refine_jobs or st.n_chain_jobs) else capi.Timing()
         status, n_sig = capi.svsig_batch_raw(ctx, query_pac, read_offset, 0, len(ref), svr, MIN_INDEL)
+        w4 = time.perf_counter()
         t_sig = ctx.timing()
         dev = {"map_seed_chain": mt.lookup_ms + mt.emit_ms + mt.sort_ms + mt.chain_ms,
                "map_extend": et.ihf_ms + et.sort_ms + et.chain_ms + et.trace_ms,
                "svr": t_svr.pack_ms + t_svr.dp_ms + t_svr.scan_ms,
                "svsig": t_sig.pack_ms + t_sig.dp_ms + t_sig.scan_ms}
-        return {"dev": dev, "dp_ms": t_svr.dp_ms + t_sig.dp_ms, "sig_dp_ms": t_sig.dp_ms, "sig_cells": int(t_sig.dp_cells),
+        wall = {"map": (w1 - w0) * 1e3, "m4": (w2 - w1) * 1e3, "svr": (w3 - w2) * 1e3, "svsig": (w4 - w3) * 1e3}
+        return {"dev": dev, "wall": wall, "dp_ms": t_svr.dp_ms + t_sig.dp_ms, "sig_dp_ms": t_sig.dp_ms, "sig_cells": int(t_sig.dp_cells),
                 "cells": int(t_svr.dp_cells) + int(t_sig.dp_cells), "dp_launches": t_svr.dp_launches + t_sig.dp_launches,
                 "sig_launches": t_sig.dp_launches,
                 "h2d": int(mt.h2d_bytes + t_svr.h2d_bytes + t_sig.h2d_bytes),
@@ -329,6 +335,8 @@ def main():
                     acc[k] += r[k]
                 for k in acc["dev"]:
                     acc["dev"][k] += r["dev"][k]
+                for k in acc["wall"]:
+                    acc["wall"][k] += r["wall"][k]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
     launches = lib.lesvgpu_launch_count() - launches0
@@ -366,6 +374,7 @@ def main():
             "gpu_launches": int(all_launches),
             "clocks": clocks,
             "stages_ms_per_step": {k: v / K for k, v in acc["dev"].items()},
+            "call_wall_ms_per_step": {k: v / K for k, v in acc["wall"].items()},
             "stage_throughput": {"map_bases_per_s": acc["bases"] / ((acc["dev"]["map_seed_chain"] + acc["dev"]["map_extend"]) / 1e3),
                                  "svr_svsig_gcups": acc["cells"] / (acc["dp_ms"] / 1e3) / 1e9},
             "roofline": {"bound": "int-issue", "kernel": "ksw_dp_kernel", "achieved": kern_gcups, "peak": int_peak,

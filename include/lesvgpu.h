@@ -33,7 +33,7 @@ enum {
 /* ---- context -------------------------------------------------------------------------------- */
 
 int lesvgpu_device_count(void);
-/* arena_bytes = HBM reserved for traceback matrices (0 = 80 % of the free memory, grown lazily). */
+/* arena_bytes = HBM reserved for traceback matrices (0 = up to 88 % of the free memory, grown lazily and never past 90 % of what is free at the time). */
 int lesvgpu_ctx_create(int device, size_t arena_bytes, lesvgpu_ctx** ctx);
 void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx);
 const char* lesvgpu_last_error(const lesvgpu_ctx* ctx);

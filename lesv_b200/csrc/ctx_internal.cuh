@@ -24,6 +24,15 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    cudaError_t reserve_exact(size_t n)              // no headroom: for the traceback arena, sized against free memory
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 

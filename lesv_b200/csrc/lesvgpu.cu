@@ -9,6 +9,7 @@
 #include "ksw_core.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -38,10 +39,17 @@ extern "C" int lesvgpu_ctx_create(int device, size_t arena_bytes, lesvgpu_ctx** 
     ctx->n_sm = prop.multiProcessorCount;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    ctx->arena_limit = arena_bytes ? arena_bytes : (size_t)(free_b * 0.8);
+    ctx->arena_limit = arena_bytes ? arena_bytes : (size_t)(free_b * 0.88);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LESVGPU_E_CUDA; }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
-    for (auto& st : ctx->side) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    // launch classes are issued largest shape first on side[0], side[1], ...: descending priority lets the
+    // cluster launches take their SMs before the bulk of single-CTA alignments fills the machine
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    for (int k = 0; k < kSideStreams; ++k) {
+        const int pr = std::min(prio_least, prio_greatest + k);
+        cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, pr);
+    }
     for (auto& e : ctx->side_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return LESVGPU_OK;
@@ -87,11 +95,53 @@ static inline bool band_reaches_end(int qlen, int tlen, int w)
     return true;
 }
 
+// Sum of en0 - st0 + 1 over all anti-diagonals when none is empty, in closed form: both bounds are piecewise
+// {constant, r + c, (r + c) >> 1} with at most six breakpoints; two rows on either side of every breakpoint are
+// evaluated directly, the interior of each segment with the piece that is active there.
+static inline int64_t sum_lin(int64_t a, int64_t b) { return a > b ? 0 : (a + b) * (b - a + 1) / 2; }            // sum r, r=a..b
+static inline int64_t half_prefix(int64_t x) { return x < 0 ? 0 : (x / 2) * ((x + 1) / 2); }                     // sum_{s=0..x} floor(s/2)
+static inline int64_t sum_half(int64_t a, int64_t b, int64_t c) { return a > b ? 0 : half_prefix(b + c) - half_prefix(a + c - 1); } // needs a + c >= 0
+static int64_t cells_fast(int ql, int tl, int w)
+{
+    const int nr = ql + tl - 1;
+    long long cand[] = { (long long)w, 2LL * tl - 2 - w, (long long)ql - 1, (long long)w - 1, 2LL * ql - w - 1, (long long)tl - 1 };
+    int64_t total = 0;
+    // collect breakpoints
+    int pts[16]; int np = 0; pts[np++] = 0; pts[np++] = nr;
+    for (long long x : cand) if (x > 0 && x < nr) pts[np++] = (int)x;
+    std::sort(pts, pts + np);
+    auto st0 = [&](int r) { int st = r - ql + 1; st = st > 0 ? st : 0; const int s2 = (r - w + 1) >> 1; return st > s2 ? st : s2; };
+    auto en0 = [&](int r) { int en = r < tl - 1 ? r : tl - 1; const int e2 = (r + w) >> 1; return en < e2 ? en : e2; };
+    for (int i = 0; i + 1 < np; ++i) {
+        int a = pts[i], b = pts[i + 1] - 1;          // rows a..b
+        if (a > b) continue;
+        // margins by brute force
+        while (a <= b && (a < pts[i] + 2)) { total += en0(a) - st0(a) + 1; ++a; }
+        int cnt = 0;
+        while (a <= b && cnt < 2) { total += en0(b) - st0(b) + 1; --b; ++cnt; }
+        if (a > b) continue;
+        const int mid = a + (b - a) / 2;
+        // which piece is active (constant over the interior)
+        int64_t se, ss;
+        { const int e = en0(mid);
+          if (e == tl - 1 && en0(a) == tl - 1 && en0(b) == tl - 1) se = (int64_t)(tl - 1) * (b - a + 1);
+          else if (e == mid && en0(a) == a && en0(b) == b) se = sum_lin(a, b);
+          else se = sum_half(a, b, w); }
+        { const int s = st0(mid);
+          if (s == 0 && st0(a) == 0 && st0(b) == 0) ss = 0;
+          else if (s == mid - ql + 1 && st0(a) == a - ql + 1 && st0(b) == b - ql + 1) ss = sum_lin(a, b) - (int64_t)(ql - 1) * (b - a + 1);
+          else ss = sum_half(a, b, -(int64_t)w + 1); }
+        total += se - ss + (b - a + 1);
+    }
+    return total;
+}
+
 extern "C" int64_t lesvgpu_ksw_cells(int qlen, int tlen, int max_distance, int* ok)
 {
     const int w = effective_band(qlen, tlen, max_distance);
     int64_t cells = 0;
     if (ok) *ok = 1;
+    if (qlen > 0 && tlen > 0 && band_reaches_end(qlen, tlen, w)) return cells_fast(qlen, tlen, w);
     for (int r = 0; r < qlen + tlen - 1; ++r) {
         const RowGeom g = row_geom(r, qlen, tlen, w);
         if (g.empty()) { if (ok) *ok = 0; break; }
@@ -123,8 +173,9 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         return {0, 0, 0};                                // wider than any cluster: global-memory fallback
     };
     const int nj = (int)jobs.size();
+    const auto t_enter = std::chrono::steady_clock::now();
     struct Launch {
-        int ncta, nt, first, count, n_clusters, max_slots;
+        int ncta, nt, first, count, n_clusters, max_slots, fair;
         size_t stride, smem, arena_off, arena_bytes;
         double work;
         std::vector<int> ids;
@@ -180,14 +231,18 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
         const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
         const int per_sm = L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1;
-        double share = budget * L.work / total_work;                 // SMs this launch may occupy
-        int n = (int)(share * per_sm / sms_per_job);       // round down: never oversubscribe the SMs
-        n = std::max(1, std::min(n, L.count));
+        // Every class is launched wide enough to fill the machine on its own (persistent CTAs pulling from the
+        // class queue): when one class runs dry its SMs go to the pending CTAs of the others, so no SM idles
+        // while another class still has alignments queued.  `fair` = the SMs its share of the work is worth;
+        // the arena fit below takes memory away from the surplus first.
+        const double share = budget * L.work / total_work;
+        int cap = 1 << 20;
         if (L.ncta > 1) {
-            const int cap = ksw_max_clusters(L.nt, L.ncta, L.smem);
+            cap = ksw_max_clusters(L.nt, L.ncta, L.smem);
             if (cap <= 0) { ctx->err = "cluster shape not launchable on this device"; return LESVGPU_E_CUDA; }
-            n = std::min(n, cap);
         }
+        L.fair = std::max(1, std::min(std::min((int)(share * per_sm / sms_per_job), L.count), cap));
+        int n = std::max(1, std::min(std::min(ctx->n_sm * per_sm / sms_per_job, L.count), cap));
         L.n_clusters = n;
     }
     // fit the arenas.  Cluster i of a launch starts with job i of its (size-sorted) queue and only
@@ -199,13 +254,32 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         for (int i = 0; i < L.n_clusters; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
         return b;
     };
+    // what the arena may grow to right now: the configured limit, but never more than 92 % of what is free
+    // (other stages of the library keep buffers of their own on the same device)
+    size_t arena_limit = ctx->arena_limit;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            arena_limit = std::min(arena_limit, (size_t)((free_b + ctx->d_arena.cap) * 0.90));
+    }
     for (;;) {
         arena_need = 0;
         for (Launch& L : launches) { L.arena_off = arena_need; L.arena_bytes = footprint(L); arena_need += L.arena_bytes; }
-        if (arena_need <= ctx->arena_limit) break;
+        if (arena_need <= arena_limit) break;
+        // Take memory from the surplus first: the minor classes down to 1.5 x their fair share (cluster launches
+        // run at a lower rate per SM, a bare fair share would make them the long pole), then the class with
+        // the most work (it runs longest and absorbs the SMs the others release), then everybody's rest.
+        const Launch* major = &launches[0];
+        for (const Launch& L : launches) if (L.work > major->work) major = &L;
         Launch* big = nullptr;
         for (Launch& L : launches)
-            if (L.n_clusters > 1 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+            if (&L != major && L.n_clusters > (3 * L.fair + 1) / 2 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+        if (!big)
+            for (Launch& L : launches)
+                if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+        if (!big)
+            for (Launch& L : launches)                   // ... then below the fair share
+                if (L.n_clusters > 1 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
         --big->n_clusters;
     }
@@ -234,13 +308,14 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_order.reserve(nj));
     CK(ctx->d_counter.reserve(launches.size()));
     CK(ctx->d_aoff.reserve(arena_offs.size()));
-    CK(ctx->d_arena.reserve(arena_need));
+    CK(ctx->d_arena.reserve_exact(arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
     CK(ctx->h_outs.reserve(nj));
     if (want_cigar) CK(ctx->h_cigar.reserve(cigar_words));
     if (want_runs) CK(ctx->h_runs.reserve((size_t)nj * kSigCap));
 
     cudaStream_t s = ctx->stream;
+    const auto t_planned = std::chrono::steady_clock::now();
     CK(cudaEventRecord(ctx->ev[0], s));
     CK(cudaMemcpyAsync(ctx->d_raw.p, ctx->h_raw.p, raw_bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KswJob) * nj, cudaMemcpyHostToDevice, s));
@@ -253,10 +328,14 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], s));
     // the launch classes run concurrently: one side stream each, joined back into the main stream
+    static const bool dbg = getenv("LESV_KSW_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> dbg_ev;
+    if (dbg) { dbg_ev.resize(2 * launches.size()); for (auto& e : dbg_ev) cudaEventCreate(&e); }
     for (size_t li = 0; li < launches.size(); ++li) {
         const Launch& L = launches[li];
         cudaStream_t ls = ctx->side[li % kSideStreams];
         CK(cudaStreamWaitEvent(ls, ctx->ev[2], 0));
+        if (dbg) cudaEventRecord(dbg_ev[2 * li], ls);
         if (L.ncta > 0)
             CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
                           ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
@@ -268,6 +347,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             CK(cudaGetLastError());
         }
     }
+    if (dbg) for (size_t li = 0; li < launches.size(); ++li) cudaEventRecord(dbg_ev[2 * li + 1], ctx->side[li % kSideStreams]);
     for (size_t k = 0; k < std::min<size_t>(launches.size(), kSideStreams); ++k) {
         CK(cudaEventRecord(ctx->side_done[k], ctx->side[k]));
         CK(cudaStreamWaitEvent(s, ctx->side_done[k], 0));
@@ -286,6 +366,23 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaStreamSynchronize(s));
 
+    if (dbg) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ksw debug] host: plan+alloc %.1f ms, launch+wait %.1f ms\n",
+                std::chrono::duration<double, std::milli>(t_planned - t_enter).count(),
+                std::chrono::duration<double, std::milli>(t_done - t_planned).count());
+        for (size_t li = 0; li < launches.size(); ++li) {
+            const Launch& L = launches[li];
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->ev[2], dbg_ev[2 * li]); cudaEventElapsedTime(&b, ctx->ev[2], dbg_ev[2 * li + 1]);
+            double cells = 0;
+            for (int k : L.ids) { int ok = 0; cells += (double)lesvgpu_ksw_cells(jobs[k].qlen, jobs[k].tlen, jobs[k].w, &ok); }
+            fprintf(stderr, "[ksw debug] launch %zu: ncta=%d tier=%d jobs=%d ctas/clusters=%d cells=%.1fG start=%.1f end=%.1f ms -> %.0f GCUPS on %d SMs\n",
+                    li, L.ncta, L.nt, L.count, L.n_clusters, cells / 1e9, a, b, cells / 1e6 / std::max(0.001f, b - a),
+                    L.n_clusters * std::max(1, L.ncta) / (L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1));
+        }
+        for (auto& e : dbg_ev) cudaEventDestroy(e);
+    }
     lesvgpu_timing& T = ctx->timing;
     cudaEventElapsedTime(&T.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&T.pack_ms, ctx->ev[1], ctx->ev[2]);
@@ -297,7 +394,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     g_lesv_launches += (unsigned long long)T.kernel_launches;
     T.h2d_bytes = raw_bytes + sizeof(KswJob) * nj + sizeof(int) * nj;
     T.d2h_bytes = d2h;
-    for (const KswJob& J : jobs) { int ok = 0; T.dp_cells += (uint64_t)lesvgpu_ksw_cells(J.qlen, J.tlen, J.w, &ok); }
+    for (const KswJob& J : jobs) T.dp_cells += (uint64_t)cells_fast(J.qlen, J.tlen, J.w);
     return LESVGPU_OK;
 }
 

@@ -58,3 +58,24 @@ def test_no_cpu_fallback_without_gpu():
         return
     h = C.c_void_p()
     assert capi.load().lesvgpu_ctx_create(0, 0, C.byref(h)) == capi.E_NOGPU
+
+
+def test_library_cell_count_equals_oracle_loop():
+    """lesvgpu_ksw_cells (closed form when the band reaches the last cell) == the oracle's row-by-row count
+    (ksw2_extd2_sse.c:124-138); host arithmetic only, no GPU."""
+    from lesv_b200 import capi
+    rng = np.random.default_rng(12)
+    n_ok = 0
+    for it in range(4000):
+        ql, tl = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+        w = abs(ql - tl) + int(rng.integers(0, 4000)) if it % 3 else int(rng.integers(1, 3000))
+        if it % 7 == 0:
+            w = max(ql, tl)
+        if it % 11 == 0:
+            ql = 1 + it % 5
+        w = max(w, 1)
+        got = capi.ksw_cells(ql, tl, w)
+        exp = H.oracle_cells(ql, tl, w)
+        assert got == exp, (ql, tl, w, got, exp)
+        n_ok += exp[1]
+    assert n_ok > 2000
