@@ -42,7 +42,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from lesv_b200 import synth  # noqa: E402
+from lesv_b200 import shard, synth  # noqa: E402
 
 READ_LEN = 50000
 REF_LEN = 50_000_000
@@ -270,7 +270,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ref, sample = make_genomes(args.seed, args.ref_len)                          # replicated on every GPU
-    reads = make_reads(sample, args.reads_per_step, args.seed + 1000 * (rank + 1))   # this rank's shard
+    reads = make_reads(sample, args.reads_per_step, shard.read_seed_of_rank(args.seed, rank))   # this rank's shard
     subject_pac, _ = pack_pac([ref])
     query_pac, qoffs = pack_pac(reads)
     qsizes = np.array([len(r) for r in reads], dtype=np.int64)
@@ -342,13 +342,8 @@ def main():
     launches = lib.lesvgpu_launch_count() - launches0
     dev_ms = sum(acc["dev"].values())
 
-    stats = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(acc["bases"]), float(acc["cells"]), float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max = [float(x) for x in stats.tolist()]
-    all_bases, all_cells, all_launches = [float(x) for x in tot.tolist()]
+    dev_ms_max, wall_ms_max, all_bases, all_cells, all_launches = shard.reduce_stats(
+        dev_ms, wall_ms, float(acc["bases"]), float(acc["cells"]), float(launches), world, device="cuda")
 
     if rank == 0:
         K = args.steps

@@ -164,6 +164,10 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
         static const int tiers[] = {64, 96, 128, 160, 320, 512, 640};
+        static const int split2 = getenv("LESV_KSW_SPLIT2") ? atoi(getenv("LESV_KSW_SPLIT2")) : 0;
+        // experiment: alignments of 321..640 blocks as 2-CTA clusters of <= 320 threads, two CTAs (of different
+        // alignments) per SM, so one CTA's row barrier overlaps the other's arithmetic
+        if (split2 && wb > split2 && wb <= 640) return {2, 320, ((wb + 1) / 2 + 31) / 32 * 32};
         if (wb <= 640) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};
@@ -230,7 +234,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         L.smem = ksw_smem_bytes(mq, mt);
         if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
         const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
-        const int per_sm = L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1;
+        const int per_sm = (L.ncta == 1 || L.nt <= 320) ? ksw_ctas_per_sm(L.nt) : 1;
         // Every class is launched wide enough to fill the machine on its own (persistent CTAs pulling from the
         // class queue): when one class runs dry its SMs go to the pending CTAs of the others, so no SM idles
         // while another class still has alignments queued.  `fair` = the SMs its share of the work is worth;

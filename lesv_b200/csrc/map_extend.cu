@@ -267,63 +267,146 @@ __device__ __forceinline__ int gap_class(int n, int m)
     return 4;
 }
 
-__global__ void __launch_bounds__(32)
+// One warp per candidate.  Co-diagonal seed runs are independent (s_extract_mem works on one run at a time), so
+// the lanes take runs round-robin: count, prefix-sum, write.  Trace seeds are a short sequential filter (lane 0);
+// the gap jobs follow from consecutive trace seeds in closed form (enumerate_gaps), 32 at a time.
+__global__ void __launch_bounds__(128)
 trace_prep_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
                   const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, uint32_t n_cand,
                   const int* __restrict__ cand_info, const int* __restrict__ hs_w, const int* __restrict__ hs_r, int word,
+                  int* __restrict__ run_start /* scratch, per seed */, int* __restrict__ run_off /* scratch, per seed */,
                   PrepBufs pb, CandPrep* __restrict__ preps)
 {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    const uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (x >= n_cand) return;
     const int c = cand_list[x];                       // = 3 * window + rank
     const WinDev W = wins[c / kMaxCandPerWindow];
     const ReadDev rd = reads[W.read];
     const int* ci = cand_info + 3 * (size_t)c;
     const int seed_off = ci[1], seed_cnt = ci[2];
+    const int* sw = hs_w + seed_off;
+    const int* sr = hs_r + seed_off;
+    int* rs = run_start + seed_off;
+    int* ro = run_off + seed_off;
     auto Q = [&](int i) -> uint32_t {
         return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)i)) : pac_code(qpac, rd.off + (uint32_t)i);
     };
     auto S = [&](int j) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)j); };
     CandPrep P;
     P.n_mems = 0; P.tsc = 0; P.status = lesvtb::kOk; P.job_first = 0; P.mem_off = 0;
-    // MEMs between the chain's seeds can outnumber the seeds: count, then take room from the pool
-    int n_mems = lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, (lesvtb::Mem*)nullptr, 0);
+    // runs of seeds on one diagonal (init_hit_finder.c:480-492)
+    int G = 0;
+    for (int base = 0; base < seed_cnt; base += 32) {
+        const int j = base + lane;
+        const bool head = j < seed_cnt && (j == 0 || sw[j] - sw[j - 1] != sr[j] - sr[j - 1]);
+        const unsigned bal = __ballot_sync(kFull, head);
+        if (head) rs[G + __popc(bal & lt_mask)] = j;
+        G += __popc(bal);
+    }
+    __syncwarp();
+    auto run_of = [&](int g, int& ri, int& wi, int& ml) {
+        const int i = rs[g], jend = g + 1 < G ? rs[g + 1] : seed_cnt;
+        ri = sr[i]; wi = sw[i]; ml = sw[jend - 1] + word - sw[i];
+    };
+    for (int g = lane; g < G; g += 32) {
+        int ri, wi, ml;
+        run_of(g, ri, wi, ml);
+        ro[g] = lesvtb::extract_mem_run(Q, S, ri, wi, ml, word, (lesvtb::Mem*)nullptr, 0, 0);
+    }
+    __syncwarp();
+    int n_mems = 0;
+    for (int base = 0; base < G; base += 32) {        // exclusive prefix sum of the per-run counts
+        const int g = base + lane;
+        const int cnt = g < G ? ro[g] : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += v; }
+        if (g < G) ro[g] = n_mems + incl - cnt;
+        n_mems += __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
     if (n_mems > 0) {
         const unsigned long long need = 2ull * (unsigned)n_mems + 2;
-        const unsigned long long off = atomicAdd(pb.mem_counter, need);
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(pb.mem_counter, need);
+        off = __shfl_sync(kFull, off, 0);
         if (off + need > pb.mem_cap) { P.status = lesvtb::kScratchOverflow; n_mems = 0; }
         else {
             lesvtb::Mem* mems = pb.mem_pool + off;
             lesvtb::Mem* ts = mems + n_mems;
-            lesvtb::extract_mems(Q, S, hs_w + seed_off, hs_r + seed_off, seed_cnt, word, mems, n_mems);
+            for (int g = lane; g < G; g += 32) {
+                int ri, wi, ml;
+                run_of(g, ri, wi, ml);
+                lesvtb::extract_mem_run(Q, S, ri, wi, ml, word, mems, n_mems, ro[g]);
+            }
+            __syncwarp();
             P.mem_off = off;
-            P.tsc = lesvtb::trace_points(mems, n_mems, ts);
-            const int n_jobs = P.tsc - 1;
+            int tsc = 0;
+            if (lane == 0) tsc = lesvtb::trace_points(mems, n_mems, ts);
+            tsc = __shfl_sync(kFull, tsc, 0);
+            __syncwarp();
+            P.tsc = tsc;
+            const int n_jobs = tsc - 1;
+            const int E = 10, E2 = 20;
+            auto gap_of = [&](int i, int& qa, int& n, int& sa, int& m) {          // enumerate_gaps, gap i
+                const lesvtb::Mem a = ts[i], b = ts[i + 1];
+                if (a.len > E2) { qa = a.q + a.len - E; sa = a.s + a.len - E; }
+                else if (i == 0) { qa = a.q; sa = a.s; }
+                else { qa = a.q + a.len / 2; sa = a.s + a.len / 2; }
+                int qto, sto;
+                if (b.len > E2) { qto = b.q + E; sto = b.s + E; }
+                else { qto = b.q + b.len / 2; sto = b.s + b.len / 2; }
+                n = qto - qa; m = sto - sa;
+            };
             unsigned long long bytes = 0;
-            lesvtb::enumerate_gaps(ts, P.tsc, [&](int, int, int n, int, int m) { bytes += (unsigned)(n + m); });
+            for (int i = lane; i < n_jobs; i += 32) { int qa, n, sa, m; gap_of(i, qa, n, sa, m); bytes += (unsigned)(n + m); }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(kFull, bytes, d);
             if (n_jobs > 0) {
-                const uint32_t j0 = atomicAdd(pb.job_counter, (uint32_t)n_jobs);
-                const unsigned long long s0 = atomicAdd(pb.slot_counter, bytes);
+                uint32_t j0 = 0;
+                unsigned long long s0 = 0;
+                if (lane == 0) { j0 = atomicAdd(pb.job_counter, (uint32_t)n_jobs); s0 = atomicAdd(pb.slot_counter, bytes); }
+                j0 = __shfl_sync(kFull, j0, 0); s0 = __shfl_sync(kFull, s0, 0);
                 if ((unsigned long long)j0 + (unsigned)n_jobs > pb.jobs_cap || s0 + bytes > pb.slot_cap) P.status = lesvtb::kScratchOverflow;
                 else {
                     P.job_first = j0;
                     unsigned long long slot = s0;
-                    lesvtb::enumerate_gaps(ts, P.tsc, [&](int i, int qa, int n, int sa, int m) {
-                        GapJob J;
-                        J.qa = qa; J.n = n; J.sa = sa; J.m = m; J.cand = x; J.len = 0; J.slot = slot;
-                        slot += (unsigned)(n + m);
-                        pb.jobs[j0 + i] = J;
-                        if (n > 0 && m > 0) {                      // edlib_wrapper.c:43: nothing to align otherwise
-                            const int cls = gap_class(n, m);
-                            pb.queue[cls][atomicAdd(&pb.queue_count[cls], 1u)] = j0 + (uint32_t)i;
+                    for (int base = 0; base < n_jobs; base += 32) {
+                        const int i = base + lane;
+                        int qa = 0, n = 0, sa = 0, m = 0;
+                        if (i < n_jobs) gap_of(i, qa, n, sa, m);
+                        const unsigned long long sz = i < n_jobs ? (unsigned)(n + m) : 0u;
+                        unsigned long long incl = sz;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const unsigned long long v = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += v; }
+                        int cls = -1;
+                        if (i < n_jobs) {
+                            GapJob J;
+                            J.qa = qa; J.n = n; J.sa = sa; J.m = m; J.cand = x; J.len = 0; J.slot = slot + incl - sz;
+                            pb.jobs[j0 + i] = J;
+                            if (n > 0 && m > 0) cls = gap_class(n, m);          // edlib_wrapper.c:43: nothing to align otherwise
                         }
-                    });
+#pragma unroll
+                        for (int k = 0; k < kGapClasses; ++k) {
+                            const unsigned bal = __ballot_sync(kFull, cls == k);
+                            if (bal) {
+                                uint32_t qb = 0;
+                                if (lane == __ffs(bal) - 1) qb = atomicAdd(&pb.queue_count[k], (uint32_t)__popc(bal));
+                                qb = __shfl_sync(kFull, qb, __ffs(bal) - 1);
+                                if (cls == k) pb.queue[k][qb + __popc(bal & lt_mask)] = j0 + (uint32_t)i;
+                            }
+                        }
+                        slot += __shfl_sync(kFull, incl, 31);
+                    }
                 }
             }
         }
     }
     P.n_mems = n_mems;
-    preps[x] = P;
+    if (lane == 0) preps[x] = P;
 }
 
 template <int CELLS, int CLS>
@@ -792,8 +875,9 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         pb.slot_cap = slot_cap; pb.slot_counter = E->d_pool_counter.p + 2;
         for (int k = 0; k < kGapClasses; ++k) pb.queue[k] = E->d_queue.p + (size_t)k * jobs_cap;
         pb.queue_count = c32 + 2;
-        trace_prep_kernel<<<nblk(n_cand, 32), 32, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, n_cand,
-                                                          E->d_cand_info.p, E->d_hs_w.p, E->d_hs_r.p, word, pb, E->d_preps.p); ++g_lesv_launches;
+        trace_prep_kernel<<<nblk((uint64_t)n_cand * 32, 128), 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p,
+                                                                           E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_hs_w.p, E->d_hs_r.p,
+                                                                           word, E->d_f.p, E->d_p.p, pb, E->d_preps.p); ++g_lesv_launches;
         CK(cudaEventRecord(E->ev[0], s));
         const unsigned small_grid = (unsigned)dev_sms * 8;
         gap_small_kernel<kSmallCells0, 0><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,

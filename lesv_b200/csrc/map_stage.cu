@@ -22,6 +22,7 @@
 //   - seeds with equal subject offset enter the chaining in ascending query offset (the reference
 //     leaves that order to an unstable sort, sort_sr_hit_seeds.cpp:53-56).
 #include "map_state.cuh"
+#include "chain_warp.cuh"
 #include "gpu_prims.cuh"
 
 #include <algorithm>
@@ -221,38 +222,46 @@ struct ChainScratch {
     lesvchain::IntPair* u;
 };
 
+// One warp per (read strand, contig) segment: seed list on lane 0, chaining DP on the warp (chain_warp.cuh),
+// backtracking and joining on lane 0.
 __global__ void __launch_bounds__(128)
 chain_kernel(const uint64_t* __restrict__ mkey, const uint64_t* __restrict__ mval, const uint32_t* __restrict__ seg_start,
              uint32_t n_seg, uint32_t n_match, int soff_bits, const uint64_t* __restrict__ seq_off, int nseq, int k,
              int min_cnt, int min_score, ChainScratch sc, DdfHit* __restrict__ hits, uint32_t hit_cap,
              uint32_t* __restrict__ hit_counter, uint32_t* __restrict__ seg_ctx_sid)
 {
-    const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (sg >= n_seg) return;
     const uint32_t a = seg_start[sg], b = sg + 1 < n_seg ? seg_start[sg + 1] : n_match;
     const uint64_t m = (1ull << soff_bits) - 1;
     const uint32_t ctx = (uint32_t)(mkey[a] >> soff_bits);
     const int sid = contig_of(seq_off, nseq, mkey[a] & m);
-    seg_ctx_sid[2 * sg] = ctx; seg_ctx_sid[2 * sg + 1] = (uint32_t)sid;
+    if (lane == 0) { seg_ctx_sid[2 * sg] = ctx; seg_ctx_sid[2 * sg + 1] = (uint32_t)sid; }
     if ((int)(b - a) < min_cnt) return;                                  // chain_and_extend_kmer_matches.c:167
     const uint64_t sbeg = seq_off[sid];
     lesvchain::Seed* seeds = sc.seeds + a;
     int n = 0;
-    for (uint32_t i = a; i < b;) {                                       // :105-125: drop offsets hit by > 4 query positions
-        uint32_t j = i + 1;
-        while (j < b && mkey[j] == mkey[i]) ++j;
-        if (j - i <= 4)
-            for (uint32_t x = i; x < j; ++x) {
-                seeds[n].q = (int)mval[x]; seeds[n].s = (int)((mkey[x] & m) - sbeg); seeds[n].len = k; ++n;
-            }
-        i = j;
+    if (lane == 0) {
+        for (uint32_t i = a; i < b;) {                                   // :105-125: drop offsets hit by > 4 query positions
+            uint32_t j = i + 1;
+            while (j < b && mkey[j] == mkey[i]) ++j;
+            if (j - i <= 4)
+                for (uint32_t x = i; x < j; ++x) {
+                    seeds[n].q = (int)mval[x]; seeds[n].s = (int)((mkey[x] & m) - sbeg); seeds[n].len = k; ++n;
+                }
+            i = j;
+        }
     }
+    n = __shfl_sync(0xFFFFFFFFu, n, 0);
     if (n == 0) return;
+    const lesvchain::Params P = lesvchain::make_params(min_cnt, min_score);
+    lesvchain::score_seeds_warp(P, seeds, n, false, sc.f + a, sc.p + a, sc.t + a, sc.v + a);
+    if (lane != 0) return;
     lesvchain::Hit pre[lesvchain::kMaxChains], out[lesvchain::kMaxJoined];
     int members[lesvchain::kMaxChains], n_pre = 0;
-    const lesvchain::Params P = lesvchain::make_params(min_cnt, min_score);
-    const int nh = lesvchain::find_candidates(P, seeds, n, false, sc.f + a, sc.p + a, sc.t + a, sc.v + a, sc.u + a,
-                                              pre, &n_pre, out, members);
+    const int nh = lesvchain::find_candidates_scored(P, seeds, n, sc.f + a, sc.p + a, sc.t + a, sc.v + a, sc.u + a,
+                                                     pre, &n_pre, out, members);
     if (nh == 0) return;
     const uint32_t o = atomicAdd(hit_counter, (uint32_t)nh);
     if (o + nh > hit_cap) return;                                        // host checks the counter and retries
@@ -629,7 +638,7 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
         CK(cudaMemsetAsync(M->d_counter.p + 1, 0, 4, s));
         CK(cudaMemsetAsync(M->d_seg_info.p, 0, sizeof(uint32_t) * 2 * n_seg, s));
         ChainScratch sc{M->d_seeds.p, M->d_f.p, M->d_p.p, M->d_t.p, M->d_v.p, M->d_u.p};
-        chain_kernel<<<nblocks(n_seg, 128), 128, 0, s>>>(K, V, M->d_seg_start.p, n_seg, n_match, M->soff_bits, M->d_seq_off.p,
+        chain_kernel<<<nblocks((uint64_t)n_seg * 32, 128), 128, 0, s>>>(K, V, M->d_seg_start.p, n_seg, n_match, M->soff_bits, M->d_seq_off.p,
                                                          (int)M->sseqs.size(), k, min_cnt, min_score, sc, M->d_hits.p, hit_cap,
                                                          M->d_counter.p + 1, M->d_seg_info.p); ++g_lesv_launches;
         CK(cudaEventRecord(ev[5], s));

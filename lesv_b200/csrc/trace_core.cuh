@@ -266,6 +266,29 @@ TRC_HD inline int shw_path(FQ Q, int n, FT T, int m, Scratch& sc, uint8_t* out, 
 
 // ---- MEMs of a chain (init_hit_finder.c:469-505, 255-297) -------------------------------------------
 // chain seeds: (w = window offset, r = read offset), word_size bases each, in chain order.
+// s_extract_mem (init_hit_finder.c:255-297) over one co-diagonal run of seeds: ml bases starting at read
+// offset ri / window offset wi.  Appends to mems[n..] (mems == nullptr: count only); returns the new n, -1 if full.
+template <class FQ, class FS>
+TRC_HD inline int extract_mem_run(FQ Q, FS S, int ri, int wi, int ml, int word_size, Mem* mems, int cap, int n)
+{
+    int x = 0;
+    while (x < ml) {
+        while (x < ml) { if (Q(ri) == S(wi)) break; ++ri; ++wi; ++x; }
+        if (ml - x < word_size) break;
+        int y = x;
+        while (y < ml) { if (Q(ri) != S(wi)) break; ++ri; ++wi; ++y; }
+        if (y - x >= word_size) {
+            if (mems) {
+                if (n >= cap) return -1;
+                mems[n].len = y - x; mems[n].q = ri - (y - x); mems[n].s = wi - (y - x);
+            }
+            ++n;
+        }
+        x = y;
+    }
+    return n;
+}
+
 template <class FQ, class FS>
 TRC_HD inline int extract_mems(FQ Q, FS S, const int* seed_w, const int* seed_r, int n_seeds, int word_size,
                                Mem* mems, int cap)
@@ -275,22 +298,8 @@ TRC_HD inline int extract_mems(FQ Q, FS S, const int* seed_w, const int* seed_r,
         int j = i + 1;
         while (j < n_seeds && seed_w[j] - seed_w[i] == seed_r[j] - seed_r[i]) ++j;
         const int ml = seed_w[j - 1] + word_size - seed_w[i];
-        // s_extract_mem(read, window, read off, window off, ml, word_size)
-        int x = 0, ri = seed_r[i], wi = seed_w[i];
-        while (x < ml) {
-            while (x < ml) { if (Q(ri) == S(wi)) break; ++ri; ++wi; ++x; }
-            if (ml - x < word_size) break;
-            int y = x;
-            while (y < ml) { if (Q(ri) != S(wi)) break; ++ri; ++wi; ++y; }
-            if (y - x >= word_size) {
-                if (mems) {                            // mems == nullptr: count only
-                    if (n >= cap) return -1;
-                    mems[n].len = y - x; mems[n].q = ri - (y - x); mems[n].s = wi - (y - x);
-                }
-                ++n;
-            }
-            x = y;
-        }
+        n = extract_mem_run(Q, S, seed_r[i], seed_w[i], ml, word_size, mems, cap, n);
+        if (n < 0) return -1;
         i = j;
     }
     return n;
