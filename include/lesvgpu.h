@@ -312,6 +312,9 @@ void lesvgpu_map_last_timing(const lesvgpu_ctx* ctx, lesvgpu_map_timing* t);
  * the output of edlib_nw (algo/edlib_wrapper.c:32-111).  ops_out: n + m bytes. */
 int lesvgpu_debug_edlib_nw(lesvgpu_ctx* ctx, const uint8_t* query, int n, const uint8_t* target, int m,
                            uint8_t* ops_out, int* n_ops);
+/* the same through the thread-block variant used for giant gaps (strips pipelined over the block's warps) */
+int lesvgpu_debug_edlib_nw_block(lesvgpu_ctx* ctx, const uint8_t* query, int n, const uint8_t* target, int m,
+                                 uint8_t* ops_out, int* n_ops);
 
 /* DP cells ksw_extd2_sse visits for one pair (sum over anti-diagonals of the band width,
  * algo/ksw2_extd2_sse.c:124-138); *ok = 0 if the band cuts the matrix. Host arithmetic only. */

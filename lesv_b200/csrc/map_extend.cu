@@ -439,28 +439,63 @@ struct SlabBufs {
     size_t cells, peq_words;
 };
 
-// One warp per gap (trace_warp.cuh), persistent warps with a 1 MB slab each.
-__global__ void __launch_bounds__(128)
+// Persistent blocks of kBigWarps warps, a 1 MB slab per warp.  Giant gaps (edlib's Hirschberg route or > 16 K
+// block-columns) first, one per block, the strips of the query pipelined over the block's warps
+// (trace_warp.cuh: nw_path_cta); then the big ones, one per warp (nw_path_warp).
+constexpr int kBigWarps = 8;
+
+__global__ void __launch_bounds__(kBigWarps * 32)
 gap_big_kernel(const WinDev* __restrict__ wins, const ReadDev* __restrict__ reads, const uint8_t* __restrict__ qpac,
                const uint8_t* __restrict__ spac, const int* __restrict__ cand_list, GapJob* __restrict__ jobs,
                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ giant_queue,
                const uint32_t* __restrict__ queue_count, uint8_t* __restrict__ slots,
                SlabBufs sb, int8_t* __restrict__ carry_pool, size_t carry_stride, uint32_t* __restrict__ work_counter)
 {
+    __shared__ int progress[lesvtw::kMaxStrips];
+    __shared__ int sh_len;
+    __shared__ uint32_t sh_job;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     lesvtb::Scratch sc;
-    sc.P = sb.P + warp * sb.cells; sc.M = sb.M + warp * sb.cells; sc.score = sb.score + warp * sb.cells;
     sc.peq = nullptr; sc.cap_cells = sb.cells; sc.cap_peq = 0;
     sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
+    const uint32_t n_giant = queue_count[4], n_big = queue_count[3];
+    // ---- giants: the whole block on one gap, the slab and carry buffers of the block's first warp onwards ----
+    {
+        const size_t w0 = (size_t)blockIdx.x * kBigWarps;
+        sc.P = sb.P + w0 * sb.cells; sc.M = sb.M + w0 * sb.cells; sc.score = sb.score + w0 * sb.cells;
+        sc.cap_cells = sb.cells * kBigWarps;             // the slabs of the block's warps are contiguous
+        int8_t* carry = carry_pool + w0 * carry_stride;
+        for (;;) {
+            if (threadIdx.x == 0) sh_job = atomicAdd(work_counter, 1u);
+            __syncthreads();
+            const uint32_t j = sh_job;
+            __syncthreads();
+            if (j >= n_giant) break;
+            GapJob& J = jobs[giant_queue[j]];
+            const WinDev W = wins[cand_list[J.cand] / kMaxCandPerWindow];
+            const ReadDev rd = reads[W.read];
+            const int qa = J.qa, sa = J.sa, n = J.n, m = J.m;
+            auto fq = [&](int i) -> uint32_t {
+                return W.strand ? 3u - pac_code(qpac, rd.off + (rd.len - 1 - (uint32_t)(qa + i))) : pac_code(qpac, rd.off + (uint32_t)(qa + i));
+            };
+            auto fs = [&](int i) -> uint32_t { return pac_code(spac, W.s_off + (uint32_t)(sa + i)); };
+            const int r = lesvtw::nw_path_cta<kBigWarps>(fq, n, fs, m, sc, carry, carry_stride, progress, &sh_len, slots + J.slot,
+                                                         (size_t)(n + m));
+            if (threadIdx.x == 0) J.len = r;
+            __syncthreads();
+        }
+    }
+    // ---- big gaps: one per warp ---------------------------------------------------------------------------
+    sc.cap_cells = sb.cells;
+    sc.P = sb.P + warp * sb.cells; sc.M = sb.M + warp * sb.cells; sc.score = sb.score + warp * sb.cells;
     int8_t* carry = carry_pool + warp * carry_stride;
-    const uint32_t n_giant = queue_count[4], n_jobs = n_giant + queue_count[3];
     for (;;) {
         uint32_t j = 0;
-        if (lane == 0) j = atomicAdd(work_counter, 1u);
+        if (lane == 0) j = atomicAdd(work_counter + 1, 1u);
         j = __shfl_sync(0xFFFFFFFFu, j, 0);
-        if (j >= n_jobs) break;
-        GapJob& J = jobs[j < n_giant ? giant_queue[j] : queue[j - n_giant]];
+        if (j >= n_big) break;
+        GapJob& J = jobs[queue[j]];
         const WinDev W = wins[cand_list[J.cand] / kMaxCandPerWindow];
         const ReadDev rd = reads[W.read];
         const int qa = J.qa, sa = J.sa, n = J.n, m = J.m;
@@ -890,7 +925,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         sb.P = E->d_P.p; sb.M = E->d_M.p; sb.score = E->d_score.p; sb.peq = E->d_peq.p; sb.cells = cells; sb.peq_words = peq_words;
         const size_t carry_stride = ((size_t)max_wlen + 64 + 15) & ~(size_t)15;
         CK(E->d_carry.reserve(carry_stride * n_big_warps));
-        gap_big_kernel<<<n_big_warps / 4, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
+        gap_big_kernel<<<n_big_warps / kBigWarps, kBigWarps * 32, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
                                                        pb.queue[3], pb.queue[4], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
                                                        E->d_counters.p + 3); ++g_lesv_launches;
         CK(cudaEventRecord(E->ev[1], s));
@@ -1030,23 +1065,50 @@ debug_nw_kernel(const uint8_t* __restrict__ q, int n, const uint8_t* __restrict_
     const int r = lesvtw::nw_path_warp(fq, n, ft, m, sc, carry, out, (size_t)(n + m));
     if (threadIdx.x == 0) *n_out = r;
 }
+
+__global__ void __launch_bounds__(kBigWarps * 32)
+debug_nw_block_kernel(const uint8_t* __restrict__ q, int n, const uint8_t* __restrict__ t, int m, SlabBufs sb, int8_t* carry,
+                      size_t carry_stride, uint8_t* __restrict__ out, int* __restrict__ n_out)
+{
+    __shared__ int progress[lesvtw::kMaxStrips];
+    __shared__ int sh_len;
+    lesvtb::Scratch sc;
+    sc.P = sb.P; sc.M = sb.M; sc.score = sb.score; sc.peq = nullptr; sc.cap_cells = sb.cells; sc.cap_peq = 0;
+    sc.trim_table = nullptr; sc.trim_score = nullptr; sc.path_ave = 0;
+    auto fq = [&](int i) -> uint32_t { return q[i]; };
+    auto ft = [&](int j) -> uint32_t { return t[j]; };
+    const int r = lesvtw::nw_path_cta<kBigWarps>(fq, n, ft, m, sc, carry, carry_stride, progress, &sh_len, out, (size_t)(n + m));
+    if (threadIdx.x == 0) *n_out = r;
+}
 }  // namespace
 
-extern "C" int lesvgpu_debug_edlib_nw(lesvgpu_ctx* ctx, const uint8_t* q, int n, const uint8_t* t, int m, uint8_t* ops_out, int* n_ops)
+static int debug_nw(lesvgpu_ctx* ctx, const uint8_t* q, int n, const uint8_t* t, int m, uint8_t* ops_out, int* n_ops, bool block)
 {
     if (!ctx || !q || !t || !ops_out || !n_ops || n < 0 || m < 0) return LESVGPU_E_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
     const size_t cells = std::max<size_t>(52500, 2 * ((size_t)n + 1));
+    const size_t carry_stride = ((size_t)m + 64 + 15) & ~(size_t)15;
     DevBuf<uint64_t> P, Mv; DevBuf<int> score; DevBuf<uint8_t> dq, dt, dout; DevBuf<int8_t> carry; DevBuf<int> dn;
     CK(P.reserve(cells)); CK(Mv.reserve(cells)); CK(score.reserve(cells)); CK(dq.reserve(n + 1)); CK(dt.reserve(m + 1));
-    CK(dout.reserve((size_t)n + m + 1)); CK(carry.reserve(m + 64)); CK(dn.reserve(1));
+    CK(dout.reserve((size_t)n + m + 1)); CK(carry.reserve(carry_stride * kBigWarps)); CK(dn.reserve(1));
     CK(cudaMemcpy(dq.p, q, n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt.p, t, m, cudaMemcpyHostToDevice));
     SlabBufs sb{P.p, Mv.p, score.p, nullptr, cells, 0};
-    debug_nw_kernel<<<1, 32, 0, ctx->stream>>>(dq.p, n, dt.p, m, sb, carry.p, dout.p, dn.p); ++g_lesv_launches;
+    if (block) debug_nw_block_kernel<<<1, kBigWarps * 32, 0, ctx->stream>>>(dq.p, n, dt.p, m, sb, carry.p, carry_stride, dout.p, dn.p);
+    else debug_nw_kernel<<<1, 32, 0, ctx->stream>>>(dq.p, n, dt.p, m, sb, carry.p, dout.p, dn.p);
+    ++g_lesv_launches;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpy(n_ops, dn.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (*n_ops > 0) CK(cudaMemcpy(ops_out, dout.p, *n_ops, cudaMemcpyDeviceToHost));
     P.release(); Mv.release(); score.release(); dq.release(); dt.release(); dout.release(); carry.release(); dn.release();
     return LESVGPU_OK;
+}
+
+extern "C" int lesvgpu_debug_edlib_nw(lesvgpu_ctx* ctx, const uint8_t* q, int n, const uint8_t* t, int m, uint8_t* ops_out, int* n_ops)
+{
+    return debug_nw(ctx, q, n, t, m, ops_out, n_ops, false);
+}
+extern "C" int lesvgpu_debug_edlib_nw_block(lesvgpu_ctx* ctx, const uint8_t* q, int n, const uint8_t* t, int m, uint8_t* ops_out, int* n_ops)
+{
+    return debug_nw(ctx, q, n, t, m, ops_out, n_ops, true);
 }

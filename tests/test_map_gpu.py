@@ -172,9 +172,10 @@ def test_warp_edlib_nw_equals_sequential_restatement(ctx):
     from lesv_b200.synth import mutate
     lib = ctx.lib
     lib.lesvgpu_debug_edlib_nw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.lesvgpu_debug_edlib_nw_block.argtypes = lib.lesvgpu_debug_edlib_nw.argtypes
     em = H.trace_emul()
     rng = np.random.default_rng(21)
-    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 500, 1000, 2047, 2048, 2049, 2100, 3000, 4100, 5000, 9000]
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 500, 1000, 2047, 2048, 2049, 2100, 3000, 4100, 5000, 9000, 17000]
     n_h = 0
     for it, n in enumerate(sizes * 2):
         two = it % 5 == 3                                   # two-letter alphabet: many co-optimal paths and splits
@@ -194,4 +195,7 @@ def test_warp_edlib_nw_equals_sequential_restatement(ctx):
         ng = C.c_int()
         assert lib.lesvgpu_debug_edlib_nw(ctx.h, H._ptr(q), len(q), H._ptr(t), len(t), H._ptr(got), C.byref(ng)) == 0
         assert ng.value == ne and np.array_equal(got[:ne], exp[:ne]), (it, len(q), len(t))
+        got[:] = 0
+        assert lib.lesvgpu_debug_edlib_nw_block(ctx.h, H._ptr(q), len(q), H._ptr(t), len(t), H._ptr(got), C.byref(ng)) == 0
+        assert ng.value == ne and np.array_equal(got[:ne], exp[:ne]), ("block", it, len(q), len(t))
     assert n_h >= 8                                          # Hirschberg route exercised
