@@ -216,7 +216,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=1184)
+    ap.add_argument("--reads-per-step", type=int, default=2368)
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
