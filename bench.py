@@ -267,6 +267,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ref, sample = make_genomes(args.seed, args.ref_len)                          # replicated on every GPU
@@ -341,6 +342,9 @@ def main():
         wall_ms = (time.perf_counter() - t0) * 1e3
     launches = lib.lesvgpu_launch_count() - launches0
     dev_ms = sum(acc["dev"].values())
+    if world > 1:                                       # per-rank view for diagnosis (stderr; rank 0's JSON line is the result)
+        print(f"[bench rank {rank}] device ms/step " + ", ".join(f"{k} {v / args.steps:.1f}" for k, v in acc["dev"].items()) +
+              f"; wall {wall_ms / args.steps:.1f}; clocks {clk.summary()}", file=sys.stderr, flush=True)
 
     dev_ms_max, wall_ms_max, all_bases, all_cells, all_launches = shard.reduce_stats(
         dev_ms, wall_ms, float(acc["bases"]), float(acc["cells"]), float(launches), world, device="cuda")

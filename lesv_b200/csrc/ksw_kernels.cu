@@ -375,6 +375,9 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     __shared__ uint2 skew_ring[kSync == kSyncSkew ? kMaxWarps : 1][kSync == kSyncSkew ? 4 * kSkewK : 1];
     constexpr bool kBarrier = kSync != kSyncRing;       // slots need no tags / flow control
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Programmatic dependent launch: the launch classes of a batch are chained in one stream, each allowed to start
+    // as soon as every CTA of the class before it is resident (lesvgpu.cu: run_jobs).  Nothing is waited for.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
     // The queue is sorted by decreasing traceback size and cluster i starts with job i, so the arena
     // of cluster i only has to hold job i: everything it pulls later is smaller.
@@ -745,8 +748,13 @@ static KswKernelFn cluster_kernel()
 
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* arena_stride, uint32_t* d_cigar,
-                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
+                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s, bool after_resident)
 {
+    // after_resident: programmatic stream serialization -- this launch may start once all CTAs of the previous
+    // kernel in the stream have executed griddepcontrol.launch_dependents (i.e. are resident), not when it ends.
+    cudaLaunchAttribute pdl[2];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = after_resident ? 1 : 0;
     // Single-CTA alignments synchronise once per anti-diagonal with a CTA barrier (waiting warps
     // sleep); the tagged-slot ring is what clusters need (no barrier spans CTAs cheaply) and can be
     // forced for single CTAs with LESV_KSW_RING=1 -- measured slower there: polling lanes burn issue
@@ -756,8 +764,12 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 #define LESV_LAUNCH1(MODE)                                                                                         \
     do {                                                                                                           \
         cudaFuncSetAttribute(ksw_dp_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        ksw_dp_kernel<false, MODE><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,          \
-                                                                arena_stride, d_cigar, d_runs, d_out, d_counter);  \
+        cudaLaunchConfig_t c1 = {};                                                                                \
+        c1.gridDim = dim3((unsigned)n_clusters); c1.blockDim = dim3((unsigned)nt); c1.dynamicSmemBytes = smem;     \
+        c1.stream = s; c1.attrs = pdl; c1.numAttrs = 1;                                                            \
+        cudaError_t e1 = cudaLaunchKernelEx(&c1, ksw_dp_kernel<false, MODE>, d_jobs, d_order, njobs, d_pool, d_arena, \
+                                            arena_stride, d_cigar, d_runs, d_out, d_counter);                      \
+        if (e1 != cudaSuccess) return e1;                                                                          \
     } while (0)
         static const int skew_k = getenv("LESV_KSW_SKEW") ? atoi(getenv("LESV_KSW_SKEW")) : 8;
         if (sync_mode == kSyncSkew) {
@@ -794,10 +806,11 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     cfg.blockDim = dim3((unsigned)nt);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1] = pdl[0];
+    cfg.attrs = at; cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
 }

@@ -71,7 +71,7 @@ void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const ui
 // smem = ksw_smem_bytes(longest query, longest target among these jobs).
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_job_order,
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* d_arena_off, uint32_t* d_cigar,
-                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
+                       KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s, bool after_resident = false);
 int ksw_max_clusters(int nt, int ncta, size_t smem);
 
 // Fallback for bands no cluster shape can hold: slot contexts in global scratch (ksw_wide_scratch_words per CTA).

@@ -214,11 +214,21 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     std::sort(launches.begin(), launches.end(), [](const Launch& a, const Launch& b) {
         return a.ncta * a.nt != b.ncta * b.nt ? a.ncta * a.nt > b.ncta * b.nt : a.nt > b.nt;
     });
+    {   // ... except that the class with the most work goes last: it is launched machine-wide and absorbs the SMs
+        // the others release (the launches are chained, see below)
+        size_t mi = 0;
+        for (size_t i = 1; i < launches.size(); ++i) if (launches[i].work > launches[mi].work) mi = i;
+        std::rotate(launches.begin() + mi, launches.begin() + mi + 1, launches.end());
+    }
     std::vector<int> order;
     order.reserve(nj);
     size_t arena_need = 0, scratch_need = 0;
     // SM budget: every launch gets SMs in proportion to its share of the work (traceback bytes ~ cells)
     const double budget = ctx->n_sm * 1.0;
+    auto shape_weight = [](int ncta) { return ncta <= 1 ? 1.0 : ncta == 2 ? 1.4 : ncta == 4 ? 1.7 : 2.2; };
+    double weighted_work = 0;
+    const Launch* major = &launches[0];
+    for (const Launch& L : launches) { weighted_work += L.work * shape_weight(L.ncta); if (L.work > major->work) major = &L; }
     for (Launch& L : launches) {
         std::sort(L.ids.begin(), L.ids.end(), [&](int a, int b) {
             return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
@@ -235,18 +245,22 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (L.smem > 200 * 1024) { ctx->err = "sequence too long for the shared-memory staging buffers"; return LESVGPU_E_ARG; }
         const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
         const int per_sm = (L.ncta == 1 || L.nt <= 320) ? ksw_ctas_per_sm(L.nt) : 1;
-        // Every class is launched wide enough to fill the machine on its own (persistent CTAs pulling from the
-        // class queue): when one class runs dry its SMs go to the pending CTAs of the others, so no SM idles
-        // while another class still has alignments queued.  `fair` = the SMs its share of the work is worth;
-        // the arena fit below takes memory away from the surplus first.
-        const double share = budget * L.work / total_work;
+        // `fair` = the SMs the class needs to finish together with the others: its share of the work, weighted by
+        // what an SM achieves in that shape (measured: 2-CTA clusters run at ~0.7x the single-CTA rate per SM,
+        // full-band 8-CTA clusters at ~0.45x because an anti-diagonal of the whole matrix is a triangle).
+        // The class with the most work is additionally launched wide enough to fill the machine on its own
+        // (persistent CTAs pulling from the class queue), the others 25 % above fair: when a class runs dry its SMs
+        // go to the pending CTAs, so no SM idles while alignments are queued.  The arena fit below takes memory
+        // away from the surplus first, so under memory pressure this degrades to the weighted static split.
+        const double share = budget * L.work * shape_weight(L.ncta) / weighted_work;
         int cap = 1 << 20;
         if (L.ncta > 1) {
             cap = ksw_max_clusters(L.nt, L.ncta, L.smem);
             if (cap <= 0) { ctx->err = "cluster shape not launchable on this device"; return LESVGPU_E_CUDA; }
         }
-        L.fair = std::max(1, std::min(std::min((int)(share * per_sm / sms_per_job), L.count), cap));
-        int n = std::max(1, std::min(std::min(ctx->n_sm * per_sm / sms_per_job, L.count), cap));
+        const int whole = std::max(1, std::min(std::min(ctx->n_sm * per_sm / sms_per_job, L.count), cap));
+        L.fair = std::max(1, std::min((int)(share * per_sm / sms_per_job + 0.5), whole));
+        int n = &L == major ? whole : std::min(whole, (5 * L.fair + 3) / 4);
         L.n_clusters = n;
     }
     // fit the arenas.  Cluster i of a launch starts with job i of its (size-sorted) queue and only
@@ -270,19 +284,12 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         arena_need = 0;
         for (Launch& L : launches) { L.arena_off = arena_need; L.arena_bytes = footprint(L); arena_need += L.arena_bytes; }
         if (arena_need <= arena_limit) break;
-        // Take memory from the surplus first: the minor classes down to 1.5 x their fair share (cluster launches
-        // run at a lower rate per SM, a bare fair share would make them the long pole), then the class with
-        // the most work (it runs longest and absorbs the SMs the others release), then everybody's rest.
-        const Launch* major = &launches[0];
-        for (const Launch& L : launches) if (L.work > major->work) major = &L;
+        // Take memory from the surplus first (largest footprint first), then from below the fair share.
         Launch* big = nullptr;
         for (Launch& L : launches)
-            if (&L != major && L.n_clusters > (3 * L.fair + 1) / 2 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+            if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big)
             for (Launch& L : launches)
-                if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
-        if (!big)
-            for (Launch& L : launches)                   // ... then below the fair share
                 if (L.n_clusters > 1 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
         --big->n_clusters;
@@ -332,29 +339,39 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], s));
     // the launch classes run concurrently: one side stream each, joined back into the main stream
+    // All DP launches of the batch go into ONE side stream, largest shape first, each chained to its predecessor
+    // by programmatic stream serialization: a class starts as soon as every CTA of the class before it is resident.
+    // So the cluster classes get their SMs first, the class with the most work (launched last, machine-wide) takes
+    // what is left and inherits the SMs of the others as they run dry -- independent of how the hardware would
+    // order competing streams (two processes on one box were enough to turn that order around).
     static const bool dbg = getenv("LESV_KSW_DEBUG") != nullptr;
-    std::vector<cudaEvent_t> dbg_ev;
-    if (dbg) { dbg_ev.resize(2 * launches.size()); for (auto& e : dbg_ev) cudaEventCreate(&e); }
-    for (size_t li = 0; li < launches.size(); ++li) {
-        const Launch& L = launches[li];
-        cudaStream_t ls = ctx->side[li % kSideStreams];
+    {
+        cudaStream_t ls = ctx->side[0];
         CK(cudaStreamWaitEvent(ls, ctx->ev[2], 0));
-        if (dbg) cudaEventRecord(dbg_ev[2 * li], ls);
-        if (L.ncta > 0)
-            CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
-                          ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
-                          ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls));
-        else {
-            launch_ksw_wide(L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
-                            ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
-                            L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls);
-            CK(cudaGetLastError());
+        bool chained = false, wide_used = false;
+        for (size_t li = 0; li < launches.size(); ++li) {
+            const Launch& L = launches[li];
+            if (L.ncta > 0) {
+                CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
+                              ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
+                              ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls, chained));
+                chained = true;
+            } else {
+                cudaStream_t ws = ctx->side[1];
+                if (!wide_used) CK(cudaStreamWaitEvent(ws, ctx->ev[2], 0));
+                wide_used = true;
+                launch_ksw_wide(L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
+                                ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
+                                L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ws);
+                CK(cudaGetLastError());
+            }
         }
-    }
-    if (dbg) for (size_t li = 0; li < launches.size(); ++li) cudaEventRecord(dbg_ev[2 * li + 1], ctx->side[li % kSideStreams]);
-    for (size_t k = 0; k < std::min<size_t>(launches.size(), kSideStreams); ++k) {
-        CK(cudaEventRecord(ctx->side_done[k], ctx->side[k]));
-        CK(cudaStreamWaitEvent(s, ctx->side_done[k], 0));
+        CK(cudaEventRecord(ctx->side_done[0], ls));
+        CK(cudaStreamWaitEvent(s, ctx->side_done[0], 0));
+        if (wide_used) {
+            CK(cudaEventRecord(ctx->side_done[1], ctx->side[1]));
+            CK(cudaStreamWaitEvent(s, ctx->side_done[1], 0));
+        }
     }
     CK(cudaEventRecord(ctx->ev[3], s));
     size_t d2h = sizeof(KswOut) * nj;
@@ -372,20 +389,20 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
 
     if (dbg) {
         const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ksw debug] arena %.1f GB of limit %.1f GB\n", arena_need / 1e9, arena_limit / 1e9);
         fprintf(stderr, "[ksw debug] host: plan+alloc %.1f ms, launch+wait %.1f ms\n",
                 std::chrono::duration<double, std::milli>(t_planned - t_enter).count(),
                 std::chrono::duration<double, std::milli>(t_done - t_planned).count());
+        float total = 0;
+        cudaEventElapsedTime(&total, ctx->ev[2], ctx->ev[3]);
         for (size_t li = 0; li < launches.size(); ++li) {
             const Launch& L = launches[li];
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, ctx->ev[2], dbg_ev[2 * li]); cudaEventElapsedTime(&b, ctx->ev[2], dbg_ev[2 * li + 1]);
             double cells = 0;
-            for (int k : L.ids) { int ok = 0; cells += (double)lesvgpu_ksw_cells(jobs[k].qlen, jobs[k].tlen, jobs[k].w, &ok); }
-            fprintf(stderr, "[ksw debug] launch %zu: ncta=%d tier=%d jobs=%d ctas/clusters=%d cells=%.1fG start=%.1f end=%.1f ms -> %.0f GCUPS on %d SMs\n",
-                    li, L.ncta, L.nt, L.count, L.n_clusters, cells / 1e9, a, b, cells / 1e6 / std::max(0.001f, b - a),
-                    L.n_clusters * std::max(1, L.ncta) / (L.ncta == 1 ? ksw_ctas_per_sm(L.nt) : 1));
+            for (int k : L.ids) cells += (double)cells_fast(jobs[k].qlen, jobs[k].tlen, jobs[k].w);
+            fprintf(stderr, "[ksw debug] launch %zu: ncta=%d tier=%d jobs=%d ctas/clusters=%d (fair %d) cells=%.1fG\n",
+                    li, L.ncta, L.nt, L.count, L.n_clusters, L.fair, cells / 1e9);
         }
-        for (auto& e : dbg_ev) cudaEventDestroy(e);
+        fprintf(stderr, "[ksw debug] all launches: %.1f ms\n", total);
     }
     lesvgpu_timing& T = ctx->timing;
     cudaEventElapsedTime(&T.h2d_ms, ctx->ev[0], ctx->ev[1]);
