@@ -14,6 +14,7 @@
 #include "lesv_dbbuild.hpp"
 
 #include <string>
+#include <time.h>
 
 using namespace lesvdb;
 
@@ -191,9 +192,25 @@ void format_hsp(const Options& o, const lesvgpu_hsp& h, const uint8_t* ops, cons
 
 }  // namespace
 
+static double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+// the reference logs "'<title>' takes N secs." around its phases (hbn_aux.h:95-106); LESV_TIMING=1 prints the same here
+static void phase(const char* title, double& t0)
+{
+    static const bool on = getenv("LESV_TIMING") != nullptr;
+    const double t = now_s();
+    if (on) fprintf(stderr, "[lesv-b200] '%s' takes %.2f secs.\n", title, t - t0);
+    t0 = t;
+}
+
 int main(int argc, char** argv)
 {
     const Options o = parse(argc, argv);
+    double t0 = now_s();
     if (!exists(o.db_dir) && mkdir(o.db_dir.c_str(), S_IRWXU) != 0) die("Failed to create directory " + o.db_dir);
     if (!db_is_built(o.query, o.db_dir, "query", o.min_query_size, o.max_query_vol_seqs, o.max_query_vol_res)) {
         build_db(o.query, o.db_dir, "query", o.min_query_size, o.max_query_vol_seqs, o.max_query_vol_res);
@@ -203,6 +220,7 @@ int main(int argc, char** argv)
         build_db(o.subject, o.db_dir, "subject", o.min_subject_size, o.max_subject_vol_seqs, o.max_subject_vol_res);
         db_make_built(o.subject, o.db_dir, "subject", o.min_subject_size, o.max_subject_vol_seqs, o.max_subject_vol_res);
     }
+    phase("build databases", t0);
     const std::string bdir = o.db_dir + "/backup_results";
     if (!exists(bdir) && mkdir(bdir.c_str(), S_IRWXU) != 0) die("Failed to create directory " + bdir);
     FILE* out = o.output == "-" ? stdout : fopen(o.output.c_str(), "w");
@@ -211,6 +229,7 @@ int main(int argc, char** argv)
     const int dev = getenv("LESV_GPU") ? atoi(getenv("LESV_GPU")) : 0;
     lesvgpu_ctx* ctx = nullptr;
     if (lesvgpu_ctx_create(dev, 0, &ctx) != LESVGPU_OK) die("no usable sm_100 GPU (there is no CPU path)");
+    phase("create GPU context", t0);
     lesvgpu_map_opts mo;
     memset(&mo, 0, sizeof mo);
     mo.min_ddfs = o.min_ddfs; mo.hitlist_size = o.hitlist; mo.max_hsps = o.max_hsps;
@@ -232,6 +251,7 @@ int main(int argc, char** argv)
         if (lesvgpu_subject_load(ctx, sv.pac.data(), sv.pac.size()) != LESVGPU_OK ||
             lesvgpu_index_build(ctx, sseqs.data(), (int)sseqs.size(), o.kmer_size, o.kmer_window, o.max_kmer_occ) != LESVGPU_OK)
             die(std::string("index build failed: ") + lesvgpu_last_error(ctx));
+        phase("load subject volume + build index", t0);
         for (int qvid = o.node_id; qvid < nqv; qvid += o.num_nodes) {
             const std::string rpath = results_path(o, qvid, svid);
             if (exists(rpath + ".mapped")) { copy_to(rpath, out); continue; }
@@ -278,6 +298,7 @@ int main(int argc, char** argv)
                 }
                 fwrite(text.data(), 1, text.size(), out);
                 fwrite(text.data(), 1, text.size(), backup);
+                phase("map one query batch", t0);
             }
             fclose(backup);
             FILE* m = fopen((rpath + ".mapped").c_str(), "w");   // qi_vs_sj_make_mapped

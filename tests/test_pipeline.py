@@ -121,3 +121,20 @@ def test_four_tools_against_fresh_reference_run_with_volumes(tmp_path):
                                  os.path.join(work, "svsig"))
     assert n >= 140 and n_sig >= 10
     assert len([f for f in os.listdir(os.path.join(work, "db_gpu", "backup_results")) if f.endswith(".m4x")]) >= 4
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2map")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scenario", ["c1", "k19", "repeats"])
+def test_four_tools_on_named_configs(tmp_path, scenario):
+    """tools/parity_probe.py runs both tool chains and diffs every output file:
+    c1      = BASELINE.json configs[0] at full size (1 Mbp reference, 2,000 x 10 kb reads at 12 %, 20 planted INS/DEL);
+    k19     = the README's ultra-long setting -kmer_size 19 -kmer_window 20 on 30 kb reads at 10-25 % error
+              (the int-truncated hash path of hbn_word_finder.c:263);
+    repeats = tandem repeats and dispersed 6 kb duplicates (ties in the reference's unstable sorts, Appendix A #1-#4)."""
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "parity_probe.py"), scenario, str(tmp_path)],
+                         check=True, capture_output=True, text=True).stdout
+    assert "m4: reference" in out and ", identical True" in out, out
+    assert "svr:" in out and "svsig:" in out and out.count("all files identical: True") == 2, out
+    n_m4 = int(out.split("m4: reference ")[1].split(" ")[0])
+    assert n_m4 >= {"c1": 2000, "k19": 100, "repeats": 300}[scenario]
