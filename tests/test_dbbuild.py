@@ -64,3 +64,35 @@ def test_database_files_equal_reference(tmp_path):
     assert n == 14
     assert os.path.getsize(os.path.join(work, "db_ref", "query.volume_info.bin")) > 3 * 64      # several volumes
     assert os.path.getsize(os.path.join(work, "db_ref", "query.ambig")) > 0
+
+
+def test_qx2splitseq_equals_reference(tmp_path):
+    """Subread splitting (src/app/split_seq/main.c): same pieces, same names, byte-identical output; FASTA, gzip and
+    FASTQ input, with and without overlap / last-piece merging."""
+    rng = np.random.default_rng(8)
+    work = str(tmp_path)
+    subprocess.run(["make", "-s", "-C", os.path.join(H.ROOT, "lesv_b200", "csrc"), "../bin/qx2splitseq"], check=True)
+    ours = os.path.join(H.ROOT, "lesv_b200", "bin", "qx2splitseq")
+    ref = os.path.join(H.ROOT, "oracle", "_ref", "bin", "qx2splitseq")
+    lens = [500, 4999, 5000, 5001, 6999, 7000, 7001, 12000, 26000, 10, 15000]
+    seqs = ["".join("ACGT"[x] for x in rng.integers(0, 4, n)) for n in lens]
+    with open(os.path.join(work, "a.fa"), "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(f">read{i} comment {i}\n")
+            for k in range(0, len(s), 60):
+                f.write(s[k:k + 60] + "\n")
+    with gzip.open(os.path.join(work, "b.fa.gz"), "wt") as f:
+        for i, s in enumerate(seqs[:5]):
+            f.write(f">gz{i}\n{s}\n")
+    with open(os.path.join(work, "c.fq"), "w") as f:
+        for i, s in enumerate(seqs[5:9]):
+            f.write(f"@fq{i} x\n{s}\n+\n{'I' * len(s)}\n")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    n = 0
+    for inp in ("a.fa", "b.fa.gz", "c.fq"):
+        for args in (("5000", "0", "2000"), ("5000", "300", "0"), ("3000", "100", "2999")):
+            a = subprocess.run([ref, *args, inp], cwd=work, check=True, capture_output=True, env=env).stdout
+            b = subprocess.run([ours, *args, inp], cwd=work, check=True, capture_output=True).stdout
+            assert a == b, (inp, args)
+            n += a.count(b">")
+    assert n > 100
