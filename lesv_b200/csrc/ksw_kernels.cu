@@ -730,7 +730,7 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 }
 
 // 88 registers per thread (ptxas: 86) -> 744 threads per SM
-int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 11 ? 11 : n; }
+int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 23 ? 23 : n; }
 
 // Cluster alignments: polled tagged-slot ring (551 GCUPS on 2-CTA clusters); LESV_KSW_CLUSTER_SKEW=1
 // selects skewed CTAs with a cluster barrier every LESV_KSW_SKEW rows (measured 517-549 GCUPS).

@@ -163,7 +163,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     // alignment actually uses of it.
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
-        static const int tiers[] = {64, 96, 128, 160, 320, 512, 640};
+        static const int tiers[] = {32, 64, 96, 128, 160, 320, 512, 640};
         static const int split2 = getenv("LESV_KSW_SPLIT2") ? atoi(getenv("LESV_KSW_SPLIT2")) : 0;
         // experiment: alignments of 321..640 blocks as 2-CTA clusters of <= 320 threads, two CTAs (of different
         // alignments) per SM, so one CTA's row barrier overlaps the other's arithmetic

@@ -62,7 +62,8 @@ def cpu_gcups(pairs, w):
     return cells / sec / 1e9
 
 
-for L in (1000, 5000, 10000, 20000, 50000):
+LENS = tuple(int(x) for x in os.environ.get('SWEEP_LENS', '1000,5000,10000,20000,50000').split(','))
+for L in LENS:
     base = []
     for _ in range(64):
         t = rng.integers(0, 4, L, dtype=np.uint8)
