@@ -210,7 +210,28 @@ def cpu_baseline(ref, reads, cores):
 
 
 # ---------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, the reference tools) write there
+    too, so fd 1 is pointed at stderr for the whole run and the result line goes to the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -245,7 +266,7 @@ def main():
         for k in range(K):
             base = cpu_baseline(ref, make_reads(sample, n_sample, args.seed + 77 + k), cores)
             if base is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin is missing (make -C oracle ref needs /root/reference)"}))
+                _emit({"impl": "reference", "unavailable": "oracle/_ref/bin is missing (make -C oracle ref needs /root/reference)"})
                 return
             vals.append(base)
         v = sum(b["value"] for b in vals) / len(vals)
@@ -256,7 +277,7 @@ def main():
                 "dtype": "int8", "data": "synthetic", "config": dict(config, reads_per_step_per_gpu=n_sample),
                 "cpu_baseline": base,
                 "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ---- our arm ------------------------------------------------------------------------------------
@@ -396,7 +417,7 @@ def main():
             base = cpu_baseline(ref, reads[:n_sample], cores)
             if base is not None:
                 line["cpu_baseline"] = base
-        print(json.dumps(line))
+        _emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
