@@ -125,16 +125,19 @@ def test_four_tools_against_fresh_reference_run_with_volumes(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2map")), reason="oracle/_ref not built")
-@pytest.mark.parametrize("scenario", ["c1", "k19", "repeats"])
+@pytest.mark.parametrize("scenario", ["c1", "k19", "repeats", "c3"])
 def test_four_tools_on_named_configs(tmp_path, scenario):
     """tools/parity_probe.py runs both tool chains and diffs every output file:
     c1      = BASELINE.json configs[0] at full size (1 Mbp reference, 2,000 x 10 kb reads at 12 %, 20 planted INS/DEL);
     k19     = the README's ultra-long setting -kmer_size 19 -kmer_window 20 on 30 kb reads at 10-25 % error
               (the int-truncated hash path of hbn_word_finder.c:263);
-    repeats = tandem repeats and dispersed 6 kb duplicates (ties in the reference's unstable sorts, Appendix A #1-#4)."""
+    repeats = tandem repeats and dispersed 6 kb duplicates (ties in the reference's unstable sorts, Appendix A #1-#4);
+    c3      = BASELINE.json configs[2] shape at 1/10 scale: 24 contigs with hg19's length profile (310 Mbp), 50 kb reads
+              with 40 bp-3 kb INS/DEL (the full 3.1 Gbp run is recorded in profiles/r1_c3_full_scale.txt)."""
+    env = dict(os.environ, C3_SCALE="0.1", C3_READS="48", REF_MAP_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "parity_probe.py"), scenario, str(tmp_path)],
-                         check=True, capture_output=True, text=True).stdout
+                         check=True, capture_output=True, text=True, env=env).stdout
     assert "m4: reference" in out and ", identical True" in out, out
     assert "svr:" in out and "svsig:" in out and out.count("all files identical: True") == 2, out
     n_m4 = int(out.split("m4: reference ")[1].split(" ")[0])
-    assert n_m4 >= {"c1": 2000, "k19": 100, "repeats": 300}[scenario]
+    assert n_m4 >= {"c1": 2000, "k19": 100, "repeats": 300, "c3": 40}[scenario]

@@ -30,6 +30,28 @@ elif scen == "repeats":                # tandem repeats + dispersed duplicates: 
     reads = synth.simulate_reads(ref, 300, 9000, np.random.default_rng(5), 0.10, 0.15)
     synth.write_fasta(os.path.join(work, "ref.fa"), ["chrR"], [ref], width=80)
     synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
+elif scen == "c3":                     # BASELINE.json configs[2] shape: 24 contigs, 3.1 Gbp, 50 kb reads (a sample of them)
+    hg19 = [249, 243, 198, 191, 181, 171, 159, 146, 141, 136, 135, 134, 115, 107, 103, 90, 81, 78, 59, 63, 48, 51, 155, 59]
+    scale = float(os.environ.get("C3_SCALE", "1.0"))
+    names, contigs = [], []
+    for i, mb in enumerate(hg19):
+        names.append(f"chr{i + 1}")
+        contigs.append(synth.random_codes(int(mb * 1_000_000 * scale), rng))
+    synth.write_fasta(os.path.join(work, "ref.fa"), names, contigs, width=0)
+    reads = []
+    r2 = np.random.default_rng(9)
+    for i in range(int(os.environ.get("C3_READS", "64"))):
+        c = contigs[int(r2.integers(0, len(contigs)))]
+        p0 = int(r2.integers(0, len(c) - 50000))
+        seg = c[p0:p0 + 50000]
+        if i % 4 == 0:                 # a 40 bp - 3 kb deletion or insertion inside
+            size = int(np.exp(r2.uniform(np.log(40), np.log(3000))))
+            k = int(r2.integers(5000, 40000))
+            seg = np.concatenate([seg[:k], seg[k + size:]]) if i % 8 == 0 else np.concatenate([seg[:k], synth.random_codes(size, r2), seg[k:]])
+        rd = synth.mutate(seg, float(r2.uniform(0.10, 0.15)), r2)
+        reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
+    del contigs
+    synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
 else:
     raise SystemExit("unknown scenario")
 env = dict(os.environ, OMP_NUM_THREADS="1")
@@ -45,13 +67,17 @@ def run(cmd, out=None, tag=""):
 
 print("reference:")
 with open(os.path.join(work, "ref.m4"), "wb") as f:
-    run([os.path.join(REF, "qx2map")] + map_args + ["-db_dir", "db", "-keep_db", "-num_threads", "1", "reads.fa", "ref.fa"], f, "qx2map (1 thread)")
+    run([os.path.join(REF, "qx2map")] + map_args + ["-db_dir", "db", "-keep_db", "-num_threads", os.environ.get("REF_MAP_THREADS", "1"),
+         "reads.fa", "ref.fa"], f, "qx2map")
 run([os.path.join(REF, "qx2m4x"), "db"])
 run([os.path.join(REF, "qx2svr"), "svr", "db", "3000", "70.0", "300", t])
 run([os.path.join(REF, "qx2svsig"), "svsig", "svr", "db", "40", t])
 print("ours:")
+env["LESV_TIMING"] = "1"
 with open(os.path.join(work, "gpu.m4"), "wb") as f:
     run([os.path.join(OURS, "qx2map")] + map_args + ["-db_dir", "db_gpu", "-keep_db", "reads.fa", "ref.fa"], f)
+for l in open(os.path.join(work, "log.txt"), errors="replace"):
+    if "[lesv-b200] '" in l: print("     " + l.strip())
 run([os.path.join(OURS, "qx2m4x"), "db_gpu"])
 run([os.path.join(OURS, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", t])
 run([os.path.join(OURS, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", t])
