@@ -172,10 +172,15 @@ __device__ __forceinline__ void scan_column(ScanState& z, uint32_t op, bool iden
 }
 
 // All 32 lanes run the same walk out of the shared-memory row cache; lane 0 writes results.
+// kOverlap (ksw_dp_overlap_kernel): the traceback may be stored top-down from the end of the arena (reversed), the next
+// alignment's DP is writing into the same arena while this walk runs, so rows are read with L2-only loads and the
+// row the walk still needs is published in *progress before every refill (-1 once nothing is needed any more).
+template <bool kOverlap = false>
 __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ arena, size_t prow,
                                const uint32_t* tp_s, const uint32_t* qrp_s,
                                uint32_t* __restrict__ cigar, KswGapRun* __restrict__ runs, KswOut* out,
-                               BtShared& sh, int lane)
+                               BtShared& sh, int lane, size_t arena_size = 0, bool reversed = false,
+                               volatile int* progress = nullptr)
 {
     const int qlen = job.qlen, tlen = job.tlen, w = job.w, min_indel = job.min_indel;
     const bool wr_cigar = job.cigar_cap != 0 && lane == 0, wr_runs = lane == 0;
@@ -185,6 +190,7 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
     memset(&z, 0, sizeof z);
     while (i >= 0 && j >= 0) {
         const int r0 = i + j;
+        if (kOverlap && lane == 0) *progress = r0;
         // ---- refill: rows r0 .. r0-63, two 16-byte blocks around the predicted column -------
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -199,9 +205,14 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
                 b0 = ic >> 4;
                 b1 = b0 + ((ic & 15) >= 8 ? 1 : -1);
                 if (b1 < bst || b1 > ben) b1 = -1;
-                const uint8_t* row = arena + (size_t)r * prow;
-                sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16);
-                if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16);
+                const uint8_t* row = arena + ((kOverlap && reversed) ? arena_size - (size_t)(r + 1) * prow : (size_t)r * prow);
+                if (kOverlap) {
+                    sh.cache[k][0] = __ldcg(reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16));
+                    if (b1 >= 0) sh.cache[k][1] = __ldcg(reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16));
+                } else {
+                    sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16);
+                    if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16);
+                }
             }
             sh.blk[k][0] = b0; sh.blk[k][1] = b1;
         }
@@ -239,6 +250,7 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
         }
         __syncwarp();
     }
+    if (kOverlap && lane == 0) *progress = -1;
     // leading gap (ksw2.h:146-147); it lies left of any 8-column window, so the scan ignores it
     if (i >= 0) { bt_emit(2, (uint32_t)(i + 1), cur_op, cur_len, cigar, n, wr_cigar); aln += i + 1; }
     if (j >= 0) { bt_emit(1, (uint32_t)(j + 1), cur_op, cur_len, cigar, n, wr_cigar); aln += j + 1; }
@@ -612,6 +624,138 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-CTA alignments, DP and traceback walk overlapped
+// ---------------------------------------------------------------------------------------------
+// The walk of an alignment (one warp, ~7 % of its DP time, the other warps idle) does not have to finish before the
+// CTA starts the next alignment: an extra warp walks alignment m-1 while the DP warps fill the traceback of
+// alignment m.  No second arena is needed: consecutive alignments store their rows in opposite directions
+// (even ones bottom-up from offset 0, odd ones top-down from the end of the arena), so the walk -- which runs from the
+// last row to the first, an order of magnitude faster than the DP -- always moves ahead of the write front that
+// follows it.  The DP warps check every 256 rows that this is really so (the walker publishes the row it still
+// needs) and the packed sequences are double-buffered in shared memory.  The DP warps synchronise on named
+// barrier 1, the walker takes part in nothing.
+__device__ __forceinline__ void bar_dp(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(kMaxNT + 32)
+ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
+                      const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
+                      const size_t* __restrict__ arena_off /* n_ctas + 1 entries */, uint32_t half_words,
+                      uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
+                      KswOut* __restrict__ outs, int* counter)
+{
+    extern __shared__ uint32_t seq_s[];                 // two halves of half_words words
+    __shared__ BtShared bt;
+    __shared__ uint2 carry_sh[2][kMaxWarps];
+    __shared__ int sh_job;
+    __shared__ int wk_jid[2];
+    __shared__ volatile int wk_posted, wk_done, wk_finished, wk_row;
+    __shared__ volatile unsigned long long sh_prow, sh_prev_prow, sh_asize;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ndp = (int)blockDim.x - 32;               // DP threads; the last warp walks
+    const int cta = (int)blockIdx.x;
+    uint8_t* const arena = arena_base + arena_off[cta];
+    const size_t asize = arena_off[cta + 1] - arena_off[cta];
+    if (tid == 0) { wk_posted = 0; wk_done = 0; wk_finished = 0; wk_row = -1; sh_prev_prow = 0; }
+    __syncthreads();
+    if (tid >= ndp) {
+        // ---- walker ---------------------------------------------------------------------------------------
+        for (int n = 0;; ++n) {
+            int fin = 0;
+            if (lane == 0) {
+                while (wk_posted <= n && !wk_finished) __nanosleep(200);
+                fin = wk_posted <= n;
+            }
+            fin = __shfl_sync(0xFFFFFFFFu, fin, 0);
+            if (fin) break;
+            __threadfence_block();
+            const int jid = wk_jid[n & 1];
+            const KswJob job = jobs[jid];
+            const uint32_t* tp_s = seq_s + (size_t)(n & 1) * half_words;
+            const uint32_t* qrp_s = tp_s + tp_words(job.tlen);
+            backtrack_warp<true>(job, arena, (size_t)job.tb_blocks * 16, tp_s, qrp_s, cigar_pool + job.cigar_off,
+                                 run_pool + job.sig_off, outs + jid, bt, lane, asize, (n & 1) != 0, &wk_row);
+            __syncwarp();
+            if (lane == 0) { __threadfence(); wk_done = n + 1; }
+        }
+        return;
+    }
+    // ---- DP warps ---------------------------------------------------------------------------------------------
+    bool first = true;
+    for (int m = 0;; ++m) {
+        if (tid == 0) sh_job = first ? cta : atomicAdd(counter, 1);
+        bar_dp(ndp);
+        first = false;
+        const int ji = sh_job;
+        if (ji >= njobs) break;
+        if (tid == 0) while (wk_done < m - 1) __nanosleep(500);   // walk m-2 is over: its sequence buffer and rows are free
+        bar_dp(ndp);
+        const int jid = order[ji];
+        const KswJob job = jobs[jid];
+        const int qlen = job.qlen, tlen = job.tlen, w = job.w, tb_blocks = job.tb_blocks;
+        const int ntw = (int)tp_words(tlen), nqw = (int)qrp_words(qlen);
+        uint32_t* tp_s = seq_s + (size_t)(m & 1) * half_words;
+        uint32_t* qrp_s = tp_s + ntw;
+        for (int x = tid; x < ntw; x += ndp) tp_s[x] = pool[job.tp_off + x];
+        for (int x = tid; x < nqw; x += ndp) qrp_s[x] = pool[job.qrp_off + x];
+        bar_dp(ndp);
+        const int NT = job.nt, NW = NT >> 5;
+        const bool reversed = (m & 1) != 0;
+        const size_t prow = (size_t)tb_blocks * 16;
+        ThreadCtx c;
+        thread_ctx_reset(c, tid);
+        Carry prev_out = carry_init();
+        const int wnext = warp + 1 < NW ? warp + 1 : 0;
+        const int nrow_all = qlen + tlen - 1;
+        if (tid == 0) { sh_prow = (unsigned long long)prow; sh_asize = (unsigned long long)asize; }
+        // row r lives at rowp; consecutive rows are prow apart, upwards or downwards
+        uint8_t* rowp = arena + (reversed ? asize - prow : (size_t)0);
+        const long long rstep = reversed ? -(long long)prow : (long long)prow;
+        for (int r = 0; r < nrow_all; ++r, rowp += rstep) {
+            if ((r & 255) == 0 && m > 0) {
+                // rows r .. r+255 of this alignment must not touch what walk m-1 still needs (rows <= wk_row of it)
+                if (tid == 0) {
+                    const unsigned long long mine = (unsigned long long)(r + 256 < nrow_all ? r + 256 : nrow_all) * sh_prow;
+                    for (;;) {
+                        const int need = wk_done >= m ? -1 : wk_row;
+                        if (need < 0 && wk_done >= m) break;
+                        if (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize) break;
+                        __nanosleep(500);
+                    }
+                }
+                bar_dp(ndp);
+            }
+            if (warp < NW) {
+                const uint2 nb = carry_sh[(r + 1) & 1][warp];
+                Carry cin;
+                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                Carry cout;
+                uint32_t tb[4];
+                if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                          [&]() -> Carry { return cin; }, cout, tb)) {
+                    *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                    prev_out = cout;
+                }
+                if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
+            }
+            bar_dp(ndp);
+        }
+        __threadfence();                                 // the traceback is read by the walker through L2
+        bar_dp(ndp);
+        if (tid == 0) {
+            wk_jid[m & 1] = jid;
+            wk_row = nrow_all - 1;                       // until the walker publishes its own position
+            __threadfence_block();
+            wk_posted = m + 1;
+        }
+        if (tid == 0) sh_prev_prow = (unsigned long long)prow;
+    }
+    if (tid == 0) { __threadfence_block(); wk_finished = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wide bands (window > 512 blocks: full-band retries, chained dual HSPs)
 // ---------------------------------------------------------------------------------------------
 // Same per-block code, but a thread steps through several band slots per anti-diagonal and the
@@ -793,6 +937,16 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
             cudaFuncSetAttribute(ksw_dp_kernel<false, kSyncBar, 8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             ksw_dp_kernel<false, kSyncBar, 8, 512><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,
                                                                                   arena_stride, d_cigar, d_runs, d_out, d_counter);
+        }
+        else if (nt >= 320 && 2 * smem <= 200 * 1024 && !getenv("LESV_KSW_NO_OVERLAP")) {
+            // DP of alignment m overlapped with the traceback walk of alignment m-1 (one extra warp)
+            cudaFuncSetAttribute(ksw_dp_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+            cudaLaunchConfig_t c1 = {};
+            c1.gridDim = dim3((unsigned)n_clusters); c1.blockDim = dim3((unsigned)nt + 32); c1.dynamicSmemBytes = 2 * smem;
+            c1.stream = s; c1.attrs = pdl; c1.numAttrs = 1;
+            cudaError_t e1 = cudaLaunchKernelEx(&c1, ksw_dp_overlap_kernel, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                                (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
+            if (e1 != cudaSuccess) return e1;
         }
         else LESV_LAUNCH1(kSyncBar);
 #undef LESV_LAUNCH1

@@ -305,6 +305,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             arena_offs.push_back(b);
             b += L.ncta == 0 ? L.stride : ((tb_bytes[L.ids[i]] + 255) & ~(size_t)255);
         }
+        arena_offs.push_back(b);                         // end of the last arena (ksw_dp_overlap_kernel needs the sizes)
         counters[li] = L.ncta == 0 ? 0 : L.n_clusters;       // clusters start with jobs 0..n-1
     }
     for (const Launch& L : launches)
