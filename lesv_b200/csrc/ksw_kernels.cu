@@ -681,6 +681,11 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         return;
     }
     // ---- DP warps ---------------------------------------------------------------------------------------------
+    // The walker is the block's last warp and lands on the warp scheduler of warp 0; a CTA rarely needs all of its DP
+    // warps (NW <= ndp / 32), so the logical warps are rotated by one: physical warp 0 becomes the LAST logical warp,
+    // the one most likely to sit an alignment out, and the walker shares its scheduler with one idle warp.
+    const int nwdp = ndp >> 5;
+    const int lwarp = (warp + nwdp - 1) % nwdp, ltid = lwarp * 32 + lane;
     bool first = true;
     for (int m = 0;; ++m) {
         if (tid == 0) sh_job = first ? cta : atomicAdd(counter, 1);
@@ -703,9 +708,9 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         const bool reversed = (m & 1) != 0;
         const size_t prow = (size_t)tb_blocks * 16;
         ThreadCtx c;
-        thread_ctx_reset(c, tid);
+        thread_ctx_reset(c, ltid);
         Carry prev_out = carry_init();
-        const int wnext = warp + 1 < NW ? warp + 1 : 0;
+        const int wnext = lwarp + 1 < NW ? lwarp + 1 : 0;
         const int nrow_all = qlen + tlen - 1;
         if (tid == 0) { sh_prow = (unsigned long long)prow; sh_asize = (unsigned long long)asize; }
         // row r lives at rowp; consecutive rows are prow apart, upwards or downwards
@@ -725,8 +730,8 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                 }
                 bar_dp(ndp);
             }
-            if (warp < NW) {
-                const uint2 nb = carry_sh[(r + 1) & 1][warp];
+            if (lwarp < NW) {
+                const uint2 nb = carry_sh[(r + 1) & 1][lwarp];
                 Carry cin;
                 cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
                 cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
