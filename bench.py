@@ -397,7 +397,7 @@ def main():
             "call_wall_ms_per_step": {k: v / K for k, v in acc["wall"].items()},
             "stage_throughput": {"map_bases_per_s": acc["bases"] / ((acc["dev"]["map_seed_chain"] + acc["dev"]["map_extend"]) / 1e3),
                                  "svr_svsig_gcups": acc["cells"] / (acc["dp_ms"] / 1e3) / 1e9},
-            "roofline": {"bound": "int-issue", "kernel": "ksw_dp_kernel", "achieved": kern_gcups, "peak": int_peak,
+            "roofline": {"bound": "int-issue", "kernel": "ksw_dp_overlap_kernel (single-CTA classes; ksw_dp_kernel for cluster classes)", "achieved": kern_gcups, "peak": int_peak,
                          "unit": "GCUPS", "frac": kern_gcups / int_peak,
                          "peak_def": f"{n_sm} SMs x 128 lanes x {f_mhz:.0f} MHz (median under load) / {OPS_PER_CELL} ops per cell x "
                                      f"{LANES_PACKED} cells per 32-bit op (SURVEY.md 8d)",

@@ -123,3 +123,35 @@ def test_chain_core_equals_reference(is_mem):
         assert a == b, (it, len(q), a[:2], b[:2])
         n_hits += len(a)
     assert n_hits > 300
+
+
+def test_warp_schedule_of_the_chaining_dp_equals_the_sequential_loop():
+    """chain_warp.cuh scores 32 predecessors at once and replays the order-dependent part (strict '>', t[] marks, skip
+    counter, early stop).  Its lane-by-lane host emulation (tests/emul/chain_emul.cpp) must give the f / p / v arrays
+    of the sequential loop on random, collinear, tie-heavy and repeat-like seed lists."""
+    import os
+    lib = C.CDLL(os.path.join(H.ROOT, "tests", "emul", "libchain_emul.so"))
+    lib.lesv_emul_chain_warp_diff.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(77)
+    total = 0
+    for it in range(400):
+        mode = it % 5
+        n = int(rng.integers(1, 700))
+        if mode == 0:                                   # noisy collinear chain (the normal case)
+            q = np.cumsum(rng.integers(1, 60, n)); s = q + rng.integers(-30, 30, n) + int(rng.integers(0, 5000))
+        elif mode == 1:                                 # several parallel diagonals: many near-ties
+            q = np.sort(rng.integers(0, 4000, n)); s = q + rng.choice([0, 7, 300, 1400, 1600], n)
+        elif mode == 2:                                 # lattice: exact ties everywhere, long marked runs (skip counter)
+            q = (np.arange(n) // 8) * 10; s = q + (np.arange(n) % 8) * 10
+        elif mode == 3:                                 # random cloud
+            q = rng.integers(0, 20000, n); s = rng.integers(0, 20000, n)
+        else:                                           # dense tandem-like: period 37
+            q = np.arange(n) * 3; s = (np.arange(n) * 3) % 37 + (np.arange(n) // 40) * 37
+        order = np.lexsort((q, s))                      # the kernels feed seeds sorted by (s, q)
+        q, s = q[order].astype(np.int32), s[order].astype(np.int32)
+        ln = np.full(n, 10 if it % 2 else 15, dtype=np.int32)
+        for is_mem in (0, 1):
+            bad = lib.lesv_emul_chain_warp_diff(n, H._ptr(q), H._ptr(s), H._ptr(ln), is_mem, 1 if is_mem else 3, 30)
+            assert bad == 0, (it, mode, n, is_mem, bad)
+            total += n
+    assert total > 100000
