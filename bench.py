@@ -404,9 +404,9 @@ def main():
                          "avg_launch_ms": acc["sig_dp_ms"] / max(1, acc["sig_launches"]), "launches": int(acc["sig_launches"]),
                          "launch_note": "the launch classes of one batch run concurrently on side streams; achieved = cells of the "
                                         "qx2svsig batch / CUDA-event time around all of its ksw_dp_kernel launches",
-                         # profiles/r1_ncu_summary.md: 101.7 GB of DRAM traffic for 98.88 G cells in one ncu --set full capture
-                         "traffic": 1.028 * acc["sig_cells"] / max(1, acc["sig_launches"]) / 1e9, "traffic_unit": "GB per launch",
-                         "traffic_note": "dram__bytes_read+write per cell from the ncu capture (1.028 B/cell) x cells per launch; algorithmic = 1 B/cell",
+                         # profiles/r1_ncu_summary.md: 406.8 GB of DRAM traffic for 395.5 G cells in one ncu --set full capture
+                         "traffic": 1.029 * acc["sig_cells"] / max(1, acc["sig_launches"]) / 1e9, "traffic_unit": "GB per launch",
+                         "traffic_note": "dram__bytes_read+write per cell from the ncu capture (1.029 B/cell) x cells per launch; algorithmic = 1 B/cell",
                          "hbm": {"achieved": kern_gcups, "peak": hbm_peak, "unit": "GB/s", "frac": kern_gcups / hbm_peak,
                                  "note": "1 traceback byte per DP cell, written once (of measured copy bandwidth)"}},
             "index_build_ms": index_ms,
