@@ -80,6 +80,9 @@ struct lesvgpu_ctx {
     DevBuf<lesvksw::KswGapRun> d_runs;
     DevBuf<int> d_order, d_counter;
     DevBuf<size_t> d_aoff;
+    DevBuf<lesvksw::KswStripJob> d_sjobs;          // column strips of full-matrix alignments
+    DevBuf<uint2> d_edges;
+    DevBuf<int> d_sprog;
     PinBuf<uint8_t> h_raw;
     PinBuf<uint32_t> h_cigar;
     PinBuf<lesvksw::KswOut> h_outs;

@@ -693,7 +693,13 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         first = false;
         const int ji = sh_job;
         if (ji >= njobs) break;
-        if (tid == 0) while (wk_done < m - 1) __nanosleep(500);   // walk m-2 is over: its sequence buffer and rows are free
+        if (warp == 0)                                  // walk m-2 is over: its sequence buffer and rows are free
+            for (;;) {                                  // (whole-warp poll: no divergence in front of the aligned barrier)
+                int ok = lane == 0 ? (wk_done >= m - 1) : 0;
+                ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+                if (ok) break;
+                __nanosleep(500);
+            }
         bar_dp(ndp);
         const int jid = order[ji];
         const KswJob job = jobs[jid];
@@ -719,12 +725,17 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         for (int r = 0; r < nrow_all; ++r, rowp += rstep) {
             if ((r & 255) == 0 && m > 0) {
                 // rows r .. r+255 of this alignment must not touch what walk m-1 still needs (rows <= wk_row of it)
-                if (tid == 0) {
+                if (warp == 0) {
                     const unsigned long long mine = (unsigned long long)(r + 256 < nrow_all ? r + 256 : nrow_all) * sh_prow;
                     for (;;) {
-                        const int need = wk_done >= m ? -1 : wk_row;
-                        if (need < 0 && wk_done >= m) break;
-                        if (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize) break;
+                        int ok = 0;
+                        if (lane == 0) {
+                            const int need = wk_done >= m ? -1 : wk_row;
+                            ok = (need < 0 && wk_done >= m) ||
+                                 (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize);
+                        }
+                        ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+                        if (ok) break;
                         __nanosleep(500);
                     }
                 }
@@ -758,6 +769,138 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         if (tid == 0) sh_prev_prow = (unsigned long long)prow;
     }
     if (tid == 0) { __threadfence_block(); wk_finished = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full-matrix alignments as column strips
+// ---------------------------------------------------------------------------------------------
+// An anti-diagonal of the WHOLE matrix (qx2svr's dual-HSP chaining runs without a band) grows from one cell to
+// min(qlen, tlen) cells and shrinks again, so a cluster sized for the widest row idles half of the time.  Here the
+// columns are cut into strips of kStripNT blocks; a strip is an ordinary single-CTA job whose threads keep their block
+// for the whole pass.  Strip s takes the column-15 values of strip s-1 from a per-row edge buffer in global memory
+// (written once per row by the last thread of strip s-1, prefetched one row ahead by the first thread of strip s) and
+// may work on row r once strip s-1 has finished row r-1: progress counters, published and checked every 64 rows
+// (polled by a whole warp: a single lane spinning in front of __syncthreads() lets the rest of its warp run through
+// the aligned barrier -- undefined behaviour that showed up as a slightly different alignment).
+// Strips are handed out in (strip, alignment) order, so the predecessor of a strip is always running or done -- no
+// CTA ever waits for work that has not been started.  A CTA that finishes a strip goes on to the next one of any
+// alignment; whoever finishes the last strip of an alignment walks its traceback.
+constexpr int kStripNT = 640;
+struct StripJob {
+    int jid;                 // alignment (index into jobs)
+    int s, n_strips;
+    int prog_off;            // progress[prog_off + s], done counter at progress[prog_off + n_strips]
+    unsigned long long arena_off;   // this alignment's traceback
+    unsigned long long edge_off;    // edges[edge_off + s * nrow + r]: column-15 values of strip s in row r
+};
+
+__global__ void __launch_bounds__(kStripNT)
+ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict__ sjobs, int n_sjobs,
+                    const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, uint2* __restrict__ edges,
+                    int* __restrict__ progress, uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
+                    KswOut* __restrict__ outs, int* counter)
+{
+    extern __shared__ uint32_t seq_s[];
+    __shared__ BtShared bt;
+    __shared__ uint2 carry_sh[2][kMaxWarps];
+    __shared__ int sh_job, sh_last;
+    __shared__ int bt_dummy;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kStripNT / 32;
+    bool first = true;
+    for (;;) {
+        if (tid == 0) sh_job = first ? (int)blockIdx.x : atomicAdd(counter, 1);
+        __syncthreads();
+        first = false;
+        const int si = sh_job;
+        if (si >= n_sjobs) break;
+        const StripJob sj = sjobs[si];
+        const KswJob job = jobs[sj.jid];
+        const int qlen = job.qlen, tlen = job.tlen, w = job.w, tb_blocks = job.tb_blocks;
+        const int ntw = (int)tp_words(tlen), nqw = (int)qrp_words(qlen);
+        uint32_t* tp_s = seq_s;
+        uint32_t* qrp_s = seq_s + ntw;
+        for (int x = tid; x < ntw; x += kStripNT) tp_s[x] = pool[job.tp_off + x];
+        for (int x = tid; x < nqw; x += kStripNT) qrp_s[x] = pool[job.qrp_off + x];
+        __syncthreads();
+        const int nrow_all = qlen + tlen - 1;
+        const int B0 = sj.s * kStripNT;
+        // rows in which some block of the strip can be live (a superset is fine: dead rows fall through)
+        const int c0 = 16 * B0 - 16, c1e = 16 * (B0 + kStripNT - 1) + 15;
+        int r_lo = c0 > 2 * c0 - w ? c0 : 2 * c0 - w;
+        r_lo = r_lo < 0 ? 0 : r_lo;
+        long long hi = (long long)c1e + qlen - 1, hi2 = 2ll * c1e + w;
+        hi = hi < hi2 ? hi : hi2;
+        const int r_hi = hi < nrow_all - 1 ? (int)hi : nrow_all - 1;
+        uint8_t* const arena = arena_base + sj.arena_off;
+        const size_t prow = (size_t)tb_blocks * 16;
+        const uint2* edge_in = edges + sj.edge_off + (size_t)(sj.s - 1) * nrow_all;      // strip s-1 (s > 0)
+        uint2* edge_out = edges + sj.edge_off + (size_t)sj.s * nrow_all;
+        int* prog = progress + sj.prog_off;
+        ThreadCtx c;
+        thread_ctx_reset(c, B0 + tid);
+        Carry prev_out = carry_init();
+        uint2 edge_next = make_uint2(0u, 0u);          // value for the NEXT row, loaded one row ahead (thread 0)
+        for (int r = r_lo; r <= r_hi; ++r) {
+            if (((r - r_lo) & 63) == 0) {
+                if (sj.s > 0 && warp == 0) {            // rows r .. r+63 read rows r-1 .. r+62 of the strip to the left
+                    int need = r + 63;                  // (the whole warp polls: no divergence in front of the barrier)
+                    if (need > nrow_all) need = nrow_all;
+                    for (;;) {
+                        int v = lane == 0 ? atomicAdd(prog + sj.s - 1, 0) : 0;
+                        v = __shfl_sync(0xFFFFFFFFu, v, 0);
+                        if (v >= need) break;
+                        __nanosleep(200);
+                    }
+                    __threadfence();
+                    if (r > 0) {
+                        const uint2 e = __ldcv(edge_in + (r - 1));
+                        if (tid == 0) edge_next = e;
+                    }
+                }
+                if (r > r_lo) {                         // publish: rows < r of this strip are complete
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) atomicExch(prog + sj.s, r);
+                } else __syncthreads();
+            }
+            const uint2 edge_now = edge_next;
+            if (sj.s > 0 && tid == 0 && r + 1 <= r_hi) edge_next = __ldcv(edge_in + r);   // for row r+1
+            const uint2 nb = carry_sh[(r + 1) & 1][warp];
+            Carry cin;
+            cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+            cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+            if (lane == 0) {
+                if (warp == 0) { cin.xv = edge_now.x; cin.x2 = edge_now.y; }
+                else { cin.xv = nb.x; cin.x2 = nb.y; }
+            }
+            Carry cout;
+            uint32_t tb[4];
+            if (thread_row_step<true>(c, 1 << 24, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                      [&]() -> Carry { return cin; }, cout, tb)) {
+                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                prev_out = cout;
+                if (tid == kStripNT - 1) edge_out[r] = make_uint2(cout.xv, cout.x2);
+            }
+            if (lane == 31 && warp + 1 < NW) carry_sh[r & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
+            __syncthreads();
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicExch(prog + sj.s, 0x7fffffff);
+            __threadfence();
+            sh_last = atomicAdd(prog + sj.n_strips, 1) == sj.n_strips - 1;
+        }
+        __syncthreads();
+        if (sh_last) {                                  // every strip of this alignment is done: walk it
+            __threadfence();
+            if (warp == 0)
+                backtrack_warp<true>(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off, run_pool + job.sig_off,
+                                     outs + sj.jid, bt, lane, 0, false, (volatile int*)&bt_dummy);
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -972,6 +1115,16 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     cfg.attrs = at; cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
+}
+
+cudaError_t launch_ksw_strips(int n_ctas, size_t smem, const KswJob* d_jobs, const void* d_sjobs, int n_sjobs,
+                              const uint32_t* d_pool, uint8_t* d_arena, uint2* d_edges, int* d_progress,
+                              uint32_t* d_cigar, KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
+{
+    cudaFuncSetAttribute(ksw_dp_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ksw_dp_strip_kernel<<<n_ctas, kStripNT, smem, s>>>(d_jobs, static_cast<const StripJob*>(d_sjobs), n_sjobs, d_pool, d_arena,
+                                                       d_edges, d_progress, d_cigar, d_runs, d_out, d_counter);
+    return cudaGetLastError();
 }
 
 // how many clusters of this shape can be co-resident on the device (0 = shape not launchable)

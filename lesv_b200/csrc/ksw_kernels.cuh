@@ -74,6 +74,16 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
                        KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s, bool after_resident = false);
 int ksw_max_clusters(int nt, int ncta, size_t smem);
 
+// Full-matrix alignments cut into column strips of kStripBlocks blocks (ksw_kernels.cu: ksw_dp_strip_kernel).
+constexpr int kStripBlocks = 640;
+struct KswStripJob {
+    int jid, s, n_strips, prog_off;
+    unsigned long long arena_off, edge_off;
+};
+cudaError_t launch_ksw_strips(int n_ctas, size_t smem, const KswJob* d_jobs, const void* d_sjobs, int n_sjobs,
+                              const uint32_t* d_pool, uint8_t* d_arena, uint2* d_edges, int* d_progress,
+                              uint32_t* d_cigar, KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s);
+
 // Fallback for bands no cluster shape can hold: slot contexts in global scratch (ksw_wide_scratch_words per CTA).
 void launch_ksw_wide(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d_order, int njobs,
                      const uint32_t* d_pool, uint8_t* d_arena, size_t arena_stride, uint32_t* d_scratch,

@@ -63,6 +63,7 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     ctx->d_raw.release(); ctx->d_arena.release(); ctx->d_subject.release(); ctx->d_pool.release();
     ctx->d_cigar.release(); ctx->d_scratch.release(); ctx->d_jobs.release(); ctx->d_outs.release();
     ctx->d_runs.release(); ctx->d_order.release(); ctx->d_counter.release(); ctx->d_aoff.release();
+    ctx->d_sjobs.release(); ctx->d_edges.release(); ctx->d_sprog.release();
     ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->side_done) cudaEventDestroy(e);
@@ -188,6 +189,25 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     std::vector<size_t> tb_bytes(nj);
     size_t pool_words = 0, cigar_words = 0;
     double total_work = 0;
+    // Full-matrix alignments (band >= both lengths, wider than one CTA) run as column strips with an arena per alignment
+    // (ksw_dp_strip_kernel) as long as their tracebacks fit into three quarters of the arena budget; the rest takes the cluster route.
+    static const bool use_strips = getenv("LESV_KSW_NO_STRIPS") == nullptr;
+    std::vector<int> strip_ids;
+    std::vector<char> is_strip(nj, 0);
+    size_t strip_arena = 0;
+    if (use_strips) {
+        std::vector<int> cand;
+        for (int k = 0; k < nj; ++k) {
+            const KswJob& J = jobs[k];
+            if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > 640) cand.push_back(k);
+        }
+        for (int k : cand) {
+            const KswJob& J = jobs[k];
+            const size_t tb = ((size_t)(J.qlen + J.tlen - 1) * (size_t)tb_row_blocks(J.qlen, J.tlen, J.w) * 16 + 255) & ~(size_t)255;
+            if (strip_arena + tb > ctx->arena_limit / 4 * 3) break;
+            strip_arena += tb; strip_ids.push_back(k); is_strip[k] = 1;
+        }
+    }
     for (int k = 0; k < nj; ++k) {
         KswJob& J = jobs[k];
         const Shape sh = shape_of(window_blocks(J.tlen, J.w));
@@ -201,6 +221,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (pool_words > 0xFFFFFFF0ull) { ctx->err = "batch too large (packed pool offsets are 32-bit)"; return LESVGPU_E_ARG; }
         tb_bytes[k] = (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
         if (tb_bytes[k] > ctx->arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
+        if (is_strip[k]) { J.nt = kStripBlocks; continue; }
         size_t li = 0;
         for (; li < launches.size(); ++li)
             if (launches[li].ncta == sh.ncta && launches[li].nt == sh.tier) break;
@@ -218,7 +239,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         // the others release (the launches are chained, see below)
         size_t mi = 0;
         for (size_t i = 1; i < launches.size(); ++i) if (launches[i].work > launches[mi].work) mi = i;
-        std::rotate(launches.begin() + mi, launches.begin() + mi + 1, launches.end());
+        if (!launches.empty()) std::rotate(launches.begin() + mi, launches.begin() + mi + 1, launches.end());
     }
     std::vector<int> order;
     order.reserve(nj);
@@ -227,7 +248,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     const double budget = ctx->n_sm * 1.0;
     auto shape_weight = [](int ncta) { return ncta <= 1 ? 1.0 : ncta == 2 ? 1.4 : ncta == 4 ? 1.7 : 2.2; };
     double weighted_work = 0;
-    const Launch* major = &launches[0];
+    const Launch* major = launches.empty() ? nullptr : &launches[0];
     for (const Launch& L : launches) { weighted_work += L.work * shape_weight(L.ncta); if (L.work > major->work) major = &L; }
     for (Launch& L : launches) {
         std::sort(L.ids.begin(), L.ids.end(), [&](int a, int b) {
@@ -280,6 +301,8 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
             arena_limit = std::min(arena_limit, (size_t)((free_b + ctx->d_arena.cap) * 0.90));
     }
+    if (strip_arena > arena_limit) { ctx->err = "traceback arena too small for the full-matrix alignments"; return LESVGPU_E_NOMEM; }
+    arena_limit -= strip_arena;                          // the strips' per-alignment arenas sit behind the classes' ones
     for (;;) {
         arena_need = 0;
         for (Launch& L : launches) { L.arena_off = arena_need; L.arena_bytes = footprint(L); arena_need += L.arena_bytes; }
@@ -311,6 +334,41 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     for (const Launch& L : launches)
         if (L.ncta == 0) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)L.n_clusters);
 
+    // ---- column strips of the full-matrix alignments -------------------------------------------------------------
+    std::vector<KswStripJob> sjobs;
+    size_t edge_words = 0;
+    int prog_ints = 0, strip_smem_q = 0, strip_smem_t = 0;
+    if (!strip_ids.empty()) {
+        std::sort(strip_ids.begin(), strip_ids.end(), [&](int a, int b) {
+            return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
+        });
+        struct Per { int n_strips, prog_off; size_t arena_off, edge_off; };
+        std::vector<Per> per(strip_ids.size());
+        size_t aoff = arena_need;
+        int max_strips = 0;
+        for (size_t x = 0; x < strip_ids.size(); ++x) {
+            const KswJob& J = jobs[strip_ids[x]];
+            const int max_b = ((J.tlen - 1) >> 4) + 1;
+            per[x].n_strips = (max_b + 1 + kStripBlocks - 1) / kStripBlocks;
+            per[x].prog_off = prog_ints; prog_ints += per[x].n_strips + 1;
+            per[x].arena_off = aoff; aoff += (tb_bytes[strip_ids[x]] + 255) & ~(size_t)255;
+            per[x].edge_off = edge_words; edge_words += (size_t)per[x].n_strips * (size_t)(J.qlen + J.tlen - 1);
+            max_strips = std::max(max_strips, per[x].n_strips);
+            strip_smem_q = std::max(strip_smem_q, J.qlen); strip_smem_t = std::max(strip_smem_t, J.tlen);
+        }
+        for (int st = 0; st < max_strips; ++st)            // (strip, alignment) order: a strip's predecessor is always handed out first
+            for (size_t x = 0; x < strip_ids.size(); ++x)
+                if (st < per[x].n_strips)
+                    sjobs.push_back(KswStripJob{strip_ids[x], st, per[x].n_strips, per[x].prog_off, per[x].arena_off, per[x].edge_off});
+        arena_need = aoff;
+        CK(ctx->d_sjobs.reserve(sjobs.size()));
+        CK(ctx->d_edges.reserve(edge_words));
+        CK(ctx->d_sprog.reserve((size_t)prog_ints));
+    }
+    int n_strip_ctas = sjobs.empty() ? 0 : (int)std::min<size_t>(sjobs.size(), (size_t)ctx->n_sm * (kStripBlocks <= 320 ? 2 : 1));
+    if (n_strip_ctas && getenv("LESV_KSW_STRIP_CTAS")) n_strip_ctas = std::max(1, std::min(n_strip_ctas, atoi(getenv("LESV_KSW_STRIP_CTAS"))));
+    counters.push_back(n_strip_ctas);                    // work counter of the strip launch (slot launches.size())
+
     CK(ctx->d_raw.reserve(raw_bytes + 16));
     CK(ctx->d_pool.reserve(pool_words));
     CK(ctx->d_cigar.reserve(cigar_words + 1));
@@ -318,7 +376,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_outs.reserve(nj));
     CK(ctx->d_runs.reserve((size_t)nj * kSigCap));
     CK(ctx->d_order.reserve(nj));
-    CK(ctx->d_counter.reserve(launches.size()));
+    CK(ctx->d_counter.reserve(launches.size() + 1));
     CK(ctx->d_aoff.reserve(arena_offs.size()));
     CK(ctx->d_arena.reserve_exact(arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
@@ -332,7 +390,11 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(cudaMemcpyAsync(ctx->d_raw.p, ctx->h_raw.p, raw_bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KswJob) * nj, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_counter.p, counters.data(), sizeof(int) * launches.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_counter.p, counters.data(), sizeof(int) * counters.size(), cudaMemcpyHostToDevice, s));
+    if (!sjobs.empty()) {
+        CK(cudaMemcpyAsync(ctx->d_sjobs.p, sjobs.data(), sizeof(KswStripJob) * sjobs.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(ctx->d_sprog.p, 0, sizeof(int) * (size_t)prog_ints, s));
+    }
     CK(cudaMemcpyAsync(ctx->d_aoff.p, arena_offs.data(), sizeof(size_t) * arena_offs.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->d_outs.p, 0, sizeof(KswOut) * nj, s));
     CK(cudaEventRecord(ctx->ev[1], s));
@@ -366,6 +428,15 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                                 L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ws);
                 CK(cudaGetLastError());
             }
+        }
+        if (!sjobs.empty()) {
+            cudaStream_t ss = ctx->side[2];
+            CK(cudaStreamWaitEvent(ss, ctx->ev[2], 0));
+            CK(launch_ksw_strips(n_strip_ctas, ksw_smem_bytes(strip_smem_q, strip_smem_t), ctx->d_jobs.p, ctx->d_sjobs.p, (int)sjobs.size(),
+                                 ctx->d_pool.p, ctx->d_arena.p, ctx->d_edges.p, ctx->d_sprog.p, ctx->d_cigar.p, ctx->d_runs.p,
+                                 ctx->d_outs.p, ctx->d_counter.p + launches.size(), ss));
+            CK(cudaEventRecord(ctx->side_done[2], ss));
+            CK(cudaStreamWaitEvent(s, ctx->side_done[2], 0));
         }
         CK(cudaEventRecord(ctx->side_done[0], ls));
         CK(cudaStreamWaitEvent(s, ctx->side_done[0], 0));
@@ -403,6 +474,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             fprintf(stderr, "[ksw debug] launch %zu: ncta=%d tier=%d jobs=%d ctas/clusters=%d (fair %d) cells=%.1fG\n",
                     li, L.ncta, L.nt, L.count, L.n_clusters, L.fair, cells / 1e9);
         }
+        if (!sjobs.empty()) fprintf(stderr, "[ksw debug] strips: %zu alignments, %zu strips on %d CTAs\n", strip_ids.size(), sjobs.size(), n_strip_ctas);
         fprintf(stderr, "[ksw debug] all launches: %.1f ms\n", total);
     }
     lesvgpu_timing& T = ctx->timing;
@@ -411,8 +483,8 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     cudaEventElapsedTime(&T.dp_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&T.d2h_ms, ctx->ev[3], ctx->ev[4]);
     T.scan_ms = 0.f;                                  // the scan runs inside the traceback walk
-    T.dp_launches = (int)launches.size();
-    T.kernel_launches = 1 + (int)launches.size();
+    T.dp_launches = (int)launches.size() + (sjobs.empty() ? 0 : 1);
+    T.kernel_launches = 1 + T.dp_launches;
     g_lesv_launches += (unsigned long long)T.kernel_launches;
     T.h2d_bytes = raw_bytes + sizeof(KswJob) * nj + sizeof(int) * nj;
     T.d2h_bytes = d2h;

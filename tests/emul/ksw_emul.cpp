@@ -25,6 +25,8 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
                      int skew_k = 0, unsigned seed = 0);
 static int g_eager = 0;     // 1: step with thread_row_step<true> (carry resolved up front, barrier-mode kernel)
 extern "C" void lesv_emul_set_eager(int on) { g_eager = on; }
+static int g_strip = 0;     // > 0: column strips of g_strip blocks, one strip after the other (ksw_dp_strip_kernel)
+extern "C" void lesv_emul_set_strip(int blocks) { g_strip = blocks; }
 
 extern "C" int lesv_emul_ksw_extd2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                    int w, int nt, uint32_t** cigar_out)
@@ -125,6 +127,45 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
                         ++r;
                     }
                 }
+        }
+    } else if (g_strip > 0) {
+        // ksw_dp_strip_kernel: every thread keeps one block for the whole pass (nt = 2^24 in thread_row_step), strip s
+        // takes the column-15 values of strip s-1 from a per-row edge buffer; row range and carry wiring as in the kernel
+        const int SW = g_strip;
+        const int max_b = ((tlen - 1) >> 4) + 1;
+        const int n_strips = (max_b + 1 + SW - 1) / SW;
+        const int nrow_all = (int)nrow;
+        std::vector<Carry> edge_prev(nrow, carry_init()), edge_cur(nrow, carry_init());
+        for (int st = 0; st < n_strips; ++st) {
+            const int B0 = st * SW;
+            const int c0 = 16 * B0 - 16, c1e = 16 * (B0 + SW - 1) + 15;
+            int r_lo = c0 > 2 * c0 - w ? c0 : 2 * c0 - w;
+            r_lo = r_lo < 0 ? 0 : r_lo;
+            long long hi = (long long)c1e + qlen - 1, hi2 = 2ll * c1e + w;
+            hi = hi < hi2 ? hi : hi2;
+            const int r_hi = hi < nrow_all - 1 ? (int)hi : nrow_all - 1;
+            std::vector<ThreadCtx> ts(SW);
+            std::vector<Carry> prev(SW, carry_init()), prev_next(SW, carry_init());
+            for (int t = 0; t < SW; ++t) thread_ctx_reset(ts[t], B0 + t);
+            for (auto& e : edge_cur) { e.xv = 0xDEADBEEFu; e.x2 = 0xDEADBEEFu; }
+            for (int r = r_lo; r <= r_hi; ++r) {
+                for (int tid = 0; tid < SW; ++tid) {
+                    Carry cin;
+                    if (tid == 0) { if (st > 0 && r > 0) cin = edge_prev[r - 1]; else { cin.xv = 0; cin.x2 = 0; } }
+                    else cin = prev[tid - 1];
+                    Carry cout; uint32_t tb[4];
+                    prev_next[tid] = prev[tid];
+                    if (thread_row_step<true>(ts[tid], 1 << 24, r, qlen, tlen, w, prow_blocks, tp.data(), qrp.data(),
+                                              [&]() { return cin; }, cout, tb)) {
+                        if (ts[tid].tb_off < 0 || ts[tid].tb_off >= (int)prow) return -2;
+                        memcpy(&p[(size_t)r * prow + (size_t)ts[tid].tb_off], tb, 16);
+                        prev_next[tid] = cout;
+                        if (tid == SW - 1) edge_cur[r] = cout;
+                    }
+                }
+                prev.swap(prev_next);
+            }
+            edge_prev.swap(edge_cur);
         }
     } else
     for (int r = 0; r < (int)nrow; ++r) {

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import helpers as H
+from lesv_b200.synth import mutate
 
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -79,3 +80,29 @@ def test_emulated_kernel_traceback_bytes_equal_oracle():
             assert np.array_equal(A[r, lo - st:hi - st + 1], B[r, lo - st:hi - st + 1]), (it, ql, tl, w, r)
             cells += hi - lo + 1
     assert cells > 5_000_000
+
+
+def test_strip_schedule_equals_oracle():
+    """ksw_dp_strip_kernel's schedule (threads keep one block for the whole pass, strips of columns run one after the
+    other and hand their column-15 values over through a per-row edge buffer), emulated on the host for several strip
+    widths, full-matrix and banded alignments."""
+    rng = np.random.default_rng(3)
+    lib = H.emul()
+    n = 0
+    for it in range(24):
+        ln = int(rng.integers(200, 1200))
+        q = rng.integers(0, 4, ln, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, 0.15, rng))
+        if it % 3 == 0:
+            t = np.ascontiguousarray(np.concatenate([t[:ln // 3], rng.integers(0, 4, int(rng.integers(50, 400)), dtype=np.uint8), t[ln // 3:]]))
+        w = max(len(q), len(t)) if it % 2 == 0 else abs(len(q) - len(t)) + int(rng.integers(40, 300))
+        exp, _ = H.oracle_ksw(q, t, w)
+        for sw in (2, 5, 64):
+            lib.lesv_emul_set_strip(sw)
+            try:
+                got = H.emul_ksw(q, t, w, 32, eager=True)
+            finally:
+                lib.lesv_emul_set_strip(0)
+            assert got == exp, (it, len(q), len(t), w, sw)
+            n += 1
+    assert n == 72

@@ -105,3 +105,23 @@ def test_many_small_and_mixed_shapes_in_one_batch(ctx):
         w = int(abs(len(q) - len(t)) + rng.integers(1, 1 + n // 3))
         cases.append((q, t, w))
     _check(ctx, cases)
+
+
+def test_full_matrix_alignments_as_column_strips(ctx):
+    """Alignments without a band and wider than one CTA run as column strips (ksw_dp_strip_kernel): CIGARs must equal
+    the oracle's, here on 12-20 kb pairs (2-3 strips, some with a 2 kb insertion)."""
+    from lesv_b200.synth import mutate
+    c = ctx
+    rng = np.random.default_rng(11)
+    qs, ts = [], []
+    for i in range(4):
+        n = int(rng.integers(11000, 16000))
+        t = rng.integers(0, 4, n, dtype=np.uint8)
+        q = np.ascontiguousarray(mutate(t, 0.12, rng))
+        if i % 2 == 0:
+            q = np.ascontiguousarray(np.concatenate([q[:n // 2], rng.integers(0, 4, 2000, dtype=np.uint8), q[n // 2:]]))
+        qs.append(q); ts.append(t)
+    res, cigs = c.ksw_batch(qs, ts, [-1] * len(qs))
+    for q, t, r, cg in zip(qs, ts, res, cigs):
+        exp, _ = H.oracle_ksw(q, t, -1)
+        assert r.ok and [int(x) for x in cg] == exp
