@@ -190,7 +190,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     size_t pool_words = 0, cigar_words = 0;
     double total_work = 0;
     // Full-matrix alignments (band >= both lengths, wider than one CTA) run as column strips with an arena per alignment
-    // (ksw_dp_strip_kernel) as long as their tracebacks fit into three quarters of the arena budget; the rest takes the cluster route.
+    // (ksw_dp_strip_kernel) in groups whose tracebacks fit into three quarters of the arena budget, one launch per group.
     static const bool use_strips = getenv("LESV_KSW_NO_STRIPS") == nullptr;
     std::vector<int> strip_ids;
     std::vector<char> is_strip(nj, 0);
@@ -201,11 +201,23 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             const KswJob& J = jobs[k];
             if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > 640) cand.push_back(k);
         }
+        // They are processed in groups whose arenas fit into three quarters of the budget, one launch per group.  A group
+        // costs the critical path of one alignment (~110 k rows) however few alignments it holds, so a short last group
+        // (<= 15 alignments: one round of 8-CTA clusters) takes the cluster route next to the strips instead.
+        const size_t cap = ctx->arena_limit / 4 * 3;
+        size_t group = 0, group_first = 0;
         for (int k : cand) {
             const KswJob& J = jobs[k];
             const size_t tb = ((size_t)(J.qlen + J.tlen - 1) * (size_t)tb_row_blocks(J.qlen, J.tlen, J.w) * 16 + 255) & ~(size_t)255;
-            if (strip_arena + tb > ctx->arena_limit / 4 * 3) break;
-            strip_arena += tb; strip_ids.push_back(k); is_strip[k] = 1;
+            if (tb > cap) continue;                         // a single alignment that large takes the cluster / wide route
+            if (group + tb > cap) { group = 0; group_first = strip_ids.size(); }
+            group += tb;
+            strip_arena = std::max(strip_arena, group);
+            strip_ids.push_back(k); is_strip[k] = 1;
+        }
+        if (group_first > 0 && strip_ids.size() - group_first <= 15) {
+            for (size_t x = group_first; x < strip_ids.size(); ++x) is_strip[strip_ids[x]] = 0;
+            strip_ids.resize(group_first);
         }
     }
     for (int k = 0; k < nj; ++k) {
@@ -335,39 +347,53 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (L.ncta == 0) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)L.n_clusters);
 
     // ---- column strips of the full-matrix alignments -------------------------------------------------------------
-    std::vector<KswStripJob> sjobs;
+    std::vector<KswStripJob> sjobs;                      // all groups, one after the other
+    struct StripGroup { int first, count, n_ctas; };
+    std::vector<StripGroup> sgroups;
     size_t edge_words = 0;
     int prog_ints = 0, strip_smem_q = 0, strip_smem_t = 0;
     if (!strip_ids.empty()) {
-        std::sort(strip_ids.begin(), strip_ids.end(), [&](int a, int b) {
-            return tb_bytes[a] != tb_bytes[b] ? tb_bytes[a] > tb_bytes[b] : a < b;
-        });
         struct Per { int n_strips, prog_off; size_t arena_off, edge_off; };
-        std::vector<Per> per(strip_ids.size());
-        size_t aoff = arena_need;
-        int max_strips = 0;
-        for (size_t x = 0; x < strip_ids.size(); ++x) {
-            const KswJob& J = jobs[strip_ids[x]];
-            const int max_b = ((J.tlen - 1) >> 4) + 1;
-            per[x].n_strips = (max_b + 1 + kStripBlocks - 1) / kStripBlocks;
-            per[x].prog_off = prog_ints; prog_ints += per[x].n_strips + 1;
-            per[x].arena_off = aoff; aoff += (tb_bytes[strip_ids[x]] + 255) & ~(size_t)255;
-            per[x].edge_off = edge_words; edge_words += (size_t)per[x].n_strips * (size_t)(J.qlen + J.tlen - 1);
-            max_strips = std::max(max_strips, per[x].n_strips);
-            strip_smem_q = std::max(strip_smem_q, J.qlen); strip_smem_t = std::max(strip_smem_t, J.tlen);
+        const size_t cap = ctx->arena_limit / 4 * 3;
+        size_t x0 = 0;
+        while (x0 < strip_ids.size()) {                  // a group = consecutive alignments (input order) whose arenas fit
+            size_t x1 = x0, aoff = arena_need;
+            std::vector<Per> per;
+            int max_strips = 0;
+            while (x1 < strip_ids.size()) {
+                const size_t tb = (tb_bytes[strip_ids[x1]] + 255) & ~(size_t)255;
+                if (x1 > x0 && aoff - arena_need + tb > cap) break;
+                const KswJob& J = jobs[strip_ids[x1]];
+                const int max_b = ((J.tlen - 1) >> 4) + 1;
+                Per p;
+                p.n_strips = (max_b + 1 + kStripBlocks - 1) / kStripBlocks;
+                p.prog_off = prog_ints; prog_ints += p.n_strips + 1;
+                p.arena_off = aoff; aoff += tb;
+                p.edge_off = edge_words; edge_words += (size_t)p.n_strips * (size_t)(J.qlen + J.tlen - 1);
+                max_strips = std::max(max_strips, p.n_strips);
+                strip_smem_q = std::max(strip_smem_q, J.qlen); strip_smem_t = std::max(strip_smem_t, J.tlen);
+                per.push_back(p);
+                ++x1;
+            }
+            StripGroup g{(int)sjobs.size(), 0, 0};
+            for (int st = 0; st < max_strips; ++st)        // (strip, alignment) order: a strip's predecessor is always handed out first
+                for (size_t x = x0; x < x1; ++x)
+                    if (st < per[x - x0].n_strips) {
+                        const Per& p = per[x - x0];
+                        sjobs.push_back(KswStripJob{strip_ids[x], st, p.n_strips, p.prog_off, p.arena_off, p.edge_off});
+                    }
+            g.count = (int)sjobs.size() - g.first;
+            g.n_ctas = (int)std::min<size_t>((size_t)g.count, (size_t)ctx->n_sm);
+            if (getenv("LESV_KSW_STRIP_CTAS")) g.n_ctas = std::max(1, std::min(g.n_ctas, atoi(getenv("LESV_KSW_STRIP_CTAS"))));
+            sgroups.push_back(g);
+            x0 = x1;
         }
-        for (int st = 0; st < max_strips; ++st)            // (strip, alignment) order: a strip's predecessor is always handed out first
-            for (size_t x = 0; x < strip_ids.size(); ++x)
-                if (st < per[x].n_strips)
-                    sjobs.push_back(KswStripJob{strip_ids[x], st, per[x].n_strips, per[x].prog_off, per[x].arena_off, per[x].edge_off});
-        arena_need = aoff;
+        arena_need += strip_arena;
         CK(ctx->d_sjobs.reserve(sjobs.size()));
         CK(ctx->d_edges.reserve(edge_words));
         CK(ctx->d_sprog.reserve((size_t)prog_ints));
     }
-    int n_strip_ctas = sjobs.empty() ? 0 : (int)std::min<size_t>(sjobs.size(), (size_t)ctx->n_sm * (kStripBlocks <= 320 ? 2 : 1));
-    if (n_strip_ctas && getenv("LESV_KSW_STRIP_CTAS")) n_strip_ctas = std::max(1, std::min(n_strip_ctas, atoi(getenv("LESV_KSW_STRIP_CTAS"))));
-    counters.push_back(n_strip_ctas);                    // work counter of the strip launch (slot launches.size())
+    for (const StripGroup& g : sgroups) counters.push_back(g.n_ctas);   // work counters of the strip launches (slots launches.size() + group)
 
     CK(ctx->d_raw.reserve(raw_bytes + 16));
     CK(ctx->d_pool.reserve(pool_words));
@@ -376,7 +402,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_outs.reserve(nj));
     CK(ctx->d_runs.reserve((size_t)nj * kSigCap));
     CK(ctx->d_order.reserve(nj));
-    CK(ctx->d_counter.reserve(launches.size() + 1));
+    CK(ctx->d_counter.reserve(launches.size() + sgroups.size() + 1));
     CK(ctx->d_aoff.reserve(arena_offs.size()));
     CK(ctx->d_arena.reserve_exact(arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
@@ -429,12 +455,15 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                 CK(cudaGetLastError());
             }
         }
-        if (!sjobs.empty()) {
+        if (!sjobs.empty()) {                           // one launch per group, in order, on their own stream
             cudaStream_t ss = ctx->side[2];
             CK(cudaStreamWaitEvent(ss, ctx->ev[2], 0));
-            CK(launch_ksw_strips(n_strip_ctas, ksw_smem_bytes(strip_smem_q, strip_smem_t), ctx->d_jobs.p, ctx->d_sjobs.p, (int)sjobs.size(),
-                                 ctx->d_pool.p, ctx->d_arena.p, ctx->d_edges.p, ctx->d_sprog.p, ctx->d_cigar.p, ctx->d_runs.p,
-                                 ctx->d_outs.p, ctx->d_counter.p + launches.size(), ss));
+            for (size_t gi = 0; gi < sgroups.size(); ++gi) {
+                const StripGroup& g = sgroups[gi];
+                CK(launch_ksw_strips(g.n_ctas, ksw_smem_bytes(strip_smem_q, strip_smem_t), ctx->d_jobs.p, ctx->d_sjobs.p + g.first, g.count,
+                                     ctx->d_pool.p, ctx->d_arena.p, ctx->d_edges.p, ctx->d_sprog.p, ctx->d_cigar.p, ctx->d_runs.p,
+                                     ctx->d_outs.p, ctx->d_counter.p + launches.size() + gi, ss));
+            }
             CK(cudaEventRecord(ctx->side_done[2], ss));
             CK(cudaStreamWaitEvent(s, ctx->side_done[2], 0));
         }
@@ -474,7 +503,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             fprintf(stderr, "[ksw debug] launch %zu: ncta=%d tier=%d jobs=%d ctas/clusters=%d (fair %d) cells=%.1fG\n",
                     li, L.ncta, L.nt, L.count, L.n_clusters, L.fair, cells / 1e9);
         }
-        if (!sjobs.empty()) fprintf(stderr, "[ksw debug] strips: %zu alignments, %zu strips on %d CTAs\n", strip_ids.size(), sjobs.size(), n_strip_ctas);
+        if (!sjobs.empty()) fprintf(stderr, "[ksw debug] strips: %zu alignments, %zu strips in %zu group(s)\n", strip_ids.size(), sjobs.size(), sgroups.size());
         fprintf(stderr, "[ksw debug] all launches: %.1f ms\n", total);
     }
     lesvgpu_timing& T = ctx->timing;
@@ -483,7 +512,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     cudaEventElapsedTime(&T.dp_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&T.d2h_ms, ctx->ev[3], ctx->ev[4]);
     T.scan_ms = 0.f;                                  // the scan runs inside the traceback walk
-    T.dp_launches = (int)launches.size() + (sjobs.empty() ? 0 : 1);
+    T.dp_launches = (int)launches.size() + (int)sgroups.size();
     T.kernel_launches = 1 + T.dp_launches;
     g_lesv_launches += (unsigned long long)T.kernel_launches;
     T.h2d_bytes = raw_bytes + sizeof(KswJob) * nj + sizeof(int) * nj;
