@@ -106,7 +106,8 @@ def make_reads(sample, n_reads: int, seed: int, read_len: int = READ_LEN):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, active: bool = True):
+        self.active = active                             # only rank 0 polls nvidia-smi (its line is the one reported)
         self.idx = gpu_index
         self.samples, self.reasons, self.smax = [], set(), None
         self._stop = threading.Event()
@@ -130,13 +131,15 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.active:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         s = sorted(self.samples)
@@ -346,7 +349,7 @@ def main():
     barrier()
     acc = None
     launches0 = lib.lesvgpu_launch_count()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, active=(rank == 0)) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
             r = step()
