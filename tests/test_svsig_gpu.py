@@ -140,3 +140,17 @@ def test_svr_and_svsig_dropin_on_repeats_and_large_svs(tmp_path):
     sig_out = os.path.join(work, "svsig_gpu")
     subprocess.run([BIN, sig_out, svr_out, os.path.join(work, "db"), "40", "4"], check=True)
     assert _compare_dirs(os.path.join(work, "svsig"), sig_out) >= 20
+
+
+def test_svr_batch_c_abi_equals_golden(ctx):
+    """lesvgpu_svr_batch (process_one_m4_list over one query volume) through the C ABI on the golden M4Record file."""
+    from lesv_b200 import capi
+    d = GOLD
+    Q, S = H.LesvDb(os.path.join(d, "db"), "query"), H.LesvDb(os.path.join(d, "db"), "subject")
+    capi.subject_load(ctx, S.pac)
+    m4 = np.fromfile(os.path.join(d, "db", "backup_results", "stagebackup_results_Q00000000_D00000000.m4x"), dtype=capi.M4_DTYPE)
+    svr, st = capi.svr_batch(ctx, Q.pac, Q.read_offset, S.seq_offset, S.seq_size, m4, 3000, 70.0, 300)
+    got = sorted(tuple(int(r[n]) for n in ("query_id", "qdir", "qoff", "qend", "qsize", "subject_id", "soff", "send", "dist")) for r in svr)
+    exp = sorted(tuple(int(x) for x in l.split()[:9]) for l in open(os.path.join(d, "svr", "Q00000000.sv_read")))
+    assert len(exp) >= 50 and got == exp
+    assert st.n_m4 == len(m4)
