@@ -27,23 +27,29 @@
 // the int8 value sits in the HIGH byte, so VIADD.16x2's mod-2^16 wrap IS the int8 wrap and
 // VIMNMX's signed 16-bit compare IS the int8 compare with the low byte breaking ties.  Pair j of a
 // 16-column block holds columns (j, j+8), so "one column to the left" of pair j is pair j-1 (one
-// PRMT per block fixes up pair 0).  State per column (lane):
-//     U = 256u + 127      V = 256v + 127
-//     AX = 256*max(a',0)  with x = AX/256 - (q+e);  AY, AX2, AY2 likewise (low byte 0)
-//     S = 256s + 4                                    (tag = 4 - winner index)
-// Row update of a pair:
-//     Va = V[t-1] + (256*-(q+e)   + 3 - 127)    ka  = AX[t-1]  + Va = 256a  + 3
-//     Vb = V[t-1] + (256*-(q2+e2) + 1 - 127)    ka2 = AX2[t-1] + Vb = 256a2 + 1
-//     Ua = U + (256*-(q+e) + 2 - 127)           kb  = AY  + Ua = 256b  + 2
-//     Ub = U + (256*-(q2+e2) + 0 - 127)         kb2 = AY2 + Ub = 256b2 + 0
-//     k  = max(S, ka, kb, ka2, kb2)             tag = k & 7
-//     Zc = min(k | 0xFF, 0x02FF) = 256z + 255   (clamp z <= 2)
-//     U' = Zc + ~V[t-1]    V' = Zc + ~U         (~w = -w-1 per lane; 255 - 127 - 1 = 127)
-//     AX'  = relu(ka  + (~Zc + 256(q+1)  - 3))  = 256*max(a - z + q, 0)
-//     AY'  = relu(kb  + (~Zc + 256(q+1)  - 2))
-//     AX2' = relu(ka2 + (~Zc + 256(q2+1) - 1))   AY2' = relu(kb2 + (~Zc + 256(q2+1)))
-// and the flag "x' > -(q+e)" is "high byte of AX' != 0", tested 4 columns at a time after a byte
-// permute ((bytes + 0x7f) & 0x80).
+// PRMT per block fixes up pair 0).
+//
+// sm_100a issues the packed instructions on two pipes of half a warp-instruction per clock each
+// (tools/ubench/pipes.cu, profiles/r2_pipes.txt): VIADD.16x2 and IMAD on one, VIMNMX / VIMNMX3 /
+// VIADDMNMX / LOP3 / PRMT / SHF on the other.  The representation below is chosen so that the
+// second pipe sees as few instructions as possible and both pipes carry about the same load.
+// State per column (lane), all arithmetic mod 2^16:
+//     UC = 256(u - (q+e))   VC = 256(v - (q+e))                      (low byte 0)
+//     PX = 256 max(a',0) + 3    with x = PX/256 - (q+e);  PY = .. + 2,  PX2 = .. + 1,  PY2 = .. + 0
+//     S  = 256 s + 4                                                  (tag = 4 - winner index)
+// so that the five candidates of a row need no constants:
+//     ka  = PX[t-1] + VC[t-1]        = 256a  + 3        kb  = PY  + UC        = 256b  + 2
+//     ka2 = PX2[t-1] + (VC[t-1] + D) = 256a2 + 1        kb2 = PY2 + (UC + D)  = 256b2 + 0
+//     (D = 256((q+e) - (q2+e2)))
+//     k   = max3(max3(S, ka, kb), ka2, kb2)             tag = k & 7
+//     W   = min((k | 0xFF) + K, C)   = 256(z - 2(q+e)) + 1            (one VIADDMNMX: clamp z <= 2)
+//     UC' = W + ~VC[t-1]    VC' = W + ~UC                              (~w = -w-1 per lane)
+//     N   = ~W + 256(q - 2(q+e)) + 2 = 256(q - z),   N2 = N + 256(q2 - q)
+//     PX' = max(ka + N, 3)   PY' = max(kb + N, 2)   PX2' = max(ka2 + N2, 1)   PY2' = max(kb2 + N2, 0)
+// The relu thresholds are the tags, so a clamped and an unclamped lane carry the same low byte and
+// no lane sum ever carries out of its low byte into the value.  The flag "x' > -(q+e)" is
+// min(PX', 256 + 3) = 256 flag + 3; the four flags and the tag are summed into the high byte of the
+// lane with multiply-adds (the other pipe) and one PRMT per four columns gathers the bytes.
 #pragma once
 #include <stdint.h>
 
@@ -66,21 +72,26 @@ static_assert(kLongDiff == -4, "long_diff");
 static_assert(!(kQ2 + kE2 + kLongThres * kE2 > kQ + kE + kLongThres * kE), "long_thres bump");
 
 // ---- lane representation: 256*value + tag ---------------------------------------------------
-constexpr int kLUV = 127;                                   // low byte of U and V
+constexpr int kQE = kQ + kE, kQE2 = kQ2 + kE2;
 constexpr int kTagS = 4, kTagA = 3, kTagB = 2, kTagA2 = 1, kTagB2 = 0;
 KSW_HDC uint32_t dup(int v) { return (uint32_t)(v & 0xFFFF) | ((uint32_t)(v & 0xFFFF) << 16); }
-constexpr uint32_t kVa = dup(256 * -(kQ + kE) + kTagA - kLUV);
-constexpr uint32_t kVb = dup(256 * -(kQ2 + kE2) + kTagA2 - kLUV);
-constexpr uint32_t kUa = dup(256 * -(kQ + kE) + kTagB - kLUV);
-constexpr uint32_t kUb = dup(256 * -(kQ2 + kE2) + kTagB2 - kLUV);
-constexpr uint32_t kClampZ = dup(256 * kMatch + 255);
-constexpr uint32_t kNZa = dup(256 * (kQ + 1) - kTagA), kNZb = dup(256 * (kQ + 1) - kTagB);
-constexpr uint32_t kNZa2 = dup(256 * (kQ2 + 1) - kTagA2), kNZb2 = dup(256 * (kQ2 + 1) - kTagB2);
-constexpr uint32_t kInitU = dup(256 * -(kQ + kE) + kLUV);   // u = v = -(q+e)
+constexpr uint32_t kD2 = dup(256 * (kQE - kQE2));           // VC/UC -> the long-gap candidates
+constexpr uint32_t kWK = dup(256 * (-2 * kQE) - 254);       // (k | 0xFF) + kWK = 256(z - 2(q+e)) + 1
+constexpr uint32_t kWClamp = dup(256 * (kMatch - 2 * kQE) + 1);
+constexpr uint32_t kNQ = dup(256 * (kQ - 2 * kQE) + 2);     // ~W + kNQ = 256(q - z)
+constexpr uint32_t kNQ2 = dup(256 * (kQ2 - kQ));            // N -> N2
+constexpr uint32_t kReluA = dup(kTagA), kReluB = dup(kTagB), kReluA2 = dup(kTagA2), kReluB2 = dup(kTagB2);
+constexpr uint32_t kInitUV = dup(256 * (-2 * kQE));         // u = v = -(q+e)
 constexpr uint32_t kInitS = dup(256 * 0 + kTagS);           // calloc()ed s[] = 0
 constexpr uint32_t kSMatch = dup(256 * kMatch + kTagS);
 constexpr uint32_t kSStep = (uint32_t)((256 * (kMismatch - kMatch)) & 0xFFFF);   // 0xF900, no carry out of a lane
 static_assert(256 * kMatch + kTagS + (int)kSStep < 65536, "score select stays inside its lane");
+static_assert((kSStep & 0xFF) == 0, "score step is a multiple of 256: it can be pre-shifted by up to 8 bits");
+// flags: min(P, 256 + tag) = 256 flag + tag; summed with weights 128/64/32/16 next to 256 * tag
+constexpr uint32_t kSatA = dup(256 + kTagA), kSatB = dup(256 + kTagB), kSatA2 = dup(256 + kTagA2), kSatB2 = dup(256 + kTagB2);
+constexpr int kFlagJunk = 128 * kTagA + 64 * kTagB + 32 * kTagA2 + 16 * kTagB2;   // what the tags add up to
+constexpr uint32_t kFlagFix = (uint32_t)(0u - (uint32_t)kFlagJunk * 0x00010001u); // 32-bit add: both lanes at once
+static_assert(kFlagJunk == 544, "flag sum");
 
 // value the reference writes into u[r] (top row) and uses as v1 at column 0 (:150, :154)
 KSW_HD int first_gap_diff(int r)
@@ -93,7 +104,8 @@ KSW_HD int first_gap_diff(int r)
 KSW_HD uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 KSW_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 KSW_HD uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
-KSW_HD uint32_t vaddrelu(uint32_t a, uint32_t b) { return __viaddmax_s16x2_relu(a, b, 0u); }
+KSW_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }   // max(a+b, c)
+KSW_HD uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }   // min(a+b, c)
 KSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
     uint32_t r;                              // PTX prmt: selector bit 3 = replicate the byte's sign
@@ -115,9 +127,14 @@ KSW_HD uint32_t vmin2(uint32_t a, uint32_t b)
 {
     return mk2(lo16(a) < lo16(b) ? lo16(a) : lo16(b), hi16(a) < hi16(b) ? hi16(a) : hi16(b));
 }
-KSW_HD uint32_t vaddrelu(uint32_t a, uint32_t b)
+KSW_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c)
 {
-    return mk2(max_i((int16_t)(lo16(a) + lo16(b)), 0), max_i((int16_t)(hi16(a) + hi16(b)), 0));
+    return mk2(max_i((int16_t)(lo16(a) + lo16(b)), lo16(c)), max_i((int16_t)(hi16(a) + hi16(b)), hi16(c)));
+}
+KSW_HD int min_i(int a, int b) { return a < b ? a : b; }
+KSW_HD uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c)
+{
+    return mk2(min_i((int16_t)(lo16(a) + lo16(b)), lo16(c)), min_i((int16_t)(hi16(a) + hi16(b)), hi16(c)));
 }
 KSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -149,7 +166,7 @@ KSW_HD int tb_byte_pos(int c) { return 4 * ((c & 7) >> 1) + 2 * (c & 1) + (c >> 
 
 // ---- per-block register state -----------------------------------------------------------------
 struct BlockState {
-    uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8];          // X.. = AX.. of the header comment
+    uint32_t U[8], V[8], X[8], Y[8], X2[8], Y2[8];          // UC, VC, PX, PY, PX2, PY2 of the header comment
     // The score byte s[t] of a column is one of three values -- match, mismatch, or the calloc()ed 0
     // of a column never written yet -- so the block keeps 2 bits per column (bit 2c: mismatch, bit
     // 2c+1: never written) and rebuilds the S lanes of a row from them.  Stale bytes (columns of the
@@ -159,27 +176,27 @@ struct BlockState {
     {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            U[j] = kInitU; V[j] = kInitU; X[j] = 0u; Y[j] = 0u;
-            X2[j] = 0u; Y2[j] = 0u;
+            U[j] = kInitUV; V[j] = kInitUV; X[j] = kReluA; Y[j] = kReluB;
+            X2[j] = kReluA2; Y2[j] = kReluB2;
         }
         sbits = 0xAAAAAAAAu;
     }
 };
 
-// Left-neighbour values entering a block at column -1: X^, V^ (low/high lane of xv) and X2^.
+// Left-neighbour values entering a block at column -1: PX, VC (low/high lane of xv) and PX2.
 struct Carry {
-    uint32_t xv;    // lo = X^[-1], hi = V^[-1]
-    uint32_t x2;    // lo = X2^[-1]
+    uint32_t xv;    // lo = PX[-1], hi = VC[-1]
+    uint32_t x2;    // lo = PX2[-1]
 };
 KSW_HD Carry carry_init()
 {
-    Carry c; c.xv = kInitU & 0xFFFF0000u; c.x2 = 0u; return c;
+    Carry c; c.xv = (kInitUV & 0xFFFF0000u) | (uint32_t)kTagA; c.x2 = (uint32_t)kTagA2; return c;
 }
 KSW_HD Carry carry_left_boundary(int r)     // column 0, :148-151
 {
     Carry c;
-    c.xv = (uint32_t)((256 * first_gap_diff(r) + kLUV) & 0xFFFF) << 16;
-    c.x2 = 0u;
+    c.xv = ((uint32_t)((256 * (first_gap_diff(r) - kQE)) & 0xFFFF) << 16) | (uint32_t)kTagA;
+    c.x2 = (uint32_t)kTagA2;
     return c;
 }
 
@@ -191,21 +208,49 @@ KSW_HD uint32_t mismatch_bits(uint32_t tword, uint32_t qword)
     return (x | (x >> 1)) & 0x55555555u;
 }
 
-// S lanes of a row from the block's score bits.
-KSW_HD void score_lanes(uint32_t sbits, uint32_t S[8])
+// S lanes of a row from the block's score bits: one AND and one multiply-add per pair (the bit of pair
+// j sits at 2j / 2j+16; kSStep is a multiple of 256, so for 2j <= 8 the shift is folded into the factor).
+KSW_HD void score_lanes(uint32_t sbits, bool all_written, uint32_t S[8])
 {
+    const uint32_t hi = sbits >> 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint32_t e = (sbits >> (2 * j)) & 0x00010001u;
-        S[j] = e * kSStep + kSMatch;                          // per lane: match or mismatch
+        const int sh = j < 5 ? 2 * j : 2 * j - 8;
+        const uint32_t e = (j < 5 ? sbits : hi) & (0x00010001u << sh);
+        S[j] = e * (kSStep >> sh) + kSMatch;                  // per lane: match or mismatch
     }
-    if (sbits & 0xAAAAAAAAu) {                                // leading-edge block only: columns still at calloc's 0
+    if (!all_written && (sbits & 0xAAAAAAAAu)) {              // leading-edge block only: columns still at calloc's 0
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t z = (sbits >> (2 * j + 1)) & 0x00010001u;
             S[j] -= z * (uint32_t)((kSMatch - kInitS) & 0xFFFF);    // match score -> 0, no borrow between lanes
         }
     }
+}
+
+// One pair of columns, one anti-diagonal: x1, v1, x21 are the previous-row PX, VC, PX2 of the columns to the
+// left.  Updates pair j of the block in place and returns the lane word whose HIGH bytes are the traceback bytes.
+KSW_HD uint32_t pair_row(BlockState& b, int j, uint32_t s, uint32_t x1, uint32_t v1, uint32_t x21)
+{
+    const uint32_t u0 = b.U[j];
+    const uint32_t ka = vadd2(x1, v1), kb = vadd2(b.Y[j], u0);
+    const uint32_t ka2 = vadd2(x21, vadd2(v1, kD2)), kb2 = vadd2(b.Y2[j], vadd2(u0, kD2));
+    const uint32_t k = vmax3(vmax3(s, ka, kb), ka2, kb2);
+    const uint32_t w = vaddmin(k | 0x00FF00FFu, kWK, kWClamp);
+    const uint32_t n = vadd2(~w, kNQ), n2 = vadd2(n, kNQ2);
+    b.U[j] = vadd2(w, ~v1);
+    b.V[j] = vadd2(w, ~u0);
+    const uint32_t px = vaddmax(ka, n, kReluA), py = vaddmax(kb, n, kReluB);
+    const uint32_t px2 = vaddmax(ka2, n2, kReluA2), py2 = vaddmax(kb2, n2, kReluB2);
+    b.X[j] = px; b.Y[j] = py; b.X2[j] = px2; b.Y2[j] = py2;
+    // high byte of a lane: E continues | F continues | E~ continues | F~ continues | 0 | tag (k's low byte; the
+    // value byte of k lands in the neighbouring lane's low byte, which nobody reads)
+    uint32_t t = k * 256u + kFlagFix;
+    t += vmin2(py2, kSatB2) * 16u;
+    t += vmin2(px2, kSatA2) * 32u;
+    t += vmin2(py, kSatB) * 64u;
+    t += vmin2(px, kSatA) * 128u;
+    return t;
 }
 
 // One anti-diagonal step of a 16-column block.  `carry()` returns the previous-row values of the
@@ -218,50 +263,23 @@ KSW_HD void block_row(BlockState& b, const uint32_t S[8], CarryFn&& carry, Carry
 {
     // previous-row values of column 7 = left neighbours of column 8 (high lane of pair 0)
     const uint32_t x7 = b.X[7], v7 = b.V[7], x27 = b.X2[7];
-    uint32_t xl0 = 0, vl0 = 0, x2l0 = 0;
-    uint32_t kk[8];
+    uint32_t t[8];
 #pragma unroll
-    for (int j = 7; j >= 0; --j) {          // descending: pair j-1 still holds the previous row
-        if (j == 0) {
-            const Carry cin = carry();
-            xl0 = prmt(cin.xv, x7, 0x5410);        // lo = carried X (column -1), hi = X of column 7
-            vl0 = prmt(cin.xv, v7, 0x5432);        // lo = carried V, hi = V of column 7
-            x2l0 = prmt(cin.x2, x27, 0x5410);
+    for (int j = 7; j > 0; --j) {           // descending: pair j-1 still holds the previous row
+        t[j] = pair_row(b, j, S[j], b.X[j - 1], b.V[j - 1], b.X2[j - 1]);
+        if (j == 7) {
+            cout.xv = prmt(b.X[7], b.V[7], 0x7632);      // lo = PX[7].hi, hi = VC[7].hi  (column 15)
+            cout.x2 = b.X2[7] >> 16;
         }
-        const uint32_t x1 = j ? b.X[j - 1] : xl0;
-        const uint32_t v1 = j ? b.V[j - 1] : vl0;
-        const uint32_t x21 = j ? b.X2[j - 1] : x2l0;
-        const uint32_t u0 = b.U[j];
-        const uint32_t ka = vadd2(x1, vadd2(v1, kVa)), kb = vadd2(b.Y[j], vadd2(u0, kUa));
-        const uint32_t ka2 = vadd2(x21, vadd2(v1, kVb)), kb2 = vadd2(b.Y2[j], vadd2(u0, kUb));
-        uint32_t k = vmax3(S[j], ka, kb);
-        k = vmax3(k, ka2, kb2);
-        kk[j] = k;
-        const uint32_t zc = vmin2(k | 0x00FF00FFu, kClampZ);
-        const uint32_t nz = ~zc;
-        b.U[j] = vadd2(zc, ~v1);
-        b.V[j] = vadd2(zc, ~u0);
-        b.X[j] = vaddrelu(ka, vadd2(nz, kNZa));
-        b.Y[j] = vaddrelu(kb, vadd2(nz, kNZb));
-        b.X2[j] = vaddrelu(ka2, vadd2(nz, kNZa2));
-        b.Y2[j] = vaddrelu(kb2, vadd2(nz, kNZb2));
+        if (j & 1) continue;
+        tb[j >> 1] = prmt(t[j], t[j + 1], 0x7531);
     }
-    cout.xv = prmt(b.X[7], b.V[7], 0x7632);      // lo = X[7].hi, hi = V[7].hi  (column 15)
-    cout.x2 = b.X2[7] >> 16;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {           // 4 columns per instruction from here on
-        const int j = 2 * i;
-        const uint32_t pk = prmt(kk[j], kk[j + 1], 0x6420);              // tags, 0..4
-        const uint32_t fx = prmt(b.X[j], b.X[j + 1], 0x7531) + 0x7F7F7F7Fu;   // bit 7 of a byte = value != 0
-        const uint32_t fy = (prmt(b.Y[j], b.Y[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 1;
-        const uint32_t fx2 = (prmt(b.X2[j], b.X2[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 2;
-        const uint32_t fy2 = (prmt(b.Y2[j], b.Y2[j + 1], 0x7531) + 0x7F7F7F7Fu) >> 3;
-        uint32_t m = pk | (fx & 0x80808080u);
-        m |= fy & 0x40404040u;
-        m |= fx2 & 0x20202020u;
-        m |= fy2 & 0x10101010u;
-        tb[i] = m;
-    }
+    const Carry cin = carry();
+    const uint32_t xl0 = prmt(cin.xv, x7, 0x5410);        // lo = carried PX (column -1), hi = PX of column 7
+    const uint32_t vl0 = prmt(cin.xv, v7, 0x5432);        // lo = carried VC, hi = VC of column 7
+    const uint32_t x2l0 = prmt(cin.x2, x27, 0x5410);
+    t[0] = pair_row(b, 0, S[0], xl0, vl0, x2l0);
+    tb[0] = prmt(t[0], t[1], 0x7531);
 }
 
 // Backtrack state machine, one step (ksw_backtrack, ksw2.h:121-153, is_rot = 1, min_intron_len = 0).
@@ -310,33 +328,41 @@ struct ThreadCtx {
     uint32_t tword;        // 16 target bases of block myB, 2 bits each, column c at bits 2c
     uint32_t qlo, qhi;     // window into the packed reversed query: words qwi, qwi+1 of qrp
     int qwi;
-    int fast_lo, fast_hi;  // rows in which block myB lies strictly inside the band (fast path)
+    int fast_lo, fast_n;   // fast_n rows from fast_lo on, block myB lies strictly inside the band (fast path)
     int tb_off;            // byte offset of block myB inside a traceback row: 16 * (myB mod tb_blocks)
 };
 
 KSW_HD void thread_ctx_reset(ThreadCtx& c, int slot)
 {
     c.myB = -1; c.cand = slot; c.qwi = -0x7fffffff; c.tword = 0; c.qlo = c.qhi = 0;
-    c.fast_lo = 0; c.fast_hi = -1; c.tb_off = 0;
+    c.fast_lo = 0; c.fast_n = 0; c.tb_off = 0;
     c.b.init();
 }
+KSW_HD bool row_is_fast(const ThreadCtx& c, int r) { return (unsigned)(r - c.fast_lo) < (unsigned)c.fast_n; }
 
 // Where block B of a row is stored: the live window never spans more than tb_blocks blocks
 // (ksw2_extd2_sse.c:182 asserts the same), so B mod tb_blocks is collision-free within a row.
 KSW_HD int tb_block_slot(int B, int tb_blocks) { return B % tb_blocks; }
 
+// 16 bases of the reversed query under block B in row r: the index under column 0 is qlen-1-r+16B, it slides down
+// by one per row; the shift is the same for every block of the row.
 KSW_HD uint32_t query_window(ThreadCtx& c, const uint32_t* qrp, int qlen, int r, int B)
 {
-    // reversed-query index under column 0 of the block; it slides down by one per row
-    const int qbase = qlen - 1 - r + 16 * B;
-    const int wi = (qbase >> 4) + 1;        // arithmetic shift = floor; +1 skips the pad word
+    const int qrel = qlen - 1 - r;
+    const int wi = (qrel >> 4) + 1 + B;     // arithmetic shift = floor; +1 skips the pad word
     if (wi != c.qwi) {
         if (wi == c.qwi - 1) { c.qhi = c.qlo; c.qlo = qrp[wi]; }
         else { c.qlo = qrp[wi]; c.qhi = qrp[wi + 1]; }
         c.qwi = wi;
     }
-    return funnel_r(c.qlo, c.qhi, 2 * (qbase & 15));
+    return funnel_r(c.qlo, c.qhi, 2 * (qrel & 15));
 }
+
+#if defined(__CUDA_ARCH__)
+KSW_HD bool warp_all(bool p) { return __all_sync(0xFFFFFFFFu, p); }
+#else
+KSW_HD bool warp_all(bool p) { return p; }
+#endif
 
 // tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by
 // +1 (qrp[0] is a zero pad word so that index -1..-16 reads zeros).  `carry()` fetches what the
@@ -346,7 +372,11 @@ KSW_HD uint32_t query_window(ThreadCtx& c, const uint32_t* qrp, int qlen, int r,
 // kEager: the neighbour's value is already at hand (the previous row ended with a CTA barrier), so
 // `carry()` is evaluated up front and the band-edge cases overwrite it inside the slow path; the
 // block update then sees one plain value and no per-row policy select.
-template <bool kEager = false, class CarryFn>
+// kVote: the function is entered by whole warps.  A warp whose 32 blocks all lie strictly inside the band -- all
+// but the one or two warps at the band edges -- then skips everything that concerns the edges with ONE uniform
+// branch; the edge warps are the critical path of a row (every warp of the CTA waits for them at the row barrier),
+// so their extra work is kept short as well: geometry once per warp, the rare cases behind their own branches.
+template <bool kEager = false, bool kVote = true, class CarryFn>
 KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w, int tb_blocks,
                             const uint32_t* tp, const uint32_t* qrp,
                             CarryFn&& carry, Carry& cout, uint32_t tb[4])
@@ -358,61 +388,71 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
     int policy = 0;
     uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
     bool pre_block = false;
-    // fast path: the block is strictly inside the band, nothing about the band edges matters
-    if (r < c.fast_lo || r > c.fast_hi) {
+    const bool fast = row_is_fast(c, r);
+    if (!(kVote ? warp_all(fast) : fast)) {
         const RowGeom g = row_geom(r, qlen, tlen, w);
-        const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
-        while (c.cand < bst) c.cand += nt;  // the band left this thread's block behind: take the next one
-        const int B = c.cand;
-        if (B > bwr) return false;
-        if (B != c.myB) {                   // take ownership of a new block
-            c.myB = B;
-            c.b.init();
-            c.tword = tp[B];
-            c.qwi = -0x7fffffff;
-            c.tb_off = 16 * tb_block_slot(B, tb_blocks);
-            // rows with st0 <= 16B-1 (so block B-1 was live one row earlier) and en0 >= 16B+15:
-            //   en0 = min(tlen-1, r, (r+w)>>1) >= c15  <=>  r >= max(c15, 2*c15 - w)   (c15 <= tlen-1);
-            //   row c15 itself still gets the top-row reset of column c15 below, so start one row later
-            //   st0 = max(0, r-qlen+1, (r-w+1)>>1) <= c0-1  <=>  r <= min(c0+qlen-2, 2*(c0-1)+w)
-            const int c0 = 16 * B, c15 = c0 + 15;
-            c.fast_lo = 0; c.fast_hi = -1;
-            if (B > 0 && c15 <= tlen - 1) {
-                const int lo = c15 + 1 > 2 * c15 - w ? c15 + 1 : 2 * c15 - w;
-                const int h1 = c0 + qlen - 2, h2 = 2 * (c0 - 1) + w;
-                c.fast_lo = lo; c.fast_hi = h1 < h2 ? h1 : h2;
+        if (!fast) {
+            const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
+            // leaving the fast stretch: the score bits were not tracked there (every column was fresh every row)
+            if (c.fast_n > 0 && r == c.fast_lo + c.fast_n)
+                c.b.sbits = mismatch_bits(c.tword, query_window(c, qrp, qlen, r - 1, c.myB));
+            while (c.cand < bst) c.cand += nt;  // the band left this thread's block behind: take the next one
+            const int B = c.cand;
+            if (B > bwr) return false;
+            if (B != c.myB) {                   // take ownership of a new block
+                c.myB = B;
+                c.b.init();
+                c.tword = tp[B];
+                c.qwi = -0x7fffffff;
+                c.tb_off = 16 * tb_block_slot(B, tb_blocks);
+                // rows with st0 <= 16B-1 (so block B-1 was live one row earlier) and en0 >= 16B+15:
+                //   en0 = min(tlen-1, r, (r+w)>>1) >= c15  <=>  r >= max(c15, 2*c15 - w)   (c15 <= tlen-1);
+                //   row c15 itself still gets the top-row reset of column c15 below, so start one row later
+                //   st0 = max(0, r-qlen+1, (r-w+1)>>1) <= c0-1  <=>  r <= min(c0+qlen-2, 2*(c0-1)+w)
+                const int c0 = 16 * B, c15 = c0 + 15;
+                c.fast_lo = 0; c.fast_n = 0;
+                if (B > 0 && c15 <= tlen - 1) {
+                    const int lo = c15 + 1 > 2 * c15 - w ? c15 + 1 : 2 * c15 - w;
+                    const int h1 = c0 + qlen - 2, h2 = 2 * (c0 - 1) + w;
+                    const int hi = h1 < h2 ? h1 : h2;
+                    c.fast_lo = lo; c.fast_n = hi >= lo ? hi - lo + 1 : 0;
+                }
             }
-        }
-        const int c0 = 16 * B;
-        // fresh columns: st0 <= c0 + col <= wr
-        int lo = g.st0 - c0, hi = g.wr - c0;
-        lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
-        fm = lo <= hi ? (0xFFFFFFFFu >> (30 - 2 * hi)) & (0xFFFFFFFFu << (2 * lo)) : 0u;
-        pre_block = B > ben;                // pre-block: only its score bytes exist so far
-        if (!pre_block) {
-            if ((r >> 4) == B) {            // top row of the matrix reaches column r: :152-155
-                const int col = r & 15, j = col & 7;
-                const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
-                const uint32_t uv = dup(256 * first_gap_diff(r) + kLUV);
+            const int c0 = 16 * B;
+            // fresh columns: st0 <= c0 + col <= wr
+            int lo = g.st0 - c0, hi = g.wr - c0;
+            lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
+            fm = lo <= hi ? (0xFFFFFFFFu >> (30 - 2 * hi)) & (0xFFFFFFFFu << (2 * lo)) : 0u;
+            pre_block = B > ben;                // pre-block: only its score bytes exist so far
+            if (!pre_block) {
+                if ((r >> 4) == B) {            // top row of the matrix reaches column r: :152-155
+                    const int col = r & 15, j = col & 7;
+                    const uint32_t m = col < 8 ? 0x0000FFFFu : 0xFFFF0000u;
+                    const uint32_t uv = dup(256 * (first_gap_diff(r) - kQE));
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    if (jj == j) {
-                        c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
-                        c.b.Y[jj] &= ~m;    // y = -(q+e), y2 = -(q2+e2)
-                        c.b.Y2[jj] &= ~m;
-                    }
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (jj == j) {
+                            c.b.U[jj] = (c.b.U[jj] & ~m) | (uv & m);
+                            c.b.Y[jj] = (c.b.Y[jj] & ~m) | (kReluB & m);      // y = -(q+e), y2 = -(q2+e2)
+                            c.b.Y2[jj] = (c.b.Y2[jj] & ~m) | (kReluB2 & m);
+                        }
+                }
+                // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
+                if (B == 0) policy = 1;
+                else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
+                if (kEager && policy) eager = policy == 1 ? carry_left_boundary(r) : carry_init();
             }
-            // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
-            if (B == 0) policy = 1;
-            else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
-            if (kEager && policy) eager = policy == 1 ? carry_left_boundary(r) : carry_init();
         }
     }
     const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
-    c.b.sbits = (mismatch_bits(c.tword, qword) & fm) | (c.b.sbits & ~fm);
-    if (pre_block) return false;
+    const uint32_t x = c.tword ^ qword;
+    uint32_t sb = x | (x >> 1);                // mismatch of column c at bit 2c (odd bits: don't care)
+    if (!fast) {
+        sb = c.b.sbits = (sb & 0x55555555u & fm) | (c.b.sbits & ~fm);
+        if (pre_block) return false;
+    }
     uint32_t S[8];
-    score_lanes(c.b.sbits, S);
+    score_lanes(sb, fast, S);
     if (kEager) block_row(c.b, S, [&]() -> Carry { return eager; }, cout, tb);
     else
         block_row(c.b, S, [&]() -> Carry {

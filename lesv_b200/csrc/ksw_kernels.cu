@@ -338,40 +338,12 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// kSync selects how a row's "column 15 of my left neighbour, one row earlier" dependency is honoured
-// across warps:  kSyncBar  = one CTA barrier per anti-diagonal;
-//                kSyncMbar = split-phase barrier on two mbarriers: a warp ARRIVES when its row is
-//                            done and only WAITS (hardware sleep, no polling) right before it needs
-//                            the neighbour's value in the next row, so the tail of row r overlaps
-//                            the head of row r+1;
-//                kSyncRing = tagged slots polled by the consumer (what clusters use across CTAs).
-//                kSyncSkew = the 32-block group g of the band runs kSkewK rows BEHIND group g-1, so
-//                            the carry a warp needs was published at least one barrier ago: warps
-//                            exchange column-15 values through a ring of 4*kSkewK slots and meet at
-//                            a CTA barrier only every kSkewK rows (tests/emul runs this schedule
-//                            with the warps of an interval in random order).
-enum { kSyncRing = 0, kSyncBar = 1, kSyncMbar = 2, kSyncSkew = 3 };
-constexpr int kSkewMaxK = 16;
-
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t addr)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_LOOP;\n\t}" ::"r"(addr), "r"(parity) : "memory");
-}
-
-template <bool kCluster, int kSync, int kSkewK = 8, int kBound = kMaxNT>
-__global__ void __launch_bounds__(kBound)
+// kCluster = false: one CTA per alignment, one CTA barrier per anti-diagonal (waiting warps sleep; a polled ring was
+//                   measured slower here: polling lanes burn issue slots of the SMSPs that are the bottleneck).
+// kCluster = true:  one alignment on a thread-block cluster; inside a CTA and across CTAs the carries go through the
+//                   tagged slots described above (no barrier spans CTAs cheaply).
+template <bool kCluster>
+__global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
               const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
               const size_t* __restrict__ arena_off,
@@ -381,11 +353,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     extern __shared__ uint32_t seq_s[];
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
-    __shared__ __align__(8) uint64_t row_bar[2];
-    __shared__ uint2 carry_sh[2][kMaxWarps];      // kSyncBar: column-15 values by row parity and consumer warp
-    __shared__ uint2 cl_ring[kSync == kSyncSkew && kCluster ? 4 * kSkewK : 1];   // cluster skew: filled by the CTA to my left
-    __shared__ uint2 skew_ring[kSync == kSyncSkew ? kMaxWarps : 1][kSync == kSyncSkew ? 4 * kSkewK : 1];
-    constexpr bool kBarrier = kSync != kSyncRing;       // slots need no tags / flow control
+    __shared__ uint2 carry_sh[2][kMaxWarps];      // barrier mode: column-15 values by row parity and consumer warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Programmatic dependent launch: the launch classes of a batch are chained in one stream, each allowed to start
     // as soon as every CTA of the class before it is resident (lesvgpu.cu: run_jobs).  Nothing is waited for.
@@ -420,140 +388,27 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         uint32_t* qrp_s = seq_s + ntw;
         for (int x = tid; x < ntw; x += blockDim.x) tp_s[x] = pool[job.tp_off + x];
         for (int x = tid; x < nqw; x += blockDim.x) qrp_s[x] = pool[job.qrp_off + x];
-        for (int x = tid; x < kMaxWarps * kRingD; x += blockDim.x) ps.inbox[x / kRingD][x % kRingD].tag = 0xFFFFFFFFu;
-        if (tid < kMaxWarps) ps.consumed[tid] = 0;
-        if (tid == 0) ps.right_consumed = 0;
+        if (kCluster) {
+            for (int x = tid; x < kMaxWarps * kRingD; x += blockDim.x) ps.inbox[x / kRingD][x % kRingD].tag = 0xFFFFFFFFu;
+            if (tid < kMaxWarps) ps.consumed[tid] = 0;
+            if (tid == 0) ps.right_consumed = 0;
+        }
         __syncthreads();
         if (kCluster) cluster_sync_all();          // every CTA's ring is reset before anyone publishes
 
         // this alignment uses the first NT threads of every CTA (the launch is sized for its tier)
         const int NT = job.nt, NW = NT >> 5, NTT = NT * (int)ncta;
-        if (kSync == kSyncMbar) {
-            if (tid == 0) {
-                mbar_init(smem_addr(&row_bar[0]), (uint32_t)NW);
-                mbar_init(smem_addr(&row_bar[1]), (uint32_t)NW);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
-            __syncthreads();
-        }
-        // ring endpoints of this thread (only lane 0 / lane 31 use them): my warp's inbox and where
-        // my consumed-rows counter lives; the inbox I publish into and the counter I watch
-        uint32_t in_addr = smem_addr(&ps.inbox[warp][0]);
-        uint32_t cons_addr = smem_addr(&ps.consumed[warp]);
-        uint32_t out_addr = smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]);
-        uint32_t watch_addr = smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]);
-        if (kCluster) {
-            in_addr = map_rank(in_addr, rank);
-            cons_addr = map_rank(cons_addr, rank);
-            out_addr = map_rank(out_addr, rank);
-            watch_addr = map_rank(watch_addr, rank);
-            if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
-            if (warp == NW - 1) {
-                out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
-                watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
-            }
-        }
         ThreadCtx c;
         thread_ctx_reset(c, (int)rank * NT + tid);
         Carry prev_out = carry_init();
-        const int nrow = (kSync == kSyncBar || warp < NW) ? qlen + tlen - 1 : 0;   // warps beyond NT sit this alignment out
         const size_t prow = (size_t)tb_blocks * 16;
-        if (kSync == kSyncSkew && kCluster) {
-            // Cluster flavour of the skewed schedule: the groups are the CTAs.  Inside a CTA the lean
-            // barrier loop (one __syncthreads per tick); CTA k+1 works kSkewK rows behind CTA k, takes
-            // its left-edge carries from a ring the last warp of CTA k fills through DSMEM, and the
-            // cluster meets at a hardware cluster barrier only every kSkewK ticks.
-            constexpr int R = 4 * kSkewK;
-            const int maxB = ((tlen - 1) >> 4) + 1;
-            const int nrow_all = qlen + tlen - 1;
-            const int nticks = nrow_all + kSkewK * (maxB / NT);
-            const uint32_t ring_remote = map_rank(smem_addr(&cl_ring[0]), (rank + 1) % ncta);
-            int r = -kSkewK * (c.cand / NT);
-            for (int s = 0; s < nticks; ++s, ++r) {
-                if (warp < NW) {
-                    const uint2 nb = carry_sh[(s + 1) & 1][warp];
-                    Carry cin;
-                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                    if (r < c.fast_lo || r > c.fast_hi)
-                        while (c.cand <= maxB &&
-                               (r >= nrow_all || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
-                            c.cand += NTT;
-                            r = s - kSkewK * (c.cand / NT);
-                        }
-                    if (lane == 0) {
-                        if (warp == 0) {
-                            const volatile uint2* rp = &cl_ring[(r - 1) & (R - 1)];
-                            cin.xv = rp->x; cin.x2 = rp->y;
-                        } else { cin.xv = nb.x; cin.x2 = nb.y; }
-                    }
-                    bool did = false;
-                    Carry cout;
-                    uint32_t tb[4];
-                    if (r >= 0 && r < nrow_all && c.cand <= maxB)
-                        did = thread_row_step<true>(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                                    [&]() -> Carry { return cin; }, cout, tb);
-                    if (did) {
-                        *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
-                            make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                        prev_out = cout;
-                    }
-                    if (lane == 31) {
-                        if (warp == NW - 1) {
-                            if (did)
-                                asm volatile("st.volatile.shared::cluster.v2.u32 [%0], {%1, %2};" ::
-                                             "r"(ring_remote + (uint32_t)(r & (R - 1)) * 8u), "r"(cout.xv), "r"(cout.x2) : "memory");
-                        } else carry_sh[s & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
-                    }
-                }
-                __syncthreads();
-                if ((s & (kSkewK - 1)) == kSkewK - 1) cluster_sync_all();
-            }
-        } else if (kSync == kSyncSkew) {
-            constexpr int R = 4 * kSkewK;
-            const int maxB = ((tlen - 1) >> 4) + 1;              // right-most block that ever exists
-            const int nrow_all = qlen + tlen - 1;
-            const int nticks = nrow_all + kSkewK * (maxB >> 5);
-            const uint2* inbox = skew_ring[warp < NW ? warp : 0];
-            uint2* outbox = skew_ring[warp + 1 < NW ? warp + 1 : 0];
-            int r = -kSkewK * (c.cand >> 5);                     // this thread's anti-diagonal at tick 0
-            for (int s = 0; s < nticks; ++s, ++r) {
-                Carry cin;
-                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                if (warp < NW) {
-                    if (r < c.fast_lo || r > c.fast_hi)          // the band left my block behind: take the next one
-                        while (c.cand <= maxB &&
-                               (r >= nrow_all || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
-                            c.cand += NT;
-                            r = s - kSkewK * (c.cand >> 5);
-                        }
-                    if (r >= 0 && r < nrow_all && c.cand <= maxB) {
-                        Carry cout;
-                        uint32_t tb[4];
-                        const int rc = r;
-                        if (thread_row_step(c, NT, rc, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                            [&]() -> Carry {
-                                                if (lane) return cin;
-                                                const uint2 v = inbox[(rc - 1) & (R - 1)];
-                                                Carry x; x.xv = v.x; x.x2 = v.y; return x;
-                                            }, cout, tb)) {
-                            *reinterpret_cast<uint4*>(arena + (size_t)rc * prow + (size_t)c.tb_off) =
-                                make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                            prev_out = cout;
-                            if (lane == 31) outbox[rc & (R - 1)] = make_uint2(cout.xv, cout.x2);
-                        }
-                    }
-                }
-                if ((s & (kSkewK - 1)) == kSkewK - 1) __syncthreads();
-            }
-        } else if (kSync == kSyncBar && !kCluster) {
+        const int nrow_all = qlen + tlen - 1;
+        if (!kCluster) {
             // Lean barrier loop: lane 31 leaves its column-15 values in carry_sh[row parity][next warp],
             // every lane of the next warp reads them back (one broadcast LDS) at the top of the next
             // row and lane 0 keeps them -- no divergent single-lane fetch in front of pair 0.
             const int wnext = warp + 1 < NW ? warp + 1 : 0;
             uint8_t* rowp = arena;
-            const int nrow_all = qlen + tlen - 1;
             for (int r = 0; r < nrow_all; ++r, rowp += prow) {
                 if (warp < NW) {
                     const uint2 nb = carry_sh[(r + 1) & 1][warp];
@@ -572,45 +427,50 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                 }
                 __syncthreads();
             }
-        } else
-        for (int r = 0; r < nrow; ++r) {
-            Carry cin;
-            cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-            cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-            bool fetched = false;
-            auto consume = [&]() -> Carry {        // lane 0: take row r-1 out of the inbox
-                Carry v = carry_init();
-                fetched = true;
-                if (r == 0) return v;
-                const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                if (kSync == kSyncMbar)      // every warp has finished row r-1 once this phase completes
-                    mbar_wait(smem_addr(&row_bar[(r - 1) & 1]), (uint32_t)(((r - 1) >> 1) & 1));
-                if (kBarrier) { ld_slot<kCluster>(slot, v.xv, v.x2); return v; }
-                while (ld_slot<kCluster>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
-                st_word<kCluster>(cons_addr, (uint32_t)r);
-                return v;
-            };
-            Carry cout;
-            uint32_t tb[4];
-            const bool did = warp < NW &&
-                             thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                             [&]() -> Carry { return lane == 0 ? consume() : cin; }, cout, tb);
-            if (did) {
-                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
-                    make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                prev_out = cout;
+        } else {
+            // ring endpoints of this thread (only lane 0 / lane 31 use them): my warp's inbox and where
+            // my consumed-rows counter lives; the inbox I publish into and the counter I watch
+            uint32_t in_addr = map_rank(smem_addr(&ps.inbox[warp][0]), rank);
+            uint32_t cons_addr = map_rank(smem_addr(&ps.consumed[warp]), rank);
+            uint32_t out_addr = map_rank(smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]), rank);
+            uint32_t watch_addr = map_rank(smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]), rank);
+            if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
+            if (warp == NW - 1) {
+                out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
+                watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
             }
-            if (kSync != kSyncBar && lane == 0 && !fetched) consume();  // flow control only
-            if (lane == 31 && warp < NW) {                             // publish row r
-                if (!kBarrier && r >= kRingD)
-                    while ((int)ld_word<kCluster>(watch_addr) < r - kRingD + 1) { }
-                const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                st_slot<kCluster>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
-            }
-            if (kSync == kSyncBar) __syncthreads();
-            else {
+            const int nrow = warp < NW ? nrow_all : 0;       // warps beyond NT sit this alignment out
+            for (int r = 0; r < nrow; ++r) {
+                Carry cin;
+                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                bool fetched = false;
+                auto consume = [&]() -> Carry {        // lane 0: take row r-1 out of the inbox
+                    Carry v = carry_init();
+                    fetched = true;
+                    if (r == 0) return v;
+                    const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                    while (ld_slot<true>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
+                    st_word<true>(cons_addr, (uint32_t)r);
+                    return v;
+                };
+                Carry cout;
+                uint32_t tb[4];
+                const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                                 [&]() -> Carry { return lane == 0 ? consume() : cin; }, cout, tb);
+                if (did) {
+                    *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
+                        make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                    prev_out = cout;
+                }
+                if (lane == 0 && !fetched) consume();                      // flow control only
+                if (lane == 31) {                                          // publish row r
+                    if (r >= kRingD)
+                        while ((int)ld_word<true>(watch_addr) < r - kRingD + 1) { }
+                    const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                    st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
+                }
                 __syncwarp();
-                if (kSync == kSyncMbar && lane == 0) mbar_arrive(smem_addr(&row_bar[r & 1]));
             }
         }
         __syncthreads();
@@ -981,8 +841,8 @@ ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ orde
                 Carry cin; cin.xv = pv.x; cin.x2 = pv.y;
                 Carry cout;
                 uint32_t tb[4];
-                if (thread_row_step(c, nslot, r, qlen, tlen, w, job.tb_blocks, tp_s, qrp_s,
-                                    [&]() -> Carry { return cin; }, cout, tb)) {
+                if (thread_row_step<false, false>(c, nslot, r, qlen, tlen, w, job.tb_blocks, tp_s, qrp_s,
+                                                  [&]() -> Carry { return cin; }, cout, tb)) {
                     *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
                         make_uint4(tb[0], tb[1], tb[2], tb[3]);
                     pub_r[sidx] = make_uint2(cout.xv, cout.x2);
@@ -1024,19 +884,8 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 // 88 registers per thread (ptxas: 86) -> 744 threads per SM
 int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 23 ? 23 : n; }
 
-// Cluster alignments: polled tagged-slot ring (551 GCUPS on 2-CTA clusters); LESV_KSW_CLUSTER_SKEW=1
-// selects skewed CTAs with a cluster barrier every LESV_KSW_SKEW rows (measured 517-549 GCUPS).
 using KswKernelFn = void (*)(const KswJob*, const int*, int, const uint32_t*, uint8_t*, const size_t*, uint32_t*,
                              KswGapRun*, KswOut*, int*);
-static KswKernelFn cluster_kernel()
-{
-    static const bool ring = getenv("LESV_KSW_CLUSTER_SKEW") == nullptr;
-    static const int k = getenv("LESV_KSW_SKEW") ? atoi(getenv("LESV_KSW_SKEW")) : 8;
-    if (ring) return ksw_dp_kernel<true, kSyncRing>;
-    if (k <= 4) return ksw_dp_kernel<true, kSyncSkew, 4>;
-    if (k <= 8) return ksw_dp_kernel<true, kSyncSkew, 8>;
-    return ksw_dp_kernel<true, kSyncSkew, 16>;
-}
 
 cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJob* d_jobs, const int* d_order,
                        int njobs, const uint32_t* d_pool, uint8_t* d_arena, const size_t* arena_stride, uint32_t* d_cigar,
@@ -1044,76 +893,34 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 {
     // after_resident: programmatic stream serialization -- this launch may start once all CTAs of the previous
     // kernel in the stream have executed griddepcontrol.launch_dependents (i.e. are resident), not when it ends.
-    cudaLaunchAttribute pdl[2];
-    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl[0].val.programmaticStreamSerializationAllowed = after_resident ? 1 : 0;
-    // Single-CTA alignments synchronise once per anti-diagonal with a CTA barrier (waiting warps
-    // sleep); the tagged-slot ring is what clusters need (no barrier spans CTAs cheaply) and can be
-    // forced for single CTAs with LESV_KSW_RING=1 -- measured slower there: polling lanes burn issue
-    // slots of the ALU-bound SMSPs (profiles/ksw_r1_notes.md).
-    static const int sync_mode = getenv("LESV_KSW_SYNC") ? atoi(getenv("LESV_KSW_SYNC")) : kSyncBar;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = after_resident ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
     if (ncta <= 1) {
-#define LESV_LAUNCH1(MODE)                                                                                         \
-    do {                                                                                                           \
-        cudaFuncSetAttribute(ksw_dp_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        cudaLaunchConfig_t c1 = {};                                                                                \
-        c1.gridDim = dim3((unsigned)n_clusters); c1.blockDim = dim3((unsigned)nt); c1.dynamicSmemBytes = smem;     \
-        c1.stream = s; c1.attrs = pdl; c1.numAttrs = 1;                                                            \
-        cudaError_t e1 = cudaLaunchKernelEx(&c1, ksw_dp_kernel<false, MODE>, d_jobs, d_order, njobs, d_pool, d_arena, \
-                                            arena_stride, d_cigar, d_runs, d_out, d_counter);                      \
-        if (e1 != cudaSuccess) return e1;                                                                          \
-    } while (0)
-        static const int skew_k = getenv("LESV_KSW_SKEW") ? atoi(getenv("LESV_KSW_SKEW")) : 8;
-        if (sync_mode == kSyncSkew) {
-#define LESV_LAUNCHS(KK)                                                                                              \
-    do {                                                                                                              \
-        cudaFuncSetAttribute(ksw_dp_kernel<false, kSyncSkew, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        ksw_dp_kernel<false, kSyncSkew, KK><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,    \
-                                                                         arena_stride, d_cigar, d_runs, d_out, d_counter); \
-    } while (0)
-            if (skew_k <= 2) LESV_LAUNCHS(2);
-            else if (skew_k <= 4) LESV_LAUNCHS(4);
-            else if (skew_k <= 8) LESV_LAUNCHS(8);
-            else LESV_LAUNCHS(16);
-#undef LESV_LAUNCHS
-        }
-        else if (sync_mode == kSyncMbar) LESV_LAUNCH1(kSyncMbar);
-        else if (sync_mode == kSyncRing) LESV_LAUNCH1(kSyncRing);
-        else if (nt <= 512 && getenv("LESV_KSW_512")) {     // measured slower (717 vs 745 GCUPS): off by default
-            // CTAs of <= 512 threads may use 128 registers per thread: room for the scheduler to
-            // interleave the eight independent pair updates of a row
-            cudaFuncSetAttribute(ksw_dp_kernel<false, kSyncBar, 8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            ksw_dp_kernel<false, kSyncBar, 8, 512><<<n_clusters, nt, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena,
-                                                                                  arena_stride, d_cigar, d_runs, d_out, d_counter);
-        }
-        else if (nt >= 320 && 2 * smem <= 200 * 1024 && !getenv("LESV_KSW_NO_OVERLAP")) {
+        cfg.gridDim = dim3((unsigned)n_clusters);
+        if (nt >= 320 && 2 * smem <= 200 * 1024) {
             // DP of alignment m overlapped with the traceback walk of alignment m-1 (one extra warp)
             cudaFuncSetAttribute(ksw_dp_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
-            cudaLaunchConfig_t c1 = {};
-            c1.gridDim = dim3((unsigned)n_clusters); c1.blockDim = dim3((unsigned)nt + 32); c1.dynamicSmemBytes = 2 * smem;
-            c1.stream = s; c1.attrs = pdl; c1.numAttrs = 1;
-            cudaError_t e1 = cudaLaunchKernelEx(&c1, ksw_dp_overlap_kernel, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
-                                                (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
-            if (e1 != cudaSuccess) return e1;
+            cfg.blockDim = dim3((unsigned)nt + 32); cfg.dynamicSmemBytes = 2 * smem;
+            return cudaLaunchKernelEx(&cfg, ksw_dp_overlap_kernel, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                      (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
         }
-        else LESV_LAUNCH1(kSyncBar);
-#undef LESV_LAUNCH1
-        return cudaGetLastError();
+        cudaFuncSetAttribute(ksw_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
+        return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<false>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+                                  d_cigar, d_runs, d_out, d_counter);
     }
-    auto kern = cluster_kernel();
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaLaunchConfig_t cfg = {};
+    cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
     cfg.blockDim = dim3((unsigned)nt);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1] = pdl[0];
-    cfg.attrs = at; cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)ncta; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<true>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                               d_cigar, d_runs, d_out, d_counter);
 }
 
@@ -1131,7 +938,7 @@ cudaError_t launch_ksw_strips(int n_ctas, size_t smem, const KswJob* d_jobs, con
 int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
-    auto kern = cluster_kernel();
+    KswKernelFn kern = ksw_dp_kernel<true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};

@@ -165,10 +165,6 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
         static const int tiers[] = {32, 64, 96, 128, 160, 320, 512, 640};
-        static const int split2 = getenv("LESV_KSW_SPLIT2") ? atoi(getenv("LESV_KSW_SPLIT2")) : 0;
-        // experiment: alignments of 321..640 blocks as 2-CTA clusters of <= 320 threads, two CTAs (of different
-        // alignments) per SM, so one CTA's row barrier overlaps the other's arithmetic
-        if (split2 && wb > split2 && wb <= 640) return {2, 320, ((wb + 1) / 2 + 31) / 32 * 32};
         if (wb <= 640) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};

@@ -109,7 +109,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
                         const int tid = wp * G + l;
                         ThreadCtx& c = th[tid];
                         int& r = rr[tid];
-                        if (r < c.fast_lo || r > c.fast_hi)
+                        if (!row_is_fast(c, r))
                             while (c.cand <= maxB && (r >= (int)nrow || (r >= 0 && c.cand < (row_geom(r, qlen, tlen, w).st0 >> 4)))) {
                                 c.cand += nt; r = s - K * (c.cand / G);
                             }
