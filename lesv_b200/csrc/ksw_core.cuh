@@ -155,6 +155,16 @@ KSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
 }
 #endif
 
+// A constant the compiler must keep in a register: ptxas otherwise re-materialises the register operands of
+// VIADDMNMX (it takes one immediate only) with a MOV / PRMT per use inside the block update.
+KSW_HD uint32_t reg_const(uint32_t v)
+{
+#if defined(__CUDA_ARCH__) && defined(KSW_REG_CONST)
+    asm volatile("" : "+r"(v));
+#endif
+    return v;
+}
+
 // ---- internal traceback byte -------------------------------------------------------------------
 // bits 0-2: 4 - winner (winner 0 H, 1 E, 2 F, 3 E~, 4 F~); bit 7: E continues; bit 6: F continues;
 // bit 5: E~ continues; bit 4: F~ continues; bit 3: 0.  (The reference's own layout, ksw2.h:117-120,
@@ -172,8 +182,10 @@ struct BlockState {
     // 2c+1: never written) and rebuilds the S lanes of a row from them.  Stale bytes (columns of the
     // 16-aligned band outside [st0, wr]) are simply bits that were not refreshed.
     uint32_t sbits;
+    uint32_t kwk, kzero;                                    // kWK and kReluB2 held in registers (reg_const)
     KSW_HD void init()
     {
+        kwk = reg_const(kWK); kzero = reg_const(kReluB2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             U[j] = kInitUV; V[j] = kInitUV; X[j] = kReluA; Y[j] = kReluB;
@@ -236,12 +248,12 @@ KSW_HD uint32_t pair_row(BlockState& b, int j, uint32_t s, uint32_t x1, uint32_t
     const uint32_t ka = vadd2(x1, v1), kb = vadd2(b.Y[j], u0);
     const uint32_t ka2 = vadd2(x21, vadd2(v1, kD2)), kb2 = vadd2(b.Y2[j], vadd2(u0, kD2));
     const uint32_t k = vmax3(vmax3(s, ka, kb), ka2, kb2);
-    const uint32_t w = vaddmin(k | 0x00FF00FFu, kWK, kWClamp);
+    const uint32_t w = vaddmin(k | 0x00FF00FFu, b.kwk, kWClamp);
     const uint32_t n = vadd2(~w, kNQ), n2 = vadd2(n, kNQ2);
     b.U[j] = vadd2(w, ~v1);
     b.V[j] = vadd2(w, ~u0);
     const uint32_t px = vaddmax(ka, n, kReluA), py = vaddmax(kb, n, kReluB);
-    const uint32_t px2 = vaddmax(ka2, n2, kReluA2), py2 = vaddmax(kb2, n2, kReluB2);
+    const uint32_t px2 = vaddmax(ka2, n2, kReluA2), py2 = vaddmax(kb2, n2, b.kzero);
     b.X[j] = px; b.Y[j] = py; b.X2[j] = px2; b.Y2[j] = py2;
     // high byte of a lane: E continues | F continues | E~ continues | F~ continues | 0 | tag (k's low byte; the
     // value byte of k lands in the neighbouring lane's low byte, which nobody reads)

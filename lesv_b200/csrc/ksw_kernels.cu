@@ -494,9 +494,13 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
 // follows it.  The DP warps check every 256 rows that this is really so (the walker publishes the row it still
 // needs) and the packed sequences are double-buffered in shared memory.  The DP warps synchronise on named
 // barrier 1, the walker takes part in nothing.
+#ifndef KSW_WALK_SLEEP_NS
+#define KSW_WALK_SLEEP_NS 4000      // the walker's poll for the next alignment shares a scheduler with DP warps: poll rarely
+#endif
 __device__ __forceinline__ void bar_dp(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(kMaxNT + 32)
+template <int kTier>                                    // CTA = kTier DP threads + the walker warp: fixes the register budget
+__global__ void __launch_bounds__(kTier + 32, kTier <= kTierLow ? 2 : 1)
 ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
                       const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
                       const size_t* __restrict__ arena_off /* n_ctas + 1 entries */, uint32_t half_words,
@@ -523,7 +527,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         for (int n = 0;; ++n) {
             int fin = 0;
             if (lane == 0) {
-                while (wk_posted <= n && !wk_finished) __nanosleep(200);
+                while (wk_posted <= n && !wk_finished) __nanosleep(KSW_WALK_SLEEP_NS);
                 fin = wk_posted <= n;
             }
             fin = __shfl_sync(0xFFFFFFFFu, fin, 0);
@@ -881,8 +885,8 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
     return (size_t)(tp_words(max_tlen) + qrp_words(max_qlen)) * sizeof(uint32_t);
 }
 
-// 88 registers per thread (ptxas: 86) -> 744 threads per SM
-int ksw_ctas_per_sm(int nt) { int n = 744 / nt; return n < 1 ? 1 : n > 23 ? 23 : n; }
+// <= 96 registers per thread -> 680 threads per SM
+int ksw_ctas_per_sm(int nt) { int n = 680 / nt; return n < 1 ? 1 : n > 23 ? 23 : n; }
 
 using KswKernelFn = void (*)(const KswJob*, const int*, int, const uint32_t*, uint8_t*, const size_t*, uint32_t*,
                              KswGapRun*, KswOut*, int*);
@@ -900,11 +904,16 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
     if (ncta <= 1) {
         cfg.gridDim = dim3((unsigned)n_clusters);
-        if (nt >= 320 && 2 * smem <= 200 * 1024) {
+        if (nt >= kTierLow && 2 * smem <= 200 * 1024) {
             // DP of alignment m overlapped with the traceback walk of alignment m-1 (one extra warp)
-            cudaFuncSetAttribute(ksw_dp_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+#ifdef KSW_ONE_TIER
+            auto kern = ksw_dp_overlap_kernel<kTierTop>;
+#else
+            auto kern = nt <= kTierLow ? ksw_dp_overlap_kernel<kTierLow> : nt <= kTierMid ? ksw_dp_overlap_kernel<kTierMid> : ksw_dp_overlap_kernel<kTierTop>;
+#endif
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
             cfg.blockDim = dim3((unsigned)nt + 32); cfg.dynamicSmemBytes = 2 * smem;
-            return cudaLaunchKernelEx(&cfg, ksw_dp_overlap_kernel, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
+            return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                       (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
         }
         cudaFuncSetAttribute(ksw_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

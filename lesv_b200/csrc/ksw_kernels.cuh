@@ -54,6 +54,15 @@ struct KswOut {
 __host__ __device__ static inline uint32_t tp_words(int tlen) { return (uint32_t)(tlen >> 4) + 4; }
 __host__ __device__ static inline uint32_t qrp_words(int qlen) { return (uint32_t)(qlen >> 4) + 7; }
 
+// CTA sizes of the single-CTA launch classes.  The three largest run ksw_dp_overlap_kernel, whose CTA is the tier plus
+// one walker warp: 352 / 512 / 640 threads = 11 / 16 / 20 warps, i.e. whole multiples of the four schedulers for the two
+// big ones (4 and 5 warps each; 96 registers per thread fit 5 warps per scheduler, 80 would be the limit with 6).
+#ifndef KSW_TIER_MID
+#define KSW_TIER_MID 480
+#define KSW_TIER_TOP 608
+#endif
+constexpr int kTierLow = 320, kTierMid = KSW_TIER_MID, kTierTop = KSW_TIER_TOP;
+
 // largest band window (in 16-column blocks) the register-resident kernel with NT threads holds
 __host__ __device__ static inline int window_blocks(int tlen, int w)
 {

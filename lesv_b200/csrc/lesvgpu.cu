@@ -164,8 +164,8 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     // alignment actually uses of it.
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
-        static const int tiers[] = {32, 64, 96, 128, 160, 320, 512, 640};
-        if (wb <= 640) {
+        static const int tiers[] = {32, 64, 96, 128, 160, kTierLow, kTierMid, kTierTop};
+        if (wb <= kTierTop) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};
         }
@@ -191,6 +191,15 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     std::vector<int> strip_ids;
     std::vector<char> is_strip(nj, 0);
     size_t strip_arena = 0;
+    // what the arena may grow to right now: the configured limit, but never more than 90 % of what is free
+    // (the subject, the index and the mapper's buffers live on the same device; other processes may, too)
+    size_t arena_limit = ctx->arena_limit;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            arena_limit = std::min(arena_limit, (size_t)((free_b + ctx->d_arena.cap) * 0.90));
+    }
+    const size_t strip_cap = arena_limit / 4 * 3;
     if (use_strips) {
         std::vector<int> cand;
         for (int k = 0; k < nj; ++k) {
@@ -200,7 +209,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         // They are processed in groups whose arenas fit into three quarters of the budget, one launch per group.  A group
         // costs the critical path of one alignment (~110 k rows) however few alignments it holds, so a short last group
         // (<= 15 alignments: one round of 8-CTA clusters) takes the cluster route next to the strips instead.
-        const size_t cap = ctx->arena_limit / 4 * 3;
+        const size_t cap = strip_cap;
         size_t group = 0, group_first = 0;
         for (int k : cand) {
             const KswJob& J = jobs[k];
@@ -228,7 +237,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         J.sig_off = (uint32_t)k * kSigCap;
         if (pool_words > 0xFFFFFFF0ull) { ctx->err = "batch too large (packed pool offsets are 32-bit)"; return LESVGPU_E_ARG; }
         tb_bytes[k] = (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
-        if (tb_bytes[k] > ctx->arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
+        if (tb_bytes[k] > arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
         if (is_strip[k]) { J.nt = kStripBlocks; continue; }
         size_t li = 0;
         for (; li < launches.size(); ++li)
@@ -301,14 +310,6 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         for (int i = 0; i < L.n_clusters; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
         return b;
     };
-    // what the arena may grow to right now: the configured limit, but never more than 92 % of what is free
-    // (other stages of the library keep buffers of their own on the same device)
-    size_t arena_limit = ctx->arena_limit;
-    {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-            arena_limit = std::min(arena_limit, (size_t)((free_b + ctx->d_arena.cap) * 0.90));
-    }
     if (strip_arena > arena_limit) { ctx->err = "traceback arena too small for the full-matrix alignments"; return LESVGPU_E_NOMEM; }
     arena_limit -= strip_arena;                          // the strips' per-alignment arenas sit behind the classes' ones
     for (;;) {
@@ -350,7 +351,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     int prog_ints = 0, strip_smem_q = 0, strip_smem_t = 0;
     if (!strip_ids.empty()) {
         struct Per { int n_strips, prog_off; size_t arena_off, edge_off; };
-        const size_t cap = ctx->arena_limit / 4 * 3;
+        const size_t cap = strip_cap;
         size_t x0 = 0;
         while (x0 < strip_ids.size()) {                  // a group = consecutive alignments (input order) whose arenas fit
             size_t x1 = x0, aoff = arena_need;
@@ -629,11 +630,60 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
     for (int i = 0; i < n; ++i) memcpy(ctx->h_raw.p + dst_byte[i], query_pac + src_byte[i], nbytes[i]);
     const int rc = run_jobs(ctx, jobs, raw_bytes, false, true);
     if (rc != LESVGPU_OK) return rc;
+    // The walk counts every SV-sized gap run but keeps kSigCap records per alignment.  find_sv_signature has no such
+    // limit (find_sv_signature.c:126-220), so alignments with more runs -- a small min_indel_size, a read over a
+    // tandem-repeat region -- are run once more with a CIGAR, which is scanned here for the same records.
+    const KswOut* outs = ctx->h_outs.p;
+    const KswGapRun* runs = ctx->h_runs.p;
+    std::vector<KswOut> outs_keep;
+    std::vector<KswGapRun> runs_keep;
+    std::vector<int> over;
+    std::vector<std::vector<KswGapRun>> over_runs;       // left to right
+    for (int k = 0; k < nj; ++k)
+        if (outs[k].status == 1 && outs[k].n_cigar > 0 && outs[k].trunc_ok && outs[k].n_runs > kSigCap) over.push_back(k);
+    if (!over.empty()) {
+        outs_keep.assign(outs, outs + nj);
+        runs_keep.assign(runs, runs + (size_t)nj * kSigCap);
+        outs = outs_keep.data(); runs = runs_keep.data();
+        const lesvgpu_timing first = ctx->timing;
+        std::vector<KswJob> again;
+        for (int k : over) { KswJob J = jobs[k]; J.min_indel = 0; again.push_back(J); }
+        const int rc2 = run_jobs(ctx, again, raw_bytes, true, false);
+        if (rc2 != LESVGPU_OK) return rc2;
+        lesvgpu_timing& T = ctx->timing;
+        T.h2d_ms += first.h2d_ms; T.pack_ms += first.pack_ms; T.dp_ms += first.dp_ms; T.d2h_ms += first.d2h_ms;
+        T.dp_launches += first.dp_launches; T.kernel_launches += first.kernel_launches;
+        T.h2d_bytes += first.h2d_bytes; T.d2h_bytes += first.d2h_bytes;      // dp_cells accumulates by itself
+        over_runs.resize(over.size());
+        for (size_t x = 0; x < over.size(); ++x) {
+            const KswOut& O = outs[over[x]];
+            const KswOut& O2 = ctx->h_outs.p[x];
+            if (O2.status != 1 || O2.n_cigar <= 0) { ctx->err = "re-alignment for the signature scan failed"; return LESVGPU_E_CUDA; }
+            const uint32_t* cg = ctx->h_cigar.p + again[x].cigar_off;
+            int si = 0, qi = 0;                              // target / read bases consumed so far
+            for (int c = 0; c < O2.n_cigar; ++c) {
+                const int op = (int)(cg[c] & 15u), len = (int)(cg[c] >> 4);
+                if (op == 0) { si += len; qi += len; continue; }
+                const int ds = op == 2 ? len : 0, dq = op == 1 ? len : 0;
+                if (len >= min_indel_size && si >= O.sb && qi >= O.qb && si + ds <= O.se && qi + dq <= O.qe) {
+                    KswGapRun g;
+                    if (op == 2) { g.type = 0; g.qfrom = qi; g.qto = qi + 1; g.sfrom = si; g.sto = si + len; }
+                    else { g.type = 6; g.qfrom = qi; g.qto = qi + len; g.sfrom = si; g.sto = si + 1; }
+                    over_runs[x].push_back(g);
+                }
+                si += ds; qi += dq;
+            }
+            if ((int)over_runs[x].size() != O.n_runs) { ctx->err = "signature scan of the CIGAR disagrees with the walk"; return LESVGPU_E_CUDA; }
+        }
+    }
+    size_t next_over = 0;
     for (int k = 0; k < nj; ++k) {
         const int i = job_read[k];
         const lesvgpu_svread& S = reads[i];
         lesvgpu_svsig_read& R = per_read[i];
-        const KswOut& O = ctx->h_outs.p[k];
+        const KswOut& O = outs[k];
+        const std::vector<KswGapRun>* wide = nullptr;
+        if (next_over < over.size() && over[next_over] == k) wide = &over_runs[next_over++];
         R.qb = O.qb; R.qe = O.qe; R.sb = O.sb; R.se = O.se;
         R.eff_mat = O.eff_mat; R.eff_len = O.eff_len;
         if (O.status != 1 || O.n_cigar <= 0) { R.status = 0; continue; }
@@ -647,10 +697,10 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
         }
         const double eff = O.eff_len == 0 ? 0.0 : 100.0 * O.eff_mat / O.eff_len;   // hbn_traceback_aux.c:93-94
         if (eff < 70.0) { R.status = -3; continue; }
-        if (O.n_runs > kSigCap) { ctx->err = "more than 64 SV-sized gap runs in one alignment"; return LESVGPU_E_NOMEM; }
         R.status = 1; R.n_sig = O.n_runs;
-        const KswGapRun* g = ctx->h_runs.p + (size_t)k * kSigCap;
-        for (int x = O.n_runs - 1; x >= 0; --x) {                    // the walk found them right-to-left
+        const KswGapRun* g = wide ? wide->data() : runs + (size_t)k * kSigCap;
+        for (int y = 0; y < O.n_runs; ++y) {
+            const int x = wide ? y : O.n_runs - 1 - y;               // the walk found them right-to-left
             lesvgpu_svsig v;
             v.qid = S.query_id; v.qdir = S.qdir;
             v.qfrom = g[x].qfrom; v.qto = g[x].qto;

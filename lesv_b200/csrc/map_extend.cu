@@ -992,7 +992,14 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
                 for (int k = 0; k < cand_cnt[gw]; ++k) {
                     const CandOut& o = outs[(size_t)kMaxCandPerWindow * gw + k];
                     if (o.n_mems == 0) continue;
-                    if (o.status < 0 && o.status != lesvtb::kNeedsHirschberg) {
+                    if (o.status == lesvtb::kNeedsHirschberg) {
+                        // trace_core.cuh marks this "cannot happen" (SHW blocks are <= 1459 x 1459).  Dropping the
+                        // candidate would silently diverge from the reference, so it is an error like the overflows.
+                        ++E->tm.n_unsupported;
+                        ctx->err = "an end-extension block needs the Hirschberg route, which the GPU path does not have";
+                        return LESVGPU_E_CUDA;
+                    }
+                    if (o.status < 0) {
                         ctx->err = "alignment scratch overflow (status " + std::to_string(o.status) + ")";
                         return LESVGPU_E_NOMEM;
                     }
@@ -1008,7 +1015,6 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
                         }
                     }
                     if (contained) continue;
-                    if (o.status == lesvtb::kNeedsHirschberg) { ++E->tm.n_unsupported; continue; }
                     if (o.status != lesvtb::kOk) continue;
                     lesvgpu_hsp p;
                     p.qid = qfrom + r; p.qdir = h.qdir; p.qoff = o.qoff; p.qend = o.qend; p.qsize = qsize;

@@ -148,6 +148,20 @@ extern "C" int lesvgpu_svr_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         acc.dp_launches += t.dp_launches; acc.kernel_launches += t.kernel_launches;
         acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes; acc.dp_cells += t.dp_cells;
     };
+    // The records usually come straight out of a .m4x file: a stale or foreign file (another db_dir) must end in a
+    // diagnosed error, not in an out-of-bounds read of subject_seqs[] / the read table.
+    for (size_t i = 0; i < m4c; ++i) {
+        const M4& m = m4a[i];
+        const bool ok = m.qid >= 0 && m.sid >= 0 && m.sid < n_subject && m.qsize > 0 && m.qoff >= 0 && m.qoff <= m.qend &&
+                        m.qend <= m.qsize && m.soff >= 0 && m.soff <= m.send && (size_t)m.send <= subject_seqs[m.sid].seq_size &&
+                        (m.qdir == 0 || m.qdir == 1);
+        if (!ok) {
+            char b[160];
+            snprintf(b, sizeof b, "lesvgpu_svr_batch: m4 record %zu does not fit the database (qid %d, sid %d of %d)", i, m.qid, m.sid, n_subject);
+            ctx->err = b;
+            return LESVGPU_E_ARG;
+        }
+    }
     std::vector<Group> groups;
     std::vector<lesvgpu_refine_job> jobs;
     auto emit = [&](const M4& m) { if (!in_trf(m.sid, m.soff, m.send)) out.push_back(sv_read_from_m4(m)); };

@@ -80,6 +80,43 @@ struct Reader {
     int size(int id) const { return (int)seqs[id].seq_size; }
 };
 
+// Tandem-repeat mask, one byte per subject residue (TrfArrayBuild, app/necat2sv/trf_array.cpp:10-63): every line is
+// exactly `name \t from \t to`; names the database does not know are skipped, everything else the reference asserts
+// (three columns, from < to <= contig size) is fatal here too.
+inline std::vector<char> load_trf_mask(const std::string& path, const Reader& subj)
+{
+    std::vector<char> mask(subj.info.num_seqs ? subj.seqs.back().seq_offset + subj.seqs.back().seq_size : 0, 0);
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) die("cannot open " + path);
+    char* line = nullptr;
+    size_t cap = 0, lineno = 0;
+    ssize_t len;
+    while ((len = getline(&line, &cap, f)) >= 0) {
+        ++lineno;
+        while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = 0;
+        std::vector<std::string> col(1);
+        for (ssize_t i = 0; i < len; ++i) {
+            if (line[i] == '\t') col.emplace_back();
+            else col.back().push_back(line[i]);
+        }
+        const std::string where = path + ":" + std::to_string(lineno);
+        if (col.size() != 3) die(where + ": a TRF line has exactly 3 tab-separated columns");
+        int sid = -1;
+        for (int i = 0; i < subj.info.num_seqs && sid < 0; ++i)
+            if (col[0] == subj.name(i)) sid = i;
+        if (sid < 0) continue;
+        char *e1 = nullptr, *e2 = nullptr;
+        const unsigned long long from = strtoull(col[1].c_str(), &e1, 10), to = strtoull(col[2].c_str(), &e2, 10);
+        if (col[1].empty() || col[2].empty() || *e1 || *e2) die(where + ": bad interval");
+        if (!(from < to)) die(where + ": from >= to");
+        if (to > subj.seqs[sid].seq_size) die(where + ": interval ends behind the contig");
+        memset(mask.data() + subj.seqs[sid].seq_offset + from, 1, (size_t)(to - from));
+    }
+    free(line);
+    fclose(f);
+    return mask;
+}
+
 inline std::string fixed8(int x)
 {
     char b[32];

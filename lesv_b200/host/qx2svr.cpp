@@ -13,7 +13,6 @@
 
 #include <algorithm>
 #include <fstream>
-#include <map>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -44,20 +43,7 @@ int main(int argc, char* argv[])
     std::vector<lesvgpu_seq> sseqs(subj.info.num_seqs);
     for (int i = 0; i < subj.info.num_seqs; ++i) { sseqs[i].seq_offset = subj.seqs[i].seq_offset; sseqs[i].seq_size = subj.seqs[i].seq_size; }
     std::vector<char> trf;
-    if (trf_path) {
-        trf.assign(subj.info.seq_offset_to, 0);
-        std::map<std::string, int> ids;
-        for (int i = 0; i < subj.info.num_seqs; ++i) ids[subj.name(i)] = i;
-        std::ifstream in(trf_path);
-        if (!in) die(std::string("cannot open ") + trf_path);
-        std::string name; size_t from, to;
-        while (in >> name >> from >> to) {
-            auto it = ids.find(name);
-            if (it == ids.end()) continue;
-            for (size_t x = from; x < to; ++x) trf[subj.seqs[it->second].seq_offset + x] = 1;
-        }
-        g_trf = &trf;
-    }
+    if (trf_path) { trf = load_trf_mask(trf_path, subj); g_trf = &trf; }
     lesvgpu_ctx* ctx = nullptr;
     if (lesvgpu_ctx_create(device, 0, &ctx) != LESVGPU_OK) die("no usable B200 (lesvgpu_ctx_create failed); there is no CPU path");
     if (lesvgpu_subject_load(ctx, subj.pac.data(), subj.pac.size()) != LESVGPU_OK) die(lesvgpu_last_error(ctx));

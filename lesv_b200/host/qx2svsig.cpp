@@ -11,7 +11,6 @@
 
 #include <algorithm>
 #include <fstream>
-#include <map>
 #include <sstream>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -35,25 +34,6 @@ static std::vector<lesvgpu_svread> load_sv_reads(const std::string& path)
     return v;
 }
 
-static std::vector<char> load_trf(const std::string& path, const Reader& subj)
-{
-    // TrfArrayBuild, trf_array.cpp:10-63: name \t from \t to, one byte per subject residue
-    std::vector<char> mask(subj.info.seq_offset_to, 0);
-    std::map<std::string, int> ids;
-    for (int i = 0; i < subj.info.num_seqs; ++i) ids[subj.name(i)] = i;
-    std::ifstream in(path);
-    if (!in) die("cannot open " + path);
-    std::string name;
-    size_t from, to;
-    while (in >> name >> from >> to) {
-        auto it = ids.find(name);
-        if (it == ids.end()) continue;
-        const size_t off = subj.seqs[it->second].seq_offset;
-        for (size_t x = from; x < to; ++x) mask[off + x] = 1;
-    }
-    return mask;
-}
-
 int main(int argc, char* argv[])
 {
     if (argc != 6 && argc != 7) {
@@ -71,7 +51,7 @@ int main(int argc, char* argv[])
     subj.open(db_dir, "subject");
     query.open(db_dir, "query");
     std::vector<char> trf;
-    if (trf_path) trf = load_trf(trf_path, subj);
+    if (trf_path) trf = load_trf_mask(trf_path, subj);
 
     lesvgpu_ctx* ctx = nullptr;
     if (lesvgpu_ctx_create(device, 0, &ctx) != LESVGPU_OK) die("no usable B200 (lesvgpu_ctx_create failed); there is no CPU path");

@@ -52,10 +52,79 @@ elif scen == "c3":                     # BASELINE.json configs[2] shape: 24 cont
         reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
     del contigs
     synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
+elif scen == "bigsv":                  # 50 kb reads across 6-10 kb INS/DEL: bands of 10-20 k (the 2-CTA cluster class) at real size
+    n = int(os.environ.get("BIGSV_READS", "24"))
+    ref = synth.random_codes(3_000_000, rng)
+    sample, events = synth.plant_events(ref, rng, 12, sizes=(6000, 7000, 8000, 9000, 10000), min_gap=100_000)
+    shift, spos = 0, []                # event positions in sample coordinates
+    for kind, pos, size in events:
+        spos.append(pos + shift)
+        shift += size if kind == "INS" else -size
+    r2 = np.random.default_rng(11)
+    reads = []
+    for i in range(n):
+        c = spos[i % len(spos)] + int(r2.integers(-15000, 15000))
+        s0 = max(0, min(len(sample) - 50000, c - 25000))
+        rd = synth.mutate(sample[s0:s0 + 50000], float(r2.uniform(0.10, 0.15)), r2)
+        reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
+    synth.write_fasta(os.path.join(work, "ref.fa"), ["chrB"], [ref], width=0)
+    synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(n)], reads)
+elif scen in ("trf", "minindel", "m4x", "md"):
+    # trf      = a TRF bed file through qx2svr and qx2svsig (trf_array.cpp:10-83): masked stretches cover some SV reads
+    #            entirely (dropped), some partly (kept), plus a contig name the database does not know (skipped)
+    # minindel = qx2svsig with min_indel_size 1: hundreds of gap runs per read (no cap in find_sv_signature.c:126-220)
+    # m4x      = qx2map -outfmt m4x (binary M4Record stream, mecat_results.c:281-297) on stdout and in the backup file
+    # md       = qx2map -cigar -md (MD:Z: column, mecat_results.c:86-135)
+    info = synth.make_dataset(work, ref_len=900_000, n_reads=90, read_len=9000, n_events=18, seed=61, n_contigs=3,
+                              err_lo=0.10, err_hi=0.15, event_sizes=(40, 60, 100, 300, 1000, 3000))
+    if scen == "trf":
+        with open(os.path.join(work, "trf.bed"), "w") as f:
+            for c in range(3):
+                for a, b in ((20_000, 60_000), (100_000, 103_000), (150_000, 230_000)):
+                    f.write(f"contig{c}\t{a}\t{b}\n")
+            f.write("chrUnknown\t5\t500\n")
+elif scen == "tails":                  # junk / very noisy read ends: edlib's end extension gives up, the DALIGNER wave runs
+    ref = synth.random_codes(1_000_000, rng)
+    r2 = np.random.default_rng(21)
+    reads = []
+    for i in range(80):
+        s0 = int(r2.integers(0, len(ref) - 9000))
+        core = synth.mutate(ref[s0:s0 + 8000], float(r2.uniform(0.08, 0.14)), r2)
+        def tail(seg):
+            kind = int(r2.integers(0, 3))
+            if kind == 0:
+                return synth.random_codes(int(r2.integers(150, 2600)), r2)             # unrelated sequence
+            return synth.mutate(seg, float(r2.uniform(0.30, 0.45)), r2)               # the true flank, very noisy
+        left = tail(ref[max(0, s0 - 1200):s0]) if i % 3 != 2 else np.zeros(0, np.uint8)
+        right = tail(ref[s0 + 8000:s0 + 9000]) if i % 3 != 1 else np.zeros(0, np.uint8)
+        rd = np.concatenate([left, core, right])
+        reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
+    synth.write_fasta(os.path.join(work, "ref.fa"), ["chrT"], [ref], width=0)
+    synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
+elif scen == "c4":                     # BASELINE.json configs[3] shape: ultra-long reads split by qx2splitseq 50000 0 20000,
+    # 35 % of the reads with a 20-30 % error rate, -kmer_size 19 -kmer_window 20 (README.md:164), SVR identity 80.0
+    ref_len = int(float(os.environ.get("C4_REF_MBP", "8")) * 1_000_000)
+    contigs = [synth.random_codes(ref_len // 4, rng) for _ in range(4)]
+    samples = [synth.plant_events(c, rng, 6, sizes=(40, 100, 300, 1000, 3000), min_gap=100_000)[0] for c in contigs]
+    r2 = np.random.default_rng(31)
+    reads = []
+    for i in range(int(os.environ.get("C4_READS", "10"))):
+        smp = samples[i % 4]
+        L = int(min(len(smp) - 1000, max(150_000, np.exp(r2.normal(np.log(200_000), 0.6)))))
+        s0 = int(r2.integers(0, len(smp) - L))
+        err = float(r2.uniform(0.20, 0.30)) if r2.random() < 0.35 else float(r2.uniform(0.08, 0.15))
+        rd = synth.mutate(smp[s0:s0 + L], err, r2)
+        reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
+    synth.write_fasta(os.path.join(work, "ref.fa"), [f"chr{i + 1}" for i in range(4)], contigs, width=0)
+    synth.write_fasta(os.path.join(work, "long.fa"), [f"ul{i}" for i in range(len(reads))], reads, width=0)
+    map_args += ["-kmer_size", "19", "-kmer_window", "20"]
 else:
     raise SystemExit("unknown scenario")
 env = dict(os.environ, OMP_NUM_THREADS="1")
 t = str(os.cpu_count() or 4)
+svr_args = ["3000", "80.0" if scen == "c4" else "70.0", "300", t] + (["trf.bed"] if scen == "trf" else [])
+min_indel = "1" if scen == "minindel" else "40"
+svsig_tail = [min_indel, t] + (["trf.bed"] if scen == "trf" else [])
 
 
 def run(cmd, out=None, tag=""):
@@ -65,13 +134,45 @@ def run(cmd, out=None, tag=""):
     print(f"  {tag or os.path.basename(cmd[0])}: {time.time() - t0:.1f} s", flush=True)
 
 
+if scen == "c4":                       # the step before the path: both qx2splitseq builds cut the long reads
+    with open(os.path.join(work, "reads.fa"), "wb") as f:
+        run([os.path.join(REF, "qx2splitseq"), "50000", "0", "20000", "long.fa"], f, "qx2splitseq (reference)")
+    with open(os.path.join(work, "reads_gpu.fa"), "wb") as f:
+        run([os.path.join(OURS, "qx2splitseq"), "50000", "0", "20000", "long.fa"], f, "qx2splitseq (ours)")
+    same = open(os.path.join(work, "reads.fa"), "rb").read() == open(os.path.join(work, "reads_gpu.fa"), "rb").read()
+    print(f"splitseq: identical {same}")
+if scen in ("m4x", "md"):              # mapper output formats only: the rest of the chain reads the default m4 text
+    fmt = ["-outfmt", "m4x"] if scen == "m4x" else ["-cigar", "-md"]
+    with open(os.path.join(work, "ref.out"), "wb") as f:
+        run([os.path.join(REF, "qx2map")] + map_args + fmt + ["-db_dir", "db", "-keep_db", "-num_threads", "1", "reads.fa", "ref.fa"], f, "qx2map (reference)")
+    with open(os.path.join(work, "gpu.out"), "wb") as f:
+        run([os.path.join(OURS, "qx2map")] + map_args + fmt + ["-db_dir", "db_gpu", "-keep_db", "reads.fa", "ref.fa"], f, "qx2map (ours)")
+    if scen == "m4x":
+        def recs(p):
+            raw = np.fromfile(p, dtype=np.uint8)
+            assert len(raw) % 56 == 0, p
+            return sorted(bytes(r) for r in raw.reshape(-1, 56)[:, :52])     # 4 trailing pad bytes are uninitialised in the reference
+        bk = "backup_results/stagebackup_results_Q00000000_D00000000"
+        a, b = recs(os.path.join(work, "ref.out")), recs(os.path.join(work, "gpu.out"))
+        a2, b2 = recs(os.path.join(work, "db", bk)), recs(os.path.join(work, "db_gpu", bk))
+        print(f"m4x: reference {len(a)} records, ours {len(b)}, identical {a == b}; backup files identical {a2 == b2 and a2 == a}")
+    else:
+        a, b = sorted(open(os.path.join(work, "ref.out")).readlines()), sorted(open(os.path.join(work, "gpu.out")).readlines())
+        n_md = sum("\tMD:Z:" in x for x in a)
+        print(f"md: reference {len(a)} lines ({n_md} with MD:Z:), ours {len(b)}, identical {a == b}")
+    sys.exit(0)
 print("reference:")
 with open(os.path.join(work, "ref.m4"), "wb") as f:
     run([os.path.join(REF, "qx2map")] + map_args + ["-db_dir", "db", "-keep_db", "-num_threads", os.environ.get("REF_MAP_THREADS", "1"),
          "reads.fa", "ref.fa"], f, "qx2map")
 run([os.path.join(REF, "qx2m4x"), "db"])
-run([os.path.join(REF, "qx2svr"), "svr", "db", "3000", "70.0", "300", t])
-run([os.path.join(REF, "qx2svsig"), "svsig", "svr", "db", "40", t])
+run([os.path.join(REF, "qx2svr"), "svr", "db"] + svr_args)
+run([os.path.join(REF, "qx2svsig"), "svsig", "svr", "db"] + svsig_tail)
+if os.environ.get("PROBE_REF_ONLY"):   # scenario check without a GPU: how the reference behaves on this input
+    for d, pat in (("svr", ".sv_read"), ("svsig", ".sv_signature")):
+        print(d, sum(len(open(os.path.join(work, d, f)).readlines()) for f in os.listdir(os.path.join(work, d)) if f.endswith(pat)), "records")
+    print("m4 lines", len(open(os.path.join(work, "ref.m4")).readlines()))
+    sys.exit(0)
 print("ours:")
 env["LESV_TIMING"] = "1"
 with open(os.path.join(work, "gpu.m4"), "wb") as f:
@@ -79,8 +180,8 @@ with open(os.path.join(work, "gpu.m4"), "wb") as f:
 for l in open(os.path.join(work, "log.txt"), errors="replace"):
     if "[lesv-b200] '" in l: print("     " + l.strip())
 run([os.path.join(OURS, "qx2m4x"), "db_gpu"])
-run([os.path.join(OURS, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", t])
-run([os.path.join(OURS, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", t])
+run([os.path.join(OURS, "qx2svr"), "svr_gpu", "db_gpu"] + svr_args)
+run([os.path.join(OURS, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu"] + svsig_tail)
 
 
 def lines(p):
