@@ -154,11 +154,12 @@ class ClockSampler:
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
-def reference_pipeline(ref, reads, cores: int):
+def reference_pipeline(ref, reads, cores: int, keep=None):
     """qx2map -> qx2m4x -> qx2svr -> qx2svsig of the compiled reference (oracle/_ref/bin) on `reads`.
-    Returns a dict of seconds per stage, aligned bases and signature count.  The mapping time is the
+    Returns a dict of seconds per stage, aligned bases, DP cells and signature count.  The mapping time is the
     reference's own 'mapping query ...' timer (hbn_align_one_volume.c:124,141): database packing and the
-    index build are one-off costs per reference and are reported separately."""
+    index build are one-off costs per reference and are reported separately.  keep = dict: the m4x records, SvReads and
+    signatures the reference wrote are left in it (for the parity block)."""
     work = tempfile.mkdtemp(prefix="lesv_ref_")
     try:
         synth.write_fasta(os.path.join(work, "ref.fa"), ["chr1"], [ref], width=0)
@@ -188,28 +189,43 @@ def reference_pipeline(ref, reads, cores: int):
             for line in f:
                 c = line.split("\t")
                 bases += int(c[6]) - int(c[5])
-        n_sig = 0
-        for fn in os.listdir(os.path.join(work, "svsig")):
+        sig_lines, svr_lines = [], []
+        for fn in sorted(os.listdir(os.path.join(work, "svsig"))):
             if fn.endswith(".sv_signature"):
-                n_sig += sum(1 for _ in open(os.path.join(work, "svsig", fn)))
+                sig_lines += open(os.path.join(work, "svsig", fn)).readlines()
+        for fn in sorted(os.listdir(os.path.join(work, "svr"))):
+            if fn.startswith("subject_") and fn.endswith(".sv_read"):
+                svr_lines += open(os.path.join(work, "svr", fn)).readlines()
         res["aligned_bases"] = bases
-        res["signatures"] = n_sig
+        res["signatures"] = len(sig_lines)
         res["path_s"] = res["map_s"] + res["qx2svr_wall_s"] + res["qx2svsig_wall_s"]
+        if keep is not None:
+            br = os.path.join(work, "db", "backup_results")
+            raw = [np.fromfile(os.path.join(br, fn), dtype=np.uint8) for fn in sorted(os.listdir(br)) if fn.endswith(".m4x")]
+            keep["m4x"] = np.concatenate(raw).reshape(-1, 56)[:, :52] if raw else np.zeros((0, 52), np.uint8)
+            keep["svr"] = [tuple(int(x) for x in l.split("\t")[:9]) for l in svr_lines]
+            keep["sig"] = [tuple(int(x) for x in l.split("\t")[:13]) for l in sig_lines]
         return res
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
 
-def cpu_baseline(ref, reads, cores):
+def cpu_baseline(ref, reads, cores, keep=None):
     if not os.path.exists(os.path.join(REF_BIN, "qx2map")):
         return None
-    r = reference_pipeline(ref, reads, cores)
+    r = reference_pipeline(ref, reads, cores, keep)
     return {"value": r["aligned_bases"] / r["path_s"], "unit": "bases/s", "cores": cores, "kind": "reference",
-            "sample": f"{len(reads)} reads of the same workload through oracle/_ref/bin qx2map, qx2svr, qx2svsig on {cores} threads: "
+            "sample": f"{len(reads)} reads (16 per host thread) of the same workload through oracle/_ref/bin qx2map, qx2svr, qx2svsig on {cores} threads: "
                       f"mapping {r['map_s']:.2f} s (the tool's own timer, without database/index build; whole qx2map "
                       f"{r['qx2map_wall_s']:.2f} s), qx2svr {r['qx2svr_wall_s']:.2f} s, qx2svsig {r['qx2svsig_wall_s']:.2f} s",
             "stages_s": {"map": r["map_s"], "svr": r["qx2svr_wall_s"], "svsig": r["qx2svsig_wall_s"]},
             "signatures": r["signatures"]}
+
+
+def sample_size(cores: int) -> int:
+    """Reads in the reference leg: 16 per host thread, so that qx2map's 5-read chunks and qx2svr's few full-matrix
+    alignments spread over all threads instead of leaving most of them idle behind one straggler."""
+    return max(16 * cores, 64)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -233,6 +249,178 @@ def _emit(line: dict):
         os.write(_RESULT_FD, data)
 
 
+HG19_MBP = [249, 243, 198, 191, 181, 171, 159, 146, 141, 136, 135, 134, 115, 107, 103, 90, 81, 78, 59, 63, 48, 51, 155, 59]
+
+
+def make_c3_reference(seed: int, scale: float = 1.0):
+    """BASELINE.json configs[2]: 24 contigs with hg19's length profile (3.1 Gbp at scale 1), i.i.d. uniform residues."""
+    rng = np.random.default_rng(seed)
+    return [synth.random_codes(int(mb * 1_000_000 * scale), rng) for mb in HG19_MBP]
+
+
+def make_reads_c3(contigs, n_reads: int, seed: int, read_len: int = READ_LEN):
+    """50 kb subreads at 10-15 % error drawn from the contigs in proportion to their length; every fourth read carries a
+    planted 40 bp-10 kb insertion or deletion (the sample genome of a 3.1 Gbp reference is not materialised)."""
+    rng = np.random.default_rng(seed)
+    sizes = np.array([len(c) for c in contigs], dtype=np.float64)
+    reads = []
+    for i in range(n_reads):
+        c = contigs[int(rng.choice(len(contigs), p=sizes / sizes.sum()))]
+        p0 = int(rng.integers(0, len(c) - read_len - 10000))
+        seg = c[p0:p0 + read_len]
+        if i % 4 == 0:
+            size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
+            k = int(rng.integers(5000, read_len - 15000))
+            seg = np.concatenate([seg[:k], c[p0 + k + size:p0 + read_len + size]]) if i % 8 == 0 else \
+                np.concatenate([seg[:k], synth.random_codes(size, rng), seg[k:read_len - size]])
+        r = synth.mutate(seg, float(rng.uniform(0.10, 0.15)), rng)
+        if rng.integers(0, 2):
+            r = synth.revcomp_codes(r)
+        reads.append(np.ascontiguousarray(r))
+    return reads
+
+
+class Batch:
+    """One query batch as the drop-in tools hand it to the library: packed reads (.pac layout) in HOST memory."""
+
+    def __init__(self, reads, capi):
+        self.reads = reads
+        self.query_pac, qoffs = pack_pac(reads)
+        self.qsizes = np.array([len(r) for r in reads], dtype=np.int64)
+        self.read_offset = (qoffs + 1).astype(np.uint64)
+        self.seq_arr = capi._seq_array(qoffs, self.qsizes)
+        self.nq = len(reads)
+
+
+def run_path(ctx, capi, B: Batch, subj, collect: bool = False):
+    """One batch through the path: qx2map -> (m4 text round trip) -> qx2svr -> qx2svsig, all through the C ABI with host
+    buffers.  Returns per-stage device ms, byte counts and work counts (collect: also the records themselves)."""
+    w0 = time.perf_counter()
+    h = capi.map_batch_raw(ctx, B.query_pac, B.seq_arr, 0, B.nq, hitlist_size=5, max_hsps=10)
+    w1 = time.perf_counter()
+    mt, et = capi.map_last_timing(ctx), capi.map_last_extend_timing(ctx)
+    m4 = capi.hsps_to_m4(h)
+    w2 = time.perf_counter()
+    svr, st = capi.svr_batch(ctx, B.query_pac, B.read_offset, subj["offsets"], subj["sizes"], m4, 3000, 70.0, 300)
+    w3 = time.perf_counter()
+    t_svr = ctx.timing() if (st.n_refine_jobs or st.n_chain_jobs) else capi.Timing()
+    svr_classes = ctx.class_timing() if (st.n_refine_jobs or st.n_chain_jobs) else []
+    out = capi.svsig_contigs_raw(ctx, B.query_pac, B.read_offset, subj["seq_arr"], len(subj["offsets"]), svr, MIN_INDEL, want_sigs=collect)
+    status, n_sig = out[0], out[1]
+    w4 = time.perf_counter()
+    t_sig = ctx.timing()
+    dev = {"map_seed_chain": mt.lookup_ms + mt.emit_ms + mt.sort_ms + mt.chain_ms,
+           "map_extend": et.ihf_ms + et.sort_ms + et.chain_ms + et.trace_ms,
+           "svr": t_svr.pack_ms + t_svr.dp_ms + t_svr.scan_ms,
+           "svsig": t_sig.pack_ms + t_sig.dp_ms + t_sig.scan_ms}
+    wall = {"map": (w1 - w0) * 1e3, "m4": (w2 - w1) * 1e3, "svr": (w3 - w2) * 1e3, "svsig": (w4 - w3) * 1e3}
+    r = {"dev": dev, "wall": wall, "dp_ms": t_svr.dp_ms + t_sig.dp_ms, "sig_dp_ms": t_sig.dp_ms, "sig_cells": int(t_sig.dp_cells),
+         "svr_dp_ms": t_svr.dp_ms, "svr_cells": int(t_svr.dp_cells),
+         "cells": int(t_svr.dp_cells) + int(t_sig.dp_cells), "dp_launches": t_svr.dp_launches + t_sig.dp_launches,
+         "sig_launches": t_sig.dp_launches, "classes": {"svsig": ctx.class_timing(), "svr_last_round": svr_classes},
+         "h2d": int(mt.h2d_bytes + t_svr.h2d_bytes + t_sig.h2d_bytes),
+         "d2h": int(mt.d2h_bytes + et.d2h_bytes + t_svr.d2h_bytes + t_sig.d2h_bytes),
+         "bases": int((h["qend"] - h["qoff"]).sum()), "hsps": len(h), "sv_reads": len(svr),
+         "reads_ok": int((status == 1).sum()), "signatures": n_sig, "n_unsupported": int(et.n_unsupported),
+         "svr_jobs": int(st.n_refine_jobs + st.n_chain_jobs)}
+    if collect:
+        r["records"] = {"m4": m4, "svr": svr, "sig": out[2]}
+    return r
+
+
+def parity_block(ours, ref_keep):
+    """Our records for the sample reads against the files the reference leg wrote for the same reads (outside the
+    timed region): M4Record multiset (first 52 bytes: the 4 trailing pad bytes are uninitialised in the reference),
+    subject_*.sv_read and subject_*.sv_signature records as multisets of integer tuples."""
+    from collections import Counter
+
+    def diff(a, b):
+        ca, cb = Counter(a), Counter(b)
+        return sum(((ca - cb) + (cb - ca)).values())
+    m4 = ours["m4"]
+    mine_m4 = [bytes(x) for x in np.frombuffer(m4.tobytes(), dtype=np.uint8).reshape(-1, 56)[:, :52]]
+    ref_m4 = [bytes(x) for x in ref_keep["m4x"]]
+    svr = ours["svr"]
+    mine_svr = [tuple(int(r[k]) for k in ("query_id", "qdir", "qoff", "qend", "qsize", "subject_id", "soff", "send", "dist")) for r in svr]
+    mine_sig = [tuple(int(v) for v in r) for r in ours["sig"].tolist()]
+    d = {"m4": diff(mine_m4, ref_m4), "sv_read": diff(mine_svr, ref_keep["svr"]), "sv_signature": diff(mine_sig, ref_keep["sig"])}
+    return {"checked": {"m4": len(ref_m4), "sv_read": len(ref_keep["svr"]), "sv_signature": len(ref_keep["sig"])},
+            "n_diff": sum(d.values()), "diff_by_file": d,
+            "note": "reference leg on all host threads, GPU with the whole sample as one batch: the query-side k-mer occurrence "
+                    "filter is per thread slice in the reference (SURVEY.md Appendix A #5), identical on non-repetitive references"}
+
+
+def c5_block(ctx, capi, cores: int, seed: int, n_sm: int, f_mhz: float):
+    """BASELINE.json configs[4] on a bounded sample: query/target pairs with lengths log-uniform in 1-50 kb (target = query
+    mutated at 12 %), band w in {64 .. 1024} passed as max_distance; pairs whose length difference exceeds the band fail
+    up front in both implementations and are left out.  GPU = lesvgpu_ksw_batch kernel time (CUDA events); reference =
+    nw_ksw2_extd2 of oracle/_ref/libhbn_ref.so called from one Python thread per host core (ctypes releases the GIL)."""
+    import ctypes as C
+    rng = np.random.default_rng(seed + 5)
+    n_pairs = int(os.environ.get("LESV_C5_PAIRS", "3072"))
+    base = []
+    for _ in range(n_pairs):
+        L = int(np.exp(rng.uniform(np.log(1000), np.log(50000))))
+        q = rng.integers(0, 4, L, dtype=np.uint8)
+        base.append((q, np.ascontiguousarray(synth.mutate(q, 0.12, rng))))
+    peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9
+    so = os.path.join(ROOT, "oracle", "_ref", "libhbn_ref.so")
+    lib = None
+    if os.path.exists(so):
+        lib = C.CDLL(so)
+        lib.Ksw2DataNew.restype = C.c_void_p
+        lib.ksw2_extd2_set_params.argtypes = [C.c_void_p]
+        lib.nw_ksw2_extd2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
+
+    class KString(C.Structure):
+        _fields_ = [("l", C.c_size_t), ("m", C.c_size_t), ("s", C.c_void_p)]
+
+    def cpu_gcups(pairs, w):
+        it, lock = iter(range(len(pairs))), threading.Lock()
+
+        def worker():
+            data = lib.Ksw2DataNew()
+            lib.ksw2_extd2_set_params(data)
+            qa, sa, ints, ident = KString(), KString(), [C.c_int() for _ in range(4)], C.c_double()
+            while True:
+                with lock:
+                    i = next(it, None)
+                if i is None:
+                    return
+                q, t = pairs[i]
+                lib.nw_ksw2_extd2(data, 0, q.ctypes.data, 0, len(q), len(q), 0, t.ctypes.data, 0, len(t), len(t), 0,
+                                  C.c_double(0.0), w, *[C.addressof(x) for x in ints], C.addressof(ident), C.addressof(qa), C.addressof(sa))
+        ths = [threading.Thread(target=worker) for _ in range(cores)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        sec = time.perf_counter() - t0
+        return sum(capi.ksw_cells(len(q), len(t), w)[0] for q, t in pairs) / sec / 1e9
+
+    rows = []
+    for w in (64, 128, 256, 512, 1024):
+        good = [(q, t) for q, t in base if abs(len(q) - len(t)) <= w]
+        if not good:
+            continue
+        qs, ts = [p[0] for p in good], [p[1] for p in good]
+        ctx.ksw_batch(qs[:64], ts[:64], [w] * min(64, len(good)), want_cigars=False)          # warm-up
+        res, _ = ctx.ksw_batch(qs, ts, [w] * len(good), want_cigars=False)
+        tm = ctx.timing()
+        g = tm.dp_cells / (tm.dp_ms / 1e3) / 1e9
+        row = {"band": w, "pairs": len(good), "ok": int(sum(r.ok for r in res)), "gcells": tm.dp_cells / 1e9, "gpu_ms": tm.dp_ms,
+               "gcups": g, "roofline_frac": g / peak}
+        if lib is not None:
+            n_cpu = min(len(good), 4 * cores)
+            row["reference_gcups"] = cpu_gcups(good[:n_cpu], w)
+            row["reference_pairs"] = n_cpu
+        rows.append(row)
+    return {"workload": f"C5 sample: {n_pairs} pairs, lengths log-uniform 1-50 kb, target = query at 12 % error; of BASELINE's 1 M pairs "
+                        "(same length and band distribution)", "reference_threads": cores if lib is not None else 0, "bands": rows}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -241,28 +429,42 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=2368)
+    ap.add_argument("--batches", type=int, default=4, help="distinct read batches cycled through the steps")
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 = BASELINE configs[1] (headline); c3 = configs[2]: 24 contigs / 3.1 Gbp (x --c3-scale), index replicated per GPU")
+    ap.add_argument("--c3-scale", type=float, default=1.0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank has its own batches; strong: one fixed read set, sub-batches pulled by all ranks from a shared queue")
+    ap.add_argument("--extra", default="c5", help="comma list of extra blocks on rank 0 at N=1: c5 (band sweep sample), none")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    config = {"workload": "C2: 50 Mbp synthetic contig, 50 kb subreads at 10-15 % error sampled from a genome with planted "
-                          "40 bp-10 kb INS/DEL (~1 per 250 kb); mapping + SvRead selection + SV signatures "
-                          "(-max_target_seqs 5 -max_hsps 10, SVR 3000/70.0/300, min indel 40)",
-              "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN, "ref_len": args.ref_len,
-              "l2": "each step streams new candidate windows and > 100 GB of traceback: far beyond the 126 MB L2",
+    c3 = args.workload == "c3"
+    what = ("C3: 24 contigs with hg19's length profile, %.2f Gbp" % (3.098 * args.c3_scale)) if c3 else "C2: 50 Mbp synthetic contig"
+    config = {"workload": what + ", 50 kb subreads at 10-15 % error with planted 40 bp-10 kb INS/DEL"
+                          + (" (every 4th read)" if c3 else " (~1 per 250 kb of the sample genome)") +
+                          "; mapping + SvRead selection + SV signatures (-max_target_seqs 5 -max_hsps 10, SVR 3000/70.0/300, min indel 40)",
+              "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN,
+              "ref_len": int(sum(HG19_MBP) * 1e6 * args.c3_scale) if c3 else args.ref_len,
+              "batches": f"{args.batches} distinct read batches per GPU, cycled step by step (warm-up included)",
+              "l2": "every step maps another batch and writes > 100 GB of traceback: far beyond the 126 MB L2",
               "seed": args.seed}
 
     # ---- reference arm: the reference's own CPU tools on the host cores --------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
+        if c3:
+            _emit({"impl": "reference", "unavailable": "the reference arm runs the C2 workload (its index build for 3.1 Gbp alone takes minutes)"})
+            return
         ref, sample = make_genomes(args.seed, args.ref_len)
-        n_sample = max(4 * cores, 16)
+        n_sample = sample_size(cores)
         K = max(1, min(args.steps, 2))
         vals = []
         base = None
@@ -277,7 +479,7 @@ def main():
         base = dict(vals[-1], value=v)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus, "steps": K, "warmup": 0,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8", "data": "synthetic", "config": dict(config, reads_per_step_per_gpu=n_sample),
+                "dtype": "int8", "data": "synthetic", "config": dict(config, reads_per_step_per_gpu=n_sample, batches=f"{K} samples"),
                 "cpu_baseline": base,
                 "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         _emit(line)
@@ -294,84 +496,94 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ref, sample = make_genomes(args.seed, args.ref_len)                          # replicated on every GPU
-    reads = make_reads(sample, args.reads_per_step, shard.read_seed_of_rank(args.seed, rank))   # this rank's shard
-    subject_pac, _ = pack_pac([ref])
-    query_pac, qoffs = pack_pac(reads)
-    qsizes = np.array([len(r) for r in reads], dtype=np.int64)
-    read_offset = (qoffs + 1).astype(np.uint64)
-    seq_arr = capi._seq_array(qoffs, qsizes)
-    nq = len(reads)
+    strong = args.scaling == "strong"
+    n_batches = max(1, args.batches)
+    if c3:
+        contigs = make_c3_reference(args.seed, args.c3_scale)                    # replicated on every GPU
+        ref = sample = None
+    else:
+        ref, sample = make_genomes(args.seed, args.ref_len)
+        contigs = [ref]
+    subject_pac, s_offs = pack_pac(contigs)
+    subj = {"offsets": [int(x) for x in s_offs], "sizes": [len(c) for c in contigs]}
+    subj["seq_arr"] = capi._seq_array(subj["offsets"], subj["sizes"])
+
+    def reads_of(seed, n):
+        return make_reads_c3(contigs, n, seed) if c3 else make_reads(sample, n, seed)
+    if strong:      # one read set for the whole job (every rank holds it; ranks pull sub-batches from the shared queue)
+        batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches * world)]
+    else:           # this rank's own batches
+        batches = [Batch(reads_of(shard.read_seed_of_rank(args.seed, rank) + b, args.reads_per_step), capi) for b in range(n_batches)]
+    if c3:
+        subject_bases = sum(subj["sizes"])
+        del contigs
 
     ctx = capi.Context(local_rank)
     lib = ctx.lib
     lib.lesvgpu_launch_count.restype = C.c_uint64
     capi.subject_load(ctx, subject_pac)
     t0 = time.perf_counter()
-    capi.index_build(ctx, [0], [len(ref)], 15, 10, 200)
+    capi.index_build(ctx, subj["offsets"], subj["sizes"], 15, 10, 200)
     index_ms = (time.perf_counter() - t0) * 1e3
-
-    def step():
-        """one batch through the path; returns per-stage device ms, byte counts, work counts"""
-        w0 = time.perf_counter()
-        h = capi.map_batch_raw(ctx, query_pac, seq_arr, 0, nq, hitlist_size=5, max_hsps=10)
-        w1 = time.perf_counter()
-        mt, et = capi.map_last_timing(ctx), capi.map_last_extend_timing(ctx)
-        m4 = capi.hsps_to_m4(h)
-        w2 = time.perf_counter()
-        svr, st = capi.svr_batch(ctx, query_pac, read_offset, [0], [len(ref)], m4, 3000, 70.0, 300)
-        w3 = time.perf_counter()
-        t_svr = ctx.timing() if (st.n_refine_jobs or st.n_chain_jobs) else capi.Timing()
-        status, n_sig = capi.svsig_batch_raw(ctx, query_pac, read_offset, 0, len(ref), svr, MIN_INDEL)
-        w4 = time.perf_counter()
-        t_sig = ctx.timing()
-        dev = {"map_seed_chain": mt.lookup_ms + mt.emit_ms + mt.sort_ms + mt.chain_ms,
-               "map_extend": et.ihf_ms + et.sort_ms + et.chain_ms + et.trace_ms,
-               "svr": t_svr.pack_ms + t_svr.dp_ms + t_svr.scan_ms,
-               "svsig": t_sig.pack_ms + t_sig.dp_ms + t_sig.scan_ms}
-        wall = {"map": (w1 - w0) * 1e3, "m4": (w2 - w1) * 1e3, "svr": (w3 - w2) * 1e3, "svsig": (w4 - w3) * 1e3}
-        return {"dev": dev, "wall": wall, "dp_ms": t_svr.dp_ms + t_sig.dp_ms, "sig_dp_ms": t_sig.dp_ms, "sig_cells": int(t_sig.dp_cells),
-                "cells": int(t_svr.dp_cells) + int(t_sig.dp_cells), "dp_launches": t_svr.dp_launches + t_sig.dp_launches,
-                "sig_launches": t_sig.dp_launches,
-                "h2d": int(mt.h2d_bytes + t_svr.h2d_bytes + t_sig.h2d_bytes),
-                "d2h": int(mt.d2h_bytes + et.d2h_bytes + t_svr.d2h_bytes + t_sig.d2h_bytes),
-                "bases": int((h["qend"] - h["qoff"]).sum()), "hsps": len(h), "sv_reads": len(svr),
-                "reads_ok": int((status == 1).sum()), "signatures": n_sig,
-                "svr_jobs": int(st.n_refine_jobs + st.n_chain_jobs)}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    for k in range(args.warmup):
+        run_path(ctx, capi, batches[k % len(batches)], subj)
     barrier()
     acc = None
+    n_done = 0
     launches0 = lib.lesvgpu_launch_count()
+    queue = shard.WorkQueue(args.steps * world, world) if strong else None
     with ClockSampler(local_rank, active=(rank == 0)) as clk:
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = step()
-            if acc is None:
-                acc = r
+        k = 0
+        while True:
+            if strong:
+                item = queue.next()
+                if item is None:
+                    break
+                B = batches[item % len(batches)]
             else:
-                for k in ("dp_ms", "sig_dp_ms", "sig_cells", "cells", "dp_launches", "sig_launches", "bases"):
-                    acc[k] += r[k]
-                for k in acc["dev"]:
-                    acc["dev"][k] += r["dev"][k]
-                for k in acc["wall"]:
-                    acc["wall"][k] += r["wall"][k]
+                if k >= args.steps:
+                    break
+                B = batches[(args.warmup + k) % len(batches)]
+            k += 1
+            r = run_path(ctx, capi, B, subj)
+            n_done += 1
+            if acc is None:
+                acc = {key: (dict(v) if isinstance(v, dict) and key in ("dev", "wall") else v) for key, v in r.items()}
+                acc["class_sum"] = {}
+            else:
+                for key in ("dp_ms", "sig_dp_ms", "sig_cells", "svr_dp_ms", "svr_cells", "cells", "dp_launches", "sig_launches", "bases",
+                            "n_unsupported"):
+                    acc[key] += r[key]
+                for key in acc["dev"]:
+                    acc["dev"][key] += r["dev"][key]
+                for key in acc["wall"]:
+                    acc["wall"][key] += r["wall"][key]
+            for c in r["classes"]["svsig"]:
+                name = ("strips" if c["ctas_per_alignment"] < 0 else "global-memory fallback" if c["ctas_per_alignment"] == 0 else
+                        f"{c['ctas_per_alignment']}-CTA cluster" if c["ctas_per_alignment"] > 1 else f"single CTA, {c['threads']} threads")
+                e = acc["class_sum"].setdefault(name, {"alignments": 0, "cells": 0, "done_ms": 0.0, "ctas": c["n_ctas"]})
+                e["alignments"] += c["n_alignments"]; e["cells"] += c["cells"]; e["done_ms"] += c["done_ms"]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
     launches = lib.lesvgpu_launch_count() - launches0
+    if acc is None:                                     # strong scaling with more ranks than sub-batches
+        acc = {"dev": {"map_seed_chain": 0.0, "map_extend": 0.0, "svr": 0.0, "svsig": 0.0}, "wall": {}, "bases": 0, "cells": 0, "dp_ms": 0.0,
+               "sig_dp_ms": 0.0, "sig_cells": 0, "svr_dp_ms": 0.0, "svr_cells": 0, "sig_launches": 0, "n_unsupported": 0, "class_sum": {}}
     dev_ms = sum(acc["dev"].values())
     if world > 1:                                       # per-rank view for diagnosis (stderr; rank 0's JSON line is the result)
-        print(f"[bench rank {rank}] device ms/step " + ", ".join(f"{k} {v / args.steps:.1f}" for k, v in acc["dev"].items()) +
-              f"; wall {wall_ms / args.steps:.1f}; clocks {clk.summary()}", file=sys.stderr, flush=True)
+        print(f"[bench rank {rank}] {n_done} batches, device ms/batch " + ", ".join(f"{k} {v / max(1, n_done):.1f}" for k, v in acc["dev"].items()) +
+              f"; wall {wall_ms / max(1, n_done):.1f}; clocks {clk.summary()}", file=sys.stderr, flush=True)
 
     dev_ms_max, wall_ms_max, all_bases, all_cells, all_launches = shard.reduce_stats(
         dev_ms, wall_ms, float(acc["bases"]), float(acc["cells"]), float(launches), world, device="cuda")
+    dev_hi, dev_mean, dev_lo = shard.spread(dev_ms, world, device="cuda")
 
     if rank == 0:
         K = args.steps
@@ -385,41 +597,60 @@ def main():
         f_mhz = clocks["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
         int_peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9      # GCUPS, SURVEY.md 8d
-        kern_gcups = acc["sig_cells"] / (acc["sig_dp_ms"] / 1e3) / 1e9               # rank 0's qx2svsig DP kernel launches
+        kern_gcups = acc["sig_cells"] / (max(acc["sig_dp_ms"], 1e-9) / 1e3) / 1e9    # rank 0's qx2svsig DP launches
+        classes = {name: {"alignments_per_step": e["alignments"] / max(1, n_done), "gcells_per_step": e["cells"] / max(1, n_done) / 1e9,
+                          "ctas": e["ctas"], "done_ms_per_step": e["done_ms"] / max(1, n_done),
+                          "gcups_over_done_ms": e["cells"] / max(e["done_ms"], 1e-9) / 1e6}
+                   for name, e in acc["class_sum"].items()}
         line = {
             "metric": METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": config,
             "gcups": all_cells / (acc["dp_ms"] / 1e3) / 1e9 if world == 1 else None,
-            "e2e": {"value": all_bases / (wall_ms_max / 1e3), "unit": "bases/s", "h2d_bytes_per_step": r["h2d"],
-                    "d2h_bytes_per_step": r["d2h"], "wall_ms_per_step": wall_ms_max / K},
+            "e2e": {"value": all_bases / (wall_ms_max / 1e3), "unit": "bases/s", "h2d_bytes_per_step": r["h2d"] if n_done else 0,
+                    "d2h_bytes_per_step": r["d2h"] if n_done else 0, "wall_ms_per_step": wall_ms_max / K},
             "gpu_launches": int(all_launches),
             "clocks": clocks,
-            "stages_ms_per_step": {k: v / K for k, v in acc["dev"].items()},
-            "call_wall_ms_per_step": {k: v / K for k, v in acc["wall"].items()},
-            "stage_throughput": {"map_bases_per_s": acc["bases"] / ((acc["dev"]["map_seed_chain"] + acc["dev"]["map_extend"]) / 1e3),
-                                 "svr_svsig_gcups": acc["cells"] / (acc["dp_ms"] / 1e3) / 1e9},
+            "rank_spread": {"dev_ms_max": dev_hi, "dev_ms_mean": dev_mean, "dev_ms_min": dev_lo,
+                            "note": "summed device time of the timed steps per rank; the job is as slow as dev_ms_max"},
+            "stages_ms_per_step": {k: v / max(1, n_done) for k, v in acc["dev"].items()},
+            "call_wall_ms_per_step": {k: v / max(1, n_done) for k, v in acc["wall"].items()},
+            "stage_throughput": {"map_bases_per_s": acc["bases"] / (max(acc["dev"]["map_seed_chain"] + acc["dev"]["map_extend"], 1e-9) / 1e3),
+                                 "svr_gcups": acc["svr_cells"] / (max(acc["svr_dp_ms"], 1e-9) / 1e3) / 1e9,
+                                 "svsig_gcups": kern_gcups,
+                                 "svr_svsig_gcups": acc["cells"] / (max(acc["dp_ms"], 1e-9) / 1e3) / 1e9},
+            "svsig_launch_classes": classes,
             "roofline": {"bound": "int-issue", "kernel": "ksw_dp_overlap_kernel (single-CTA classes; ksw_dp_kernel for cluster classes)", "achieved": kern_gcups, "peak": int_peak,
                          "unit": "GCUPS", "frac": kern_gcups / int_peak,
                          "peak_def": f"{n_sm} SMs x 128 lanes x {f_mhz:.0f} MHz (median under load) / {OPS_PER_CELL} ops per cell x "
                                      f"{LANES_PACKED} cells per 32-bit op (SURVEY.md 8d)",
                          "avg_launch_ms": acc["sig_dp_ms"] / max(1, acc["sig_launches"]), "launches": int(acc["sig_launches"]),
-                         "launch_note": "the launch classes of one batch run concurrently on side streams; achieved = cells of the "
-                                        "qx2svsig batch / CUDA-event time around all of its ksw_dp_kernel launches",
-                         # profiles/r1_ncu_summary.md: 406.8 GB of DRAM traffic for 395.5 G cells in one ncu --set full capture
-                         "traffic": 1.029 * acc["sig_cells"] / max(1, acc["sig_launches"]) / 1e9, "traffic_unit": "GB per launch",
-                         "traffic_note": "dram__bytes_read+write per cell from the ncu capture (1.029 B/cell) x cells per launch; algorithmic = 1 B/cell",
+                         "launch_note": "the launch classes of one batch run concurrently (chained by programmatic dependent launch); achieved = "
+                                        "cells of the qx2svsig batch / CUDA-event time around all of its K-ksw launches; per class: svsig_launch_classes",
+                         # profiles/r2_ncu_summary.md: 203.4 GB of DRAM traffic for 197.75 G cells in one ncu --set full capture
+                         "traffic": 1.028 * acc["sig_cells"] / max(1, acc["sig_launches"]) / 1e9, "traffic_unit": "GB per launch",
+                         "traffic_note": "dram__bytes_read+write per cell from the ncu capture (1.028 B/cell) x cells per launch; algorithmic = 1 B/cell",
                          "hbm": {"achieved": kern_gcups, "peak": hbm_peak, "unit": "GB/s", "frac": kern_gcups / hbm_peak,
                                  "note": "1 traceback byte per DP cell, written once (of measured copy bandwidth)"}},
             "index_build_ms": index_ms,
-            "per_step": {k: r[k] for k in ("hsps", "sv_reads", "svr_jobs", "reads_ok", "signatures")},
+            "n_unsupported": int(acc["n_unsupported"]),
+            "per_step": {k: r[k] for k in ("hsps", "sv_reads", "svr_jobs", "reads_ok", "signatures")} if n_done else {},
         }
-        if not args.no_cpu_baseline and world == 1:
-            n_sample = max(4 * cores, 16)
-            base = cpu_baseline(ref, reads[:n_sample], cores)
+        if c3:
+            line["index"] = {"subject_bases": int(subject_bases), "contigs": len(subj["sizes"]), "build_ms": index_ms}
+        if not args.no_cpu_baseline and world == 1 and not c3:
+            n_sample = sample_size(cores)
+            keep = {}
+            sample_reads = batches[0].reads[:n_sample]
+            base = cpu_baseline(ref, sample_reads, cores, keep)
             if base is not None:
                 line["cpu_baseline"] = base
+                ours = run_path(ctx, capi, Batch(sample_reads, capi), subj, collect=True)      # outside the timed region
+                line["parity"] = parity_block(ours["records"], keep)
+        extras = [x for x in args.extra.split(",") if x and x != "none"]
+        if world == 1 and "c5" in extras:
+            line["extra"] = {"c5": c5_block(ctx, capi, cores, args.seed, n_sm, f_mhz)}
         _emit(line)
     ctx.close()
     if world > 1:

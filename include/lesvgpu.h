@@ -51,6 +51,18 @@ typedef struct {
     uint64_t dp_cells;       /* DP cells of all ksw_extd2 invocations of the call (lesvgpu_ksw_cells), failed-then-retried ones included */
 } lesvgpu_timing;
 void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t);
+/* Launch classes of the last K-ksw batch (lesvgpu_ksw_batch, lesvgpu_align_refine_batch, lesvgpu_svsig_batch; for
+ * lesvgpu_svr_batch: of its last alignment round).  The classes of a batch run concurrently on one GPU, so
+ * done_ms is the time from the start of the first launch to the moment this class had finished. */
+typedef struct {
+    int ctas_per_alignment;  /* 1 = single CTA, 2..16 = thread-block cluster, 0 = global-memory fallback, -1 = column strips */
+    int threads;             /* CTA size class (DP threads)                                          */
+    int n_alignments;
+    int n_ctas;              /* persistent CTAs (clusters) launched                                  */
+    uint64_t cells;
+    float done_ms;
+} lesvgpu_class_timing;
+int lesvgpu_last_class_timing(const lesvgpu_ctx* ctx, lesvgpu_class_timing* out, int cap);   /* returns the number of classes */
 /* Kernels this process has launched through the library so far (all contexts, all stages). */
 uint64_t lesvgpu_launch_count(void);
 
@@ -165,6 +177,17 @@ typedef struct {            /* CSeqInfo.seq_offset / .seq_size, corelib/seqdb.h:
     uint64_t seq_offset;
     uint64_t seq_size;
 } lesvgpu_seq;
+
+/* lesvgpu_svsig_batch over SvReads of SEVERAL contigs in one call: reads[i].subject_id indexes subject_seqs[]
+ * (the reference loops over contigs, find_sv_signature.c:383-411; a contig with few placed reads is a batch too
+ * small to fill a GPU, and a multi-GPU driver wants sub-batches of even cost, not contigs).  Each signature carries
+ * its read's contig in the extra array *sig_subject (library-owned, parallel to *sigs). */
+int lesvgpu_svsig_batch_contigs(lesvgpu_ctx* ctx,
+                                const uint8_t* query_pac, const size_t* query_read_offset,
+                                const lesvgpu_seq* subject_seqs, int n_subject,
+                                const lesvgpu_svread* reads, int n, int min_indel_size,
+                                const char* trf_mask,
+                                lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, const int** sig_subject, int* n_sigs);
 
 /* ---- qx2svr: one trusted placement per read ------------------------------------------------------
  * lesvgpu_svr_batch stands in, over the M4Record array of one query volume, for the worker loop

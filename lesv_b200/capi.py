@@ -33,6 +33,11 @@ class Timing(C.Structure):
                 ("dp_cells", C.c_uint64)]
 
 
+class ClassTiming(C.Structure):
+    _fields_ = [("ctas_per_alignment", C.c_int), ("threads", C.c_int), ("n_alignments", C.c_int), ("n_ctas", C.c_int),
+                ("cells", C.c_uint64), ("done_ms", C.c_float)]
+
+
 _lib = None
 
 
@@ -69,6 +74,13 @@ class Context:
             raise RuntimeError(f"lesvgpu_ctx_create(device={device}) failed with status {rc} "
                                "(no B200 / sm_100 GPU visible?)")
         self.h = h
+
+    def class_timing(self):
+        """Launch classes of the last K-ksw batch: list of dicts (shape, alignments, cells, done_ms)."""
+        self.lib.lesvgpu_last_class_timing.argtypes = [C.c_void_p, C.POINTER(ClassTiming), C.c_int]
+        arr = (ClassTiming * 32)()
+        n = min(32, self.lib.lesvgpu_last_class_timing(self.h, arr, 32))
+        return [{f: getattr(arr[i], f) for f, _ in ClassTiming._fields_} for i in range(n)]
 
     def close(self):
         if self.h:
@@ -242,6 +254,39 @@ def svsig_batch_raw(ctx: "Context", query_pac, query_read_offset, subject_seq_of
         raise RuntimeError(f"lesvgpu_svsig_batch failed ({rc}): {ctx.error()}")
     status = np.frombuffer(per, dtype=np.int32).reshape(-1, 9)[:n, 0].copy()
     return status, n_sigs.value
+
+
+SVSIG_DTYPE = np.dtype([(n, np.int32) for n in ("qid", "qdir", "qfrom", "qto", "fqfrom", "fqto", "qsize", "sfrom", "sto",
+                                               "fsfrom", "fsto", "ssize", "type")])           # lesvgpu_svsig, 52 bytes
+
+
+def svsig_contigs_raw(ctx: "Context", query_pac, query_read_offset, subject_seqs, n_subject, reads: np.ndarray, min_indel: int,
+                      want_sigs: bool = False):
+    """lesvgpu_svsig_batch_contigs over a SVREAD_DTYPE array whose subject_id indexes subject_seqs (a _seq_array()).
+    Returns (status array, n_signatures[, signature array (SVSIG_DTYPE), contig of every signature])."""
+    lib = ctx.lib
+    lib.lesvgpu_svsig_batch_contigs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Seq), C.c_int, C.POINTER(SvRead), C.c_int,
+                                                C.c_int, C.c_void_p, C.POINTER(SvSigRead), C.POINTER(C.POINTER(SvSig)),
+                                                C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_int)]
+    reads = np.ascontiguousarray(reads)
+    assert reads.dtype == SVREAD_DTYPE
+    n = len(reads)
+    per = (SvSigRead * max(1, n))()
+    sigs, sid, n_sigs = C.POINTER(SvSig)(), C.POINTER(C.c_int)(), C.c_int()
+    rc = lib.lesvgpu_svsig_batch_contigs(ctx.h, query_pac.ctypes.data, query_read_offset.ctypes.data, subject_seqs, n_subject,
+                                         C.cast(reads.ctypes.data, C.POINTER(SvRead)), n, min_indel, None, per, C.byref(sigs),
+                                         C.byref(sid), C.byref(n_sigs))
+    if rc != OK:
+        raise RuntimeError(f"lesvgpu_svsig_batch_contigs failed ({rc}): {ctx.error()}")
+    status = np.frombuffer(per, dtype=np.int32).reshape(-1, 9)[:n, 0].copy()
+    if not want_sigs:
+        return status, n_sigs.value
+    if n_sigs.value == 0:
+        return status, 0, np.zeros(0, dtype=SVSIG_DTYPE), np.zeros(0, dtype=np.int32)
+    assert C.sizeof(SvSig) == SVSIG_DTYPE.itemsize
+    buf = (C.c_char * (n_sigs.value * SVSIG_DTYPE.itemsize)).from_address(C.addressof(sigs.contents))
+    sb = (C.c_int * n_sigs.value).from_address(C.addressof(sid.contents))
+    return status, n_sigs.value, np.frombuffer(buf, dtype=SVSIG_DTYPE).copy(), np.frombuffer(sb, dtype=np.int32).copy()
 
 
 def map_batch_raw(ctx: "Context", query_pac, seq_arr, qfrom, qto, hitlist_size=3, max_hsps=5):

@@ -72,6 +72,8 @@ struct lesvgpu_ctx {
     cudaEvent_t ev[8] = {};
     std::string err;
     lesvgpu_timing timing = {};
+    std::vector<lesvgpu_class_timing> classes;    // launch classes of the last K-ksw batch
+    std::vector<cudaEvent_t> class_ev;            // one event behind every class launch (grown on demand)
     DevBuf<uint8_t> d_raw, d_arena, d_subject;
     size_t subject_bytes = 0;
     DevBuf<uint32_t> d_pool, d_cigar, d_scratch;
@@ -88,6 +90,7 @@ struct lesvgpu_ctx {
     PinBuf<lesvksw::KswOut> h_outs;
     PinBuf<lesvksw::KswGapRun> h_runs;
     std::vector<lesvgpu_svsig> sigs;
+    std::vector<int> sig_subject;                 // contig of every record in sigs (lesvgpu_svsig_batch_contigs)
     std::vector<lesvgpu_svread> svreads;          // result of lesvgpu_svr_batch
     lesvmap_state* map = nullptr;                 // index + scratch of the mapping stages
 };

@@ -1,7 +1,7 @@
 // gpu_prims.cu -- exclusive scan and stable LSD radix sort (see gpu_prims.cuh).
 #include "gpu_prims.cuh"
 
-unsigned long long g_lesv_launches = 0;
+std::atomic<unsigned long long> g_lesv_launches{0};   // several feeder threads (one per GPU) count here
 
 namespace lesvmap {
 

@@ -10,7 +10,8 @@
 #include <cuda_runtime.h>
 
 // kernels launched by the mapper stages of this process (lesvgpu_launch_count, include/lesvgpu.h)
-extern unsigned long long g_lesv_launches;
+#include <atomic>
+extern std::atomic<unsigned long long> g_lesv_launches;
 
 namespace lesvmap {
 

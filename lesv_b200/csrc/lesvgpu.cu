@@ -67,6 +67,7 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->side_done) cudaEventDestroy(e);
+    for (auto& e : ctx->class_ev) cudaEventDestroy(e);
     for (auto& st : ctx->side) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     if (ctx->map) lesvmap_state_free(ctx->map);
@@ -76,6 +77,13 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
 extern "C" uint64_t lesvgpu_launch_count(void) { return g_lesv_launches; }
 extern "C" const char* lesvgpu_last_error(const lesvgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t) { if (ctx && t) *t = ctx->timing; }
+extern "C" int lesvgpu_last_class_timing(const lesvgpu_ctx* ctx, lesvgpu_class_timing* out, int cap)
+{
+    if (!ctx) return 0;
+    const int n = (int)ctx->classes.size();
+    for (int i = 0; i < n && i < cap && out; ++i) out[i] = ctx->classes[i];
+    return n;
+}
 
 static inline int effective_band(int qlen, int tlen, int max_distance)
 {
@@ -407,6 +415,11 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     if (want_cigar) CK(ctx->h_cigar.reserve(cigar_words));
     if (want_runs) CK(ctx->h_runs.reserve((size_t)nj * kSigCap));
 
+    while (ctx->class_ev.size() < launches.size() + sgroups.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        ctx->class_ev.push_back(e);
+    }
     cudaStream_t s = ctx->stream;
     const auto t_planned = std::chrono::steady_clock::now();
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -442,6 +455,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                               ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
                               ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls, chained));
                 chained = true;
+                CK(cudaEventRecord(ctx->class_ev[li], ls));
             } else {
                 cudaStream_t ws = ctx->side[1];
                 if (!wide_used) CK(cudaStreamWaitEvent(ws, ctx->ev[2], 0));
@@ -450,6 +464,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                                 ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
                                 L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ws);
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(ctx->class_ev[li], ws));
             }
         }
         if (!sjobs.empty()) {                           // one launch per group, in order, on their own stream
@@ -460,6 +475,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                 CK(launch_ksw_strips(g.n_ctas, ksw_smem_bytes(strip_smem_q, strip_smem_t), ctx->d_jobs.p, ctx->d_sjobs.p + g.first, g.count,
                                      ctx->d_pool.p, ctx->d_arena.p, ctx->d_edges.p, ctx->d_sprog.p, ctx->d_cigar.p, ctx->d_runs.p,
                                      ctx->d_outs.p, ctx->d_counter.p + launches.size() + gi, ss));
+                CK(cudaEventRecord(ctx->class_ev[launches.size() + gi], ss));
             }
             CK(cudaEventRecord(ctx->side_done[2], ss));
             CK(cudaStreamWaitEvent(s, ctx->side_done[2], 0));
@@ -502,6 +518,26 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         }
         if (!sjobs.empty()) fprintf(stderr, "[ksw debug] strips: %zu alignments, %zu strips in %zu group(s)\n", strip_ids.size(), sjobs.size(), sgroups.size());
         fprintf(stderr, "[ksw debug] all launches: %.1f ms\n", total);
+    }
+    ctx->classes.clear();
+    for (size_t li = 0; li < launches.size() + sgroups.size(); ++li) {
+        lesvgpu_class_timing c = {};
+        if (li < launches.size()) {
+            const Launch& L = launches[li];
+            c.ctas_per_alignment = L.ncta; c.threads = L.nt; c.n_alignments = L.count; c.n_ctas = L.n_clusters;
+            for (int k : L.ids) c.cells += (uint64_t)cells_fast(jobs[k].qlen, jobs[k].tlen, jobs[k].w);
+        } else {
+            const StripGroup& g = sgroups[li - launches.size()];
+            c.ctas_per_alignment = -1; c.threads = kStripBlocks; c.n_ctas = g.n_ctas;
+            for (int x = g.first; x < g.first + g.count; ++x)
+                if (sjobs[x].s == 0) {
+                    ++c.n_alignments;
+                    const KswJob& J = jobs[sjobs[x].jid];
+                    c.cells += (uint64_t)cells_fast(J.qlen, J.tlen, J.w);
+                }
+        }
+        cudaEventElapsedTime(&c.done_ms, ctx->ev[2], ctx->class_ev[li]);
+        ctx->classes.push_back(c);
     }
     lesvgpu_timing& T = ctx->timing;
     cudaEventElapsedTime(&T.h2d_ms, ctx->ev[0], ctx->ev[1]);
@@ -576,20 +612,26 @@ extern "C" int lesvgpu_subject_load(lesvgpu_ctx* ctx, const uint8_t* subject_pac
     return LESVGPU_OK;
 }
 
-extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
-                                   const uint8_t* query_pac, const size_t* query_read_offset,
-                                   size_t subject_seq_offset, int subject_size,
-                                   const lesvgpu_svread* reads, int n, int min_indel_size,
-                                   const char* trf_mask,
-                                   lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs)
+// Body of lesvgpu_svsig_batch / lesvgpu_svsig_batch_contigs.  one_contig: every read lies on subject_seqs[0]
+// whatever its subject_id says (the single-contig entry point takes the contig's offset and size, not a table).
+static int svsig_core(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,
+                      const lesvgpu_seq* subject_seqs, int n_subject, bool one_contig,
+                      const lesvgpu_svread* reads, int n, int min_indel_size, const char* trf_mask,
+                      lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs)
 {
-    if (!ctx || n < 0 || (n && (!reads || !per_read || !query_pac || !query_read_offset))) return LESVGPU_E_ARG;
+    if (!ctx || n < 0 || (n && (!reads || !per_read || !query_pac || !query_read_offset)) || !subject_seqs || n_subject <= 0) return LESVGPU_E_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LESVGPU_E_CUDA;
     if (!ctx->subject_bytes) { ctx->err = "lesvgpu_subject_load has not been called"; return LESVGPU_E_ARG; }
     ctx->timing = lesvgpu_timing{};
     ctx->sigs.clear();
+    ctx->sig_subject.clear();
     if (sigs) *sigs = nullptr;
     if (n_sigs) *n_sigs = 0;
+    for (int i = 0; i < n && !one_contig; ++i)
+        if (reads[i].subject_id < 0 || reads[i].subject_id >= n_subject) {
+            ctx->err = "SvRead names a contig the subject table does not have"; return LESVGPU_E_ARG;
+        }
+    auto contig_of = [&](const lesvgpu_svread& S) -> const lesvgpu_seq& { return subject_seqs[one_contig ? 0 : S.subject_id]; };
     std::vector<KswJob> jobs;
     std::vector<int> job_read;
     jobs.reserve(n); job_read.reserve(n);
@@ -600,8 +642,10 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
         lesvgpu_svsig_read& R = per_read[i];
         memset(&R, 0, sizeof R);
         const lesvgpu_svread& S = reads[i];
+        const size_t subject_seq_offset = contig_of(S).seq_offset;
+        const int subject_size = (int)contig_of(S).seq_size;
         const int qn = S.qend - S.qoff, sn = S.send - S.soff;
-        if (qn <= 0 || sn <= 0 || S.qend > S.qsize || S.send > subject_size || S.qoff < 0 || S.soff < 0) {
+        if (qn <= 0 || sn <= 0 || S.qend > S.qsize || S.send > subject_size || S.qoff < 0 || S.soff < 0 || S.query_id < 0) {
             ctx->err = "SvRead range outside its sequence"; return LESVGPU_E_ARG;
         }
         if (!query_read_offset[S.query_id]) { ctx->err = "read not loaded (raw_read_offset_array == 0)"; return LESVGPU_E_ARG; }
@@ -688,6 +732,8 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
         R.eff_mat = O.eff_mat; R.eff_len = O.eff_len;
         if (O.status != 1 || O.n_cigar <= 0) { R.status = 0; continue; }
         if (!O.trunc_ok) { R.status = -1; continue; }
+        const size_t subject_seq_offset = contig_of(S).seq_offset;
+        const int subject_size = (int)contig_of(S).seq_size;
         const int fqb = O.qb + S.qoff, fqe = O.qe + S.qoff;          // :334-337 (forward qoff even for REV)
         const int fsb = O.sb + S.soff, fse = O.se + S.soff;
         if (trf_mask) {                                              // fall_in_trf_subseq, trf_array.cpp:74-83
@@ -709,11 +755,38 @@ extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
             v.fsfrom = fsb; v.fsto = fse; v.ssize = subject_size;
             v.type = g[x].type;
             ctx->sigs.push_back(v);
+            ctx->sig_subject.push_back(one_contig ? 0 : S.subject_id);
         }
     }
     if (sigs) *sigs = ctx->sigs.data();
     if (n_sigs) *n_sigs = (int)ctx->sigs.size();
     return LESVGPU_OK;
+}
+
+extern "C" int lesvgpu_svsig_batch(lesvgpu_ctx* ctx,
+                                   const uint8_t* query_pac, const size_t* query_read_offset,
+                                   size_t subject_seq_offset, int subject_size,
+                                   const lesvgpu_svread* reads, int n, int min_indel_size,
+                                   const char* trf_mask,
+                                   lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, int* n_sigs)
+{
+    lesvgpu_seq one;
+    one.seq_offset = subject_seq_offset; one.seq_size = (uint64_t)(subject_size > 0 ? subject_size : 0);
+    return svsig_core(ctx, query_pac, query_read_offset, &one, 1, true, reads, n, min_indel_size, trf_mask, per_read, sigs, n_sigs);
+}
+
+extern "C" int lesvgpu_svsig_batch_contigs(lesvgpu_ctx* ctx,
+                                           const uint8_t* query_pac, const size_t* query_read_offset,
+                                           const lesvgpu_seq* subject_seqs, int n_subject,
+                                           const lesvgpu_svread* reads, int n, int min_indel_size,
+                                           const char* trf_mask,
+                                           lesvgpu_svsig_read* per_read, const lesvgpu_svsig** sigs, const int** sig_subject, int* n_sigs)
+{
+    if (sig_subject) *sig_subject = nullptr;
+    const int rc = svsig_core(ctx, query_pac, query_read_offset, subject_seqs, n_subject, false, reads, n, min_indel_size, trf_mask,
+                              per_read, sigs, n_sigs);
+    if (rc == LESVGPU_OK && sig_subject && ctx) *sig_subject = ctx->sig_subject.data();
+    return rc;
 }
 
 extern "C" int lesvgpu_align_refine_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, const size_t* query_read_offset,

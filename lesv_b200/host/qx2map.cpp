@@ -9,10 +9,15 @@
 // Files: <db_dir>/{query,subject}.* (lesv_dbbuild.hpp), <db_dir>/backup_results/stagebackup_results_Q%08d_D%08d
 // [+ .mapped], exactly as hbn_job_control.c:4-92 names them, so qx2m4x / qx2svr run on the result unchanged.
 // Output order is deterministic (volume, batch, read), where the reference's depends on thread scheduling.
-// Environment: LESV_GPU=<device> (default 0).
+// Several GPUs (lesv_gpus.hpp; LESV_GPUS / LESV_GPU select devices): the index is built on every GPU, the query batches
+// of a volume -- fixed by -query_batch_size alone, so the query-side occurrence filter sees the same reads whatever the
+// number of GPUs -- are pulled from one queue and written in batch order.  -grid "node_id
+// num_nodes" still shards whole query volumes over processes / nodes.
 #include "../../include/lesvgpu.h"
 #include "lesv_dbbuild.hpp"
+#include "lesv_gpus.hpp"
 
+#include <mutex>
 #include <string>
 #include <time.h>
 
@@ -226,9 +231,8 @@ int main(int argc, char** argv)
     FILE* out = o.output == "-" ? stdout : fopen(o.output.c_str(), "w");
     if (!out) die("cannot open " + o.output);
 
-    const int dev = getenv("LESV_GPU") ? atoi(getenv("LESV_GPU")) : 0;
-    lesvgpu_ctx* ctx = nullptr;
-    if (lesvgpu_ctx_create(dev, 0, &ctx) != LESVGPU_OK) die("no usable sm_100 GPU (there is no CPU path)");
+    lesvgpus::Pool gpus;
+    gpus.open();
     phase("create GPU context", t0);
     lesvgpu_map_opts mo;
     memset(&mo, 0, sizeof mo);
@@ -248,9 +252,11 @@ int main(int argc, char** argv)
         const Volume sv = load_volume(o.db_dir, "subject", svid);
         std::vector<lesvgpu_seq> sseqs(sv.seqs.size());
         for (size_t i = 0; i < sv.seqs.size(); ++i) { sseqs[i].seq_offset = sv.seqs[i].seq_offset; sseqs[i].seq_size = sv.seqs[i].seq_size; }
-        if (lesvgpu_subject_load(ctx, sv.pac.data(), sv.pac.size()) != LESVGPU_OK ||
-            lesvgpu_index_build(ctx, sseqs.data(), (int)sseqs.size(), o.kmer_size, o.kmer_window, o.max_kmer_occ) != LESVGPU_OK)
-            die(std::string("index build failed: ") + lesvgpu_last_error(ctx));
+        gpus.each([&](int g) {
+            if (lesvgpu_subject_load(gpus.ctx[g], sv.pac.data(), sv.pac.size()) != LESVGPU_OK ||
+                lesvgpu_index_build(gpus.ctx[g], sseqs.data(), (int)sseqs.size(), o.kmer_size, o.kmer_window, o.max_kmer_occ) != LESVGPU_OK)
+                die(std::string("index build failed: ") + lesvgpu_last_error(gpus.ctx[g]));
+        });
         phase("load subject volume + build index", t0);
         for (int qvid = o.node_id; qvid < nqv; qvid += o.num_nodes) {
             const std::string rpath = results_path(o, qvid, svid);
@@ -264,9 +270,8 @@ int main(int argc, char** argv)
             FILE* backup = fopen(rpath.c_str(), "w");
             if (!backup) die("cannot open " + rpath);
             const int nq = (int)qseqs.size();
-            int to = 0;
-            std::string text;
-            while (to < nq) {                           // get_next_batch_query_qidx_range, hbn_align_one_volume.c:56-84
+            std::vector<std::pair<int, int>> batches;
+            for (int to = 0; to < nq;) {                // get_next_batch_query_qidx_range, hbn_align_one_volume.c:56-84
                 const int from = to;
                 size_t curr = qseqs[from].seq_size;
                 to = from + 1;
@@ -274,7 +279,17 @@ int main(int argc, char** argv)
                 const size_t min_batch = (size_t)(o.query_batch_size * 0.2);
                 left -= curr;
                 if (left <= min_batch) { to = nq; left = 0; }
-                text.clear();
+                batches.emplace_back(from, to);
+            }
+            // results are written in batch order as soon as every earlier batch has been written (bounded memory with -cigar)
+            std::vector<std::string> texts(batches.size());
+            std::vector<char> ready(batches.size(), 0);
+            std::mutex write_mutex;
+            size_t next_write = 0;
+            gpus.queue((int)batches.size(), [&](int g, int bi) {
+                lesvgpu_ctx* ctx = gpus.ctx[g];
+                const int from = batches[bi].first, to = batches[bi].second;
+                std::string& text = texts[bi];
                 if (o.outfmt == "subseq") {
                     const lesvgpu_subseq_hit* w = nullptr;
                     const int* first = nullptr;
@@ -296,16 +311,22 @@ int main(int argc, char** argv)
                     for (int x = 0; x < first[to - from]; ++x)
                         format_hsp(o, hsps[x], pool ? pool + hsps[x].ops_off : nullptr, qv, sv, text);
                 }
-                fwrite(text.data(), 1, text.size(), out);
-                fwrite(text.data(), 1, text.size(), backup);
-                phase("map one query batch", t0);
-            }
+                std::lock_guard<std::mutex> lock(write_mutex);
+                ready[bi] = 1;
+                while (next_write < texts.size() && ready[next_write]) {
+                    std::string& t = texts[next_write++];
+                    fwrite(t.data(), 1, t.size(), out);
+                    fwrite(t.data(), 1, t.size(), backup);
+                    std::string().swap(t);
+                }
+            });
+            phase("map the query batches of one volume", t0);
             fclose(backup);
             FILE* m = fopen((rpath + ".mapped").c_str(), "w");   // qi_vs_sj_make_mapped
             if (m) fclose(m);
         }
     }
-    lesvgpu_ctx_destroy(ctx);
+    gpus.close();
     if (out != stdout) fclose(out);
     if (!o.keep_db) {                                   // hbn_task_struct_free, hbn_task_struct.c:50-54
         const std::string cmd = "rm -r " + o.db_dir;

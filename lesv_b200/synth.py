@@ -97,6 +97,26 @@ def simulate_reads(sample: np.ndarray, n_reads: int, read_len: int, rng: np.rand
     return reads
 
 
+def reads_with_noisy_tails(ref: np.ndarray, n_reads: int, rng: np.random.Generator, core_len: int = 8000):
+    """Reads whose ends are unrelated sequence (150-2,600 bp) or the true flank at 30-45 % error: edlib's end extension
+    (reference src/algo/hbn_traceback.c:436-486) gives up inside the tail, which leaves an overhang of <= 3 kb, so
+    hbn_traceback's left_extend / right_extend run the DALIGNER wave (:214-311)."""
+    reads = []
+    for i in range(n_reads):
+        s0 = int(rng.integers(1200, len(ref) - core_len - 1000))
+        core = mutate(ref[s0:s0 + core_len], float(rng.uniform(0.08, 0.14)), rng)
+
+        def tail(seg):
+            if int(rng.integers(0, 3)) == 0:
+                return random_codes(int(rng.integers(150, 2600)), rng)
+            return mutate(seg, float(rng.uniform(0.30, 0.45)), rng)
+        left = tail(ref[s0 - 1200:s0]) if i % 3 != 2 else np.zeros(0, np.uint8)
+        right = tail(ref[s0 + core_len:s0 + core_len + 1000]) if i % 3 != 1 else np.zeros(0, np.uint8)
+        rd = np.concatenate([left, core, right])
+        reads.append(revcomp_codes(rd) if i % 2 else rd)
+    return reads
+
+
 def write_fasta(path: str, names, seqs, width: int = 0) -> None:
     with open(path, "wb") as f:
         for name, s in zip(names, seqs):

@@ -139,7 +139,7 @@ def test_map_batch_equals_golden_m4_with_cigars(ctx):
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(H.ROOT, "oracle", "_ref", "bin", "qx2map")), reason="oracle/_ref not built")
-@pytest.mark.parametrize("case", ["reads10k", "contigs5_svs", "skip_overhang"])
+@pytest.mark.parametrize("case", ["reads10k", "contigs5_svs", "skip_overhang", "noisy_tails"])
 def test_map_batch_against_fresh_reference_run(ctx, tmp_path, case):
     import refmap
     from lesv_b200 import capi, synth
@@ -150,6 +150,13 @@ def test_map_batch_against_fresh_reference_run(ctx, tmp_path, case):
     elif case == "contigs5_svs":
         synth.make_dataset(work, ref_len=1_500_000, n_reads=50, read_len=20000, n_events=30, seed=42, n_contigs=5,
                            err_lo=0.08, err_hi=0.16)
+    elif case == "noisy_tails":
+        # junk / 30-45 % error read ends: the overhang step of hbn_traceback (left_extend / right_extend with the
+        # DALIGNER wave, hbn_traceback.c:170-311) must run on the GPU and reproduce the reference's HSP ends and CIGARs
+        ref = synth.random_codes(800_000, np.random.default_rng(44))
+        reads = synth.reads_with_noisy_tails(ref, 60, np.random.default_rng(45))
+        synth.write_fasta(os.path.join(work, "ref.fa"), ["chrT"], [ref], width=0)
+        synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
     else:
         extra = ["-skip_overhang"]
         synth.make_dataset(work, ref_len=600_000, n_reads=40, read_len=6000, n_events=10, seed=43, n_contigs=2)
@@ -163,6 +170,13 @@ def test_map_batch_against_fresh_reference_run(ctx, tmp_path, case):
     got = m4_lines(res, Q, S)
     assert len(exp) >= Q.num_seqs // 2
     assert got == exp
+    n_wave = sum(1 for lst in res for h in lst if h["flags"] & 3)       # lesvgpu_hsp.flags: the wave ran left (1) / right (2)
+    if case == "noisy_tails":
+        assert n_wave >= 10, n_wave
+        assert any(h["flags"] & 1 for lst in res for h in lst) and any(h["flags"] & 2 for lst in res for h in lst)
+    if case == "skip_overhang":
+        assert n_wave == 0
+    assert capi.map_last_extend_timing(ctx).n_unsupported == 0
     shutil.rmtree(work, ignore_errors=True)
 
 

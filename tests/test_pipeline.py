@@ -141,3 +141,97 @@ def test_four_tools_on_named_configs(tmp_path, scenario):
     assert "svr:" in out and "svsig:" in out and out.count("all files identical: True") == 2, out
     n_m4 = int(out.split("m4: reference ")[1].split(" ")[0])
     assert n_m4 >= {"c1": 2000, "k19": 100, "repeats": 300, "c3": 40}[scenario]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2map")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scenario", ["bigsv", "trf", "minindel", "tails", "c4"])
+def test_four_tools_on_reference_branches(tmp_path, scenario):
+    """More of tools/parity_probe.py, one reference branch each:
+    bigsv    = 50 kb reads across 6-10 kb INS/DEL: qx2svsig bands of 10-20 k, the 2-CTA-cluster launch class at real size;
+    trf      = a TRF bed file as 8th / 7th argument of qx2svr / qx2svsig (trf_array.cpp:10-83);
+    minindel = qx2svsig with min_indel_size 1: hundreds of records per read (more than the kernel keeps per alignment);
+    tails    = junk and 30-45 % error read ends: the overhang step of hbn_traceback (DALIGNER wave);
+    c4       = BASELINE.json configs[3] shape: 150 kb+ reads -> qx2splitseq 50000 0 20000 -> -kmer_size 19 -kmer_window 20,
+               a third of the reads at 20-30 % error, SVR identity 80.0 (README.md:164-172)."""
+    env = dict(os.environ, BIGSV_READS="16", C4_READS="8", C4_REF_MBP="8", REF_MAP_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "parity_probe.py"), scenario, str(tmp_path)],
+                         check=True, capture_output=True, text=True, env=env).stdout
+    assert "m4: reference" in out and ", identical True" in out, out
+    assert "svr:" in out and "svsig:" in out and out.count("all files identical: True") == 2, out
+    n_m4 = int(out.split("m4: reference ")[1].split(" ")[0])
+    n_svr = int(out.split("svr: ")[1].split(" ")[0])
+    n_sig = int(out.split("svsig: ")[1].split(" ")[0])
+    assert n_m4 >= {"bigsv": 16, "trf": 90, "minindel": 90, "tails": 70, "c4": 25}[scenario], out
+    if scenario == "bigsv":
+        assert n_sig >= 8, out                     # the planted 6-10 kb events are found
+    if scenario == "trf":
+        assert 40 <= n_svr <= 140, out             # 90 reads without the mask = 180 lines (Q + subject files)
+    if scenario == "minindel":
+        assert n_sig > 64 * 90, out
+    if scenario == "c4":
+        assert "splitseq: identical True" in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2map")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scenario", ["m4x", "md"])
+def test_qx2map_output_formats(tmp_path, scenario):
+    """qx2map -outfmt m4x (binary M4Record stream on stdout and in the backup file, mecat_results.c:281-297) and
+    -cigar -md (MD:Z: column, mecat_results.c:86-135) against the reference's output."""
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "parity_probe.py"), scenario, str(tmp_path)],
+                         check=True, capture_output=True, text=True).stdout
+    if scenario == "m4x":
+        assert "identical True; backup files identical True" in out, out
+        assert int(out.split("m4x: reference ")[1].split(" ")[0]) >= 90, out
+    else:
+        assert "identical True" in out and int(out.split("lines (")[1].split(" ")[0]) >= 90, out
+
+
+def _tree(work, dirs):
+    out = {}
+    for d in dirs:
+        for f in sorted(os.listdir(os.path.join(work, d))):
+            path = os.path.join(work, d, f)
+            if os.path.isfile(path):
+                out[d + "/" + f] = open(path, "rb").read()
+    return out
+
+
+@pytest.mark.gpu
+def test_tools_write_the_same_files_for_any_number_of_feeders(tmp_path):
+    """One host process, one feeder thread per GPU pulling sub-batches from a shared queue (lesv_b200/host/lesv_gpus.hpp).
+    LESV_GPUS=0 against LESV_GPUS=0,0,0 (three contexts and feeder threads; on a multi-GPU box also 0,1) with small
+    sub-batches, so that every tool really has several queue items: all output files must be byte-identical, and
+    equal to the golden run of the reference."""
+    import ctypes as C
+    from lesv_b200 import capi
+    n_dev = capi.load().lesvgpu_device_count()
+    lists = ["0", "0,0,0"] + (["0,1"] if n_dev >= 2 else [])
+    trees = []
+    for gi, gl in enumerate(lists):
+        work = str(tmp_path / f"g{gi}")
+        os.makedirs(work)
+        shutil.copy(os.path.join(GOLD, "reads.fa"), os.path.join(work, "split.fa"))
+        shutil.copy(os.path.join(GOLD, "ref.fa"), os.path.join(work, "ref.fa"))
+        env = dict(os.environ, LESV_GPUS=gl, LESV_SVSIG_BATCH="7", LESV_SVR_CHUNK="5")
+        env.pop("LESV_GPU", None)
+        with open(os.path.join(work, "gpu.map.m4"), "wb") as f, open(os.path.join(work, "gpu.log"), "ab") as log:
+            subprocess.run([os.path.join(BIN, "qx2map"), "-max_target_seqs", "5", "-max_hsps", "10", "-query_batch_size", "20k",
+                            "-db_dir", "db_gpu", "-keep_db", "split.fa", "ref.fa"], cwd=work, check=True, stdout=f, stderr=log, env=env)
+            subprocess.run([os.path.join(BIN, "qx2m4x"), "db_gpu"], cwd=work, check=True, stderr=log)
+            subprocess.run([os.path.join(BIN, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", "4"], cwd=work, check=True, stderr=log, env=env)
+            subprocess.run([os.path.join(BIN, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", "4"], cwd=work, check=True, stderr=log, env=env)
+        log = open(os.path.join(work, "gpu.log"), errors="replace").read()
+        assert f"on {len(gl.split(','))} GPU(s)" in log, log
+        t = _tree(work, ["svr_gpu", "svsig_gpu", "db_gpu/backup_results"])
+        t["map.m4"] = open(os.path.join(work, "gpu.map.m4"), "rb").read()
+        trees.append(t)
+        if gi == 0:            # against the reference's golden files (query batches of 20 kb: same reads per batch for every GPU count)
+            n, n_sig = _compare_pipeline(work, os.path.join(GOLD, "db"), os.path.join(GOLD, "map.m4"), os.path.join(GOLD, "svr"),
+                                         os.path.join(GOLD, "svsig"))
+            assert n == 60 and n_sig >= 5
+    for t in trees[1:]:
+        assert t.keys() == trees[0].keys()
+        for k in t:
+            assert t[k] == trees[0][k], k

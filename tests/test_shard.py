@@ -34,6 +34,21 @@ def _worker(rank, world, port, n_vol, out):
     assert bases == 1e6 * world * (world + 1) / 2 and cells == 2e9 * world * (world + 1) / 2
     assert launches == sum(10 + r for r in range(world))
     assert shard.read_seed_of_rank(7, rank) != shard.read_seed_of_rank(7, (rank + 1) % world)
+    hi, mean, lo = shard.spread(10.0 + 4 * rank, world)
+    assert (hi, mean, lo) == (10.0 + 4 * (world - 1), 10.0 + 2 * (world - 1), 10.0)
+    # the shared work queue: every sub-batch exactly once over both ranks, whoever asks first
+    q = shard.WorkQueue(23, world)
+    got = []
+    while True:
+        i = q.next()
+        if i is None:
+            break
+        got.append(i)
+    assert got == sorted(got)
+    seen = torch.zeros(23, dtype=torch.int64)
+    seen[got] = 1
+    dist.all_reduce(seen, op=dist.ReduceOp.SUM)
+    assert bool((seen == 1).all()), seen
     dist.barrier()
     if rank == 0:
         out.put(("ok", mine))
@@ -59,3 +74,5 @@ def test_grid_rule_matches_driver_loop():
     assert shard.volumes_of_rank(5, 1, 2) == [1, 3]
     assert shard.volumes_of_rank(2, 3, 4) == []
     assert shard.reduce_stats(1.0, 2.0, 3.0, 4.0, 5.0, 1) == (1.0, 2.0, 3.0, 4.0, 5.0)
+    q = shard.WorkQueue(3, 1)
+    assert [q.next() for _ in range(5)] == [0, 1, 2, None, None]

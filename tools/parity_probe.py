@@ -85,20 +85,7 @@ elif scen in ("trf", "minindel", "m4x", "md"):
             f.write("chrUnknown\t5\t500\n")
 elif scen == "tails":                  # junk / very noisy read ends: edlib's end extension gives up, the DALIGNER wave runs
     ref = synth.random_codes(1_000_000, rng)
-    r2 = np.random.default_rng(21)
-    reads = []
-    for i in range(80):
-        s0 = int(r2.integers(0, len(ref) - 9000))
-        core = synth.mutate(ref[s0:s0 + 8000], float(r2.uniform(0.08, 0.14)), r2)
-        def tail(seg):
-            kind = int(r2.integers(0, 3))
-            if kind == 0:
-                return synth.random_codes(int(r2.integers(150, 2600)), r2)             # unrelated sequence
-            return synth.mutate(seg, float(r2.uniform(0.30, 0.45)), r2)               # the true flank, very noisy
-        left = tail(ref[max(0, s0 - 1200):s0]) if i % 3 != 2 else np.zeros(0, np.uint8)
-        right = tail(ref[s0 + 8000:s0 + 9000]) if i % 3 != 1 else np.zeros(0, np.uint8)
-        rd = np.concatenate([left, core, right])
-        reads.append(synth.revcomp_codes(rd) if i % 2 else rd)
+    reads = synth.reads_with_noisy_tails(ref, 80, np.random.default_rng(21))
     synth.write_fasta(os.path.join(work, "ref.fa"), ["chrT"], [ref], width=0)
     synth.write_fasta(os.path.join(work, "reads.fa"), [f"r{i}" for i in range(len(reads))], reads)
 elif scen == "c4":                     # BASELINE.json configs[3] shape: ultra-long reads split by qx2splitseq 50000 0 20000,
