@@ -73,7 +73,6 @@ struct lesvgpu_ctx {
     std::string err;
     lesvgpu_timing timing = {};
     std::vector<lesvgpu_class_timing> classes;    // launch classes of the last K-ksw batch
-    std::vector<cudaEvent_t> class_ev;            // one event behind every class launch (grown on demand)
     DevBuf<uint8_t> d_raw, d_arena, d_subject;
     size_t subject_bytes = 0;
     DevBuf<uint32_t> d_pool, d_cigar, d_scratch;

@@ -338,6 +338,11 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// KswLaunchSlot behind the work counter: when the first CTA of the launch started, when the last one finished
+__device__ __forceinline__ void stamp_start(int* counter) { atomicMin(reinterpret_cast<unsigned long long*>(counter + 2), global_ns()); }
+__device__ __forceinline__ void stamp_end(int* counter) { atomicMax(reinterpret_cast<unsigned long long*>(counter + 4), global_ns()); }
+
 // kCluster = false: one CTA per alignment, one CTA barrier per anti-diagonal (waiting warps sleep; a polled ring was
 //                   measured slower here: polling lanes burn issue slots of the SMSPs that are the bottleneck).
 // kCluster = true:  one alignment on a thread-block cluster; inside a CTA and across CTAs the carries go through the
@@ -358,6 +363,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     // Programmatic dependent launch: the launch classes of a batch are chained in one stream, each allowed to start
     // as soon as every CTA of the class before it is resident (lesvgpu.cu: run_jobs).  Nothing is waited for.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) stamp_start(counter);
     const uint32_t ncta = kCluster ? cluster_nctarank() : 1u, rank = kCluster ? cluster_ctarank() : 0u;
     // The queue is sorted by decreasing traceback size and cluster i starts with job i, so the arena
     // of cluster i only has to hold job i: everything it pulls later is smaller.
@@ -481,6 +487,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         __syncthreads();
         if (kCluster) cluster_sync_all();
     }
+    if (tid == 0) stamp_end(counter);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -520,7 +527,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
     const int cta = (int)blockIdx.x;
     uint8_t* const arena = arena_base + arena_off[cta];
     const size_t asize = arena_off[cta + 1] - arena_off[cta];
-    if (tid == 0) { wk_posted = 0; wk_done = 0; wk_finished = 0; wk_row = -1; sh_prev_prow = 0; }
+    if (tid == 0) { wk_posted = 0; wk_done = 0; wk_finished = 0; wk_row = -1; sh_prev_prow = 0; stamp_start(counter); }
     __syncthreads();
     if (tid >= ndp) {
         // ---- walker ---------------------------------------------------------------------------------------
@@ -542,6 +549,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
             __syncwarp();
             if (lane == 0) { __threadfence(); wk_done = n + 1; }
         }
+        if (lane == 0) stamp_end(counter);
         return;
     }
     // ---- DP warps ---------------------------------------------------------------------------------------------
@@ -672,12 +680,13 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kStripNT / 32;
     bool first = true;
+    if (tid == 0) stamp_start(counter);
     for (;;) {
         if (tid == 0) sh_job = first ? (int)blockIdx.x : atomicAdd(counter, 1);
         __syncthreads();
         first = false;
         const int si = sh_job;
-        if (si >= n_sjobs) break;
+        if (si >= n_sjobs) { if (tid == 0) stamp_end(counter); break; }
         const StripJob sj = sjobs[si];
         const KswJob job = jobs[sj.jid];
         const int qlen = job.qlen, tlen = job.tlen, w = job.w, tb_blocks = job.tb_blocks;
@@ -804,11 +813,12 @@ ksw_dp_wide_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ orde
     uint8_t* const arena = arena_base + (size_t)blockIdx.x * arena_stride;
     uint32_t* const scratch = scratch_base + (size_t)blockIdx.x * scratch_stride_words;
 
+    if (tid == 0) stamp_start(counter);
     for (;;) {
         if (tid == 0) s_job = atomicAdd(counter, 1);
         __syncthreads();
         const int ji = s_job;
-        if (ji >= njobs) break;
+        if (ji >= njobs) { if (tid == 0) stamp_end(counter); break; }
         const int jid = order[ji];
         const KswJob job = jobs[jid];
         const int qlen = job.qlen, tlen = job.tlen, w = job.w;

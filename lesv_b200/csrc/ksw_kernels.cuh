@@ -70,6 +70,16 @@ __host__ __device__ static inline int window_blocks(int tlen, int w)
     return (cols + 15) / 16 + 3;
 }
 
+// Work counter of one launch plus its first-CTA-started / last-CTA-finished times (globaltimer, ns): the launch classes of
+// a batch overlap inside one stream (programmatic dependent launch), where an event between two launches would serialise
+// them, so the kernels stamp their own times.  Kernels receive &slot.counter.
+struct KswLaunchSlot {
+    int counter;
+    int pad;
+    unsigned long long t_start, t_end;
+};
+constexpr int kLaunchSlotInts = (int)(sizeof(KswLaunchSlot) / sizeof(int));
+
 void launch_pack(const KswJob* d_jobs, int njobs, const uint8_t* d_raw, const uint8_t* d_subject_pac,
                  uint32_t* d_pool, cudaStream_t s);
 

@@ -67,7 +67,6 @@ extern "C" void lesvgpu_ctx_destroy(lesvgpu_ctx* ctx)
     ctx->h_raw.release(); ctx->h_cigar.release(); ctx->h_outs.release(); ctx->h_runs.release();
     for (auto& e : ctx->ev) cudaEventDestroy(e);
     for (auto& e : ctx->side_done) cudaEventDestroy(e);
-    for (auto& e : ctx->class_ev) cudaEventDestroy(e);
     for (auto& st : ctx->side) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     if (ctx->map) lesvmap_state_free(ctx->map);
@@ -335,7 +334,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         --big->n_clusters;
     }
     std::vector<size_t> arena_offs;                 // per launch: n_clusters offsets relative to its arena_off
-    std::vector<int> counters(launches.size());
+    std::vector<KswLaunchSlot> counters(launches.size());
     std::vector<size_t> offs_first(launches.size());
     for (size_t li = 0; li < launches.size(); ++li) {
         const Launch& L = launches[li];
@@ -346,7 +345,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             b += L.ncta == 0 ? L.stride : ((tb_bytes[L.ids[i]] + 255) & ~(size_t)255);
         }
         arena_offs.push_back(b);                         // end of the last arena (ksw_dp_overlap_kernel needs the sizes)
-        counters[li] = L.ncta == 0 ? 0 : L.n_clusters;       // clusters start with jobs 0..n-1
+        counters[li] = KswLaunchSlot{L.ncta == 0 ? 0 : L.n_clusters, 0, ~0ull, 0ull};       // clusters start with jobs 0..n-1
     }
     for (const Launch& L : launches)
         if (L.ncta == 0) scratch_need = std::max(scratch_need, ksw_wide_scratch_words(L.max_slots) * (size_t)L.n_clusters);
@@ -398,7 +397,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         CK(ctx->d_edges.reserve(edge_words));
         CK(ctx->d_sprog.reserve((size_t)prog_ints));
     }
-    for (const StripGroup& g : sgroups) counters.push_back(g.n_ctas);   // work counters of the strip launches (slots launches.size() + group)
+    for (const StripGroup& g : sgroups) counters.push_back(KswLaunchSlot{g.n_ctas, 0, ~0ull, 0ull});   // work counters of the strip launches (slots launches.size() + group)
 
     CK(ctx->d_raw.reserve(raw_bytes + 16));
     CK(ctx->d_pool.reserve(pool_words));
@@ -407,7 +406,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_outs.reserve(nj));
     CK(ctx->d_runs.reserve((size_t)nj * kSigCap));
     CK(ctx->d_order.reserve(nj));
-    CK(ctx->d_counter.reserve(launches.size() + sgroups.size() + 1));
+    CK(ctx->d_counter.reserve((launches.size() + sgroups.size() + 1) * kLaunchSlotInts));
     CK(ctx->d_aoff.reserve(arena_offs.size()));
     CK(ctx->d_arena.reserve_exact(arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
@@ -415,18 +414,13 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     if (want_cigar) CK(ctx->h_cigar.reserve(cigar_words));
     if (want_runs) CK(ctx->h_runs.reserve((size_t)nj * kSigCap));
 
-    while (ctx->class_ev.size() < launches.size() + sgroups.size()) {
-        cudaEvent_t e;
-        CK(cudaEventCreate(&e));
-        ctx->class_ev.push_back(e);
-    }
     cudaStream_t s = ctx->stream;
     const auto t_planned = std::chrono::steady_clock::now();
     CK(cudaEventRecord(ctx->ev[0], s));
     CK(cudaMemcpyAsync(ctx->d_raw.p, ctx->h_raw.p, raw_bytes, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(KswJob) * nj, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_counter.p, counters.data(), sizeof(int) * counters.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_counter.p, counters.data(), sizeof(KswLaunchSlot) * counters.size(), cudaMemcpyHostToDevice, s));
     if (!sjobs.empty()) {
         CK(cudaMemcpyAsync(ctx->d_sjobs.p, sjobs.data(), sizeof(KswStripJob) * sjobs.size(), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(ctx->d_sprog.p, 0, sizeof(int) * (size_t)prog_ints, s));
@@ -453,18 +447,16 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             if (L.ncta > 0) {
                 CK(launch_ksw(L.nt, L.ncta, L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count,
                               ctx->d_pool.p, ctx->d_arena.p + L.arena_off, ctx->d_aoff.p + offs_first[li], ctx->d_cigar.p,
-                              ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ls, chained));
+                              ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li * kLaunchSlotInts, ls, chained));
                 chained = true;
-                CK(cudaEventRecord(ctx->class_ev[li], ls));
             } else {
                 cudaStream_t ws = ctx->side[1];
                 if (!wide_used) CK(cudaStreamWaitEvent(ws, ctx->ev[2], 0));
                 wide_used = true;
                 launch_ksw_wide(L.n_clusters, L.smem, ctx->d_jobs.p, ctx->d_order.p + L.first, L.count, ctx->d_pool.p,
                                 ctx->d_arena.p + L.arena_off, L.stride, ctx->d_scratch.p, ksw_wide_scratch_words(L.max_slots),
-                                L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li, ws);
+                                L.max_slots, ctx->d_cigar.p, ctx->d_runs.p, ctx->d_outs.p, ctx->d_counter.p + li * kLaunchSlotInts, ws);
                 CK(cudaGetLastError());
-                CK(cudaEventRecord(ctx->class_ev[li], ws));
             }
         }
         if (!sjobs.empty()) {                           // one launch per group, in order, on their own stream
@@ -474,8 +466,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                 const StripGroup& g = sgroups[gi];
                 CK(launch_ksw_strips(g.n_ctas, ksw_smem_bytes(strip_smem_q, strip_smem_t), ctx->d_jobs.p, ctx->d_sjobs.p + g.first, g.count,
                                      ctx->d_pool.p, ctx->d_arena.p, ctx->d_edges.p, ctx->d_sprog.p, ctx->d_cigar.p, ctx->d_runs.p,
-                                     ctx->d_outs.p, ctx->d_counter.p + launches.size() + gi, ss));
-                CK(cudaEventRecord(ctx->class_ev[launches.size() + gi], ss));
+                                     ctx->d_outs.p, ctx->d_counter.p + (launches.size() + gi) * kLaunchSlotInts, ss));
             }
             CK(cudaEventRecord(ctx->side_done[2], ss));
             CK(cudaStreamWaitEvent(s, ctx->side_done[2], 0));
@@ -498,6 +489,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         CK(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs.p, sizeof(KswGapRun) * (size_t)nj * kSigCap, cudaMemcpyDeviceToHost, s));
         d2h += sizeof(KswGapRun) * (size_t)nj * kSigCap;
     }
+    CK(cudaMemcpyAsync(counters.data(), ctx->d_counter.p, sizeof(KswLaunchSlot) * counters.size(), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaStreamSynchronize(s));
 
@@ -536,7 +528,9 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                     c.cells += (uint64_t)cells_fast(J.qlen, J.tlen, J.w);
                 }
         }
-        cudaEventElapsedTime(&c.done_ms, ctx->ev[2], ctx->class_ev[li]);
+        unsigned long long t_first = ~0ull;
+        for (const KswLaunchSlot& k : counters) t_first = std::min(t_first, k.t_start);
+        c.done_ms = counters[li].t_end > t_first ? (float)((counters[li].t_end - t_first) * 1e-6) : 0.f;
         ctx->classes.push_back(c);
     }
     lesvgpu_timing& T = ctx->timing;

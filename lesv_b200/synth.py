@@ -117,6 +117,38 @@ def reads_with_noisy_tails(ref: np.ndarray, n_reads: int, rng: np.random.Generat
     return reads
 
 
+def consensus_reads(contigs, n_reads: int, rng: np.random.Generator, max_len: int = 30000):
+    """Consensus-like reads as qx2csvrg hands them to qx2asvr (reference src/app/necat2sv/map_cns_sv_read.c:170-292):
+    a reference window of 3-`max_len` bp carrying one planted INS/DEL of 40 bp-3 kb, 0.5-4 % residual error, stored
+    reverse-complemented when the header says REV, named
+    <name>_svr:<dir>:<sid>:<gid>:<sfrom>:<sto>_cns:<a>:<b>:<from>:<to>:<size>:<raw> (sv_read_group_file_name.cpp:102-196,
+    corelib/cns_read_header.c:3-95).  Returns per contig a list of (name, codes)."""
+    out = [[] for _ in contigs]
+    for i in range(n_reads):
+        sid = int(rng.integers(0, len(contigs)))
+        c = contigs[sid]
+        L = int(rng.integers(3000, max_len))
+        sfrom = int(rng.integers(0, len(c) - L))
+        sto = sfrom + L
+        seg = c[sfrom:sto]
+        size = int(np.exp(rng.uniform(np.log(40), np.log(3000))))
+        k = int(rng.integers(L // 4, 3 * L // 4))
+        if i % 2 == 0:
+            seg = np.concatenate([seg[:k], random_codes(size, rng), seg[k:]])              # insertion in the sample
+        elif size < L // 3:
+            seg = np.concatenate([seg[:k], seg[k + size:]])                                # deletion
+        err = float(rng.uniform(0.005, 0.04)) if i % 7 else float(rng.uniform(0.10, 0.22))   # a few bad ones (< 85 % eff. identity)
+        rd = mutate(seg, err, rng)
+        n = len(rd)
+        cns_from, cns_to = int(rng.integers(0, n // 10)), n - int(rng.integers(0, n // 10))
+        rdir = int(rng.integers(0, 2))
+        if rdir:
+            rd = revcomp_codes(rd)
+        name = f"read{i}_svr:{rdir}:{sid}:{i % 50}:{sfrom}:{sto}_cns:{3 + i % 5}:{10 + i % 9}:{cns_from}:{cns_to}:{n}:{n + 37}"
+        out[sid].append((name, np.ascontiguousarray(rd)))
+    return out
+
+
 def write_fasta(path: str, names, seqs, width: int = 0) -> None:
     with open(path, "wb") as f:
         for name, s in zip(names, seqs):

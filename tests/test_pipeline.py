@@ -159,9 +159,10 @@ def test_four_tools_on_reference_branches(tmp_path, scenario):
                          check=True, capture_output=True, text=True, env=env).stdout
     assert "m4: reference" in out and ", identical True" in out, out
     assert "svr:" in out and "svsig:" in out and out.count("all files identical: True") == 2, out
+    import re
     n_m4 = int(out.split("m4: reference ")[1].split(" ")[0])
-    n_svr = int(out.split("svr: ")[1].split(" ")[0])
-    n_sig = int(out.split("svsig: ")[1].split(" ")[0])
+    n_svr = int(re.search(r"^svr: (\d+) records", out, re.M).group(1))
+    n_sig = int(re.search(r"^svsig: (\d+) records", out, re.M).group(1))
     assert n_m4 >= {"bigsv": 16, "trf": 90, "minindel": 90, "tails": 70, "c4": 25}[scenario], out
     if scenario == "bigsv":
         assert n_sig >= 8, out                     # the planted 6-10 kb events are found
@@ -235,3 +236,44 @@ def test_tools_write_the_same_files_for_any_number_of_feeders(tmp_path):
         assert t.keys() == trees[0].keys()
         for k in t:
             assert t[k] == trees[0][k], k
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_BIN, "qx2asvr")), reason="oracle/_ref not built")
+def test_qx2asvr_equals_reference_sam(tmp_path):
+    """consensus reads of SV groups against their reference windows (map_cns_sv_read.c:170-292), SAM
+    records with CIGAR / MD / identity tags (map_results.c:63-323).  Both tools run on the same
+    subject_%08d.normal.cns.fasta files; the reference writes records in thread order, so records compare as multisets;
+    the header is identical apart from the @PG line, which carries the program path."""
+    from lesv_b200 import synth
+    work = str(tmp_path)
+    rng = np.random.default_rng(3)
+    contigs = [synth.random_codes(400_000, rng) for _ in range(3)]
+    synth.write_fasta(os.path.join(work, "ref.fa"), [f"chr{i}" for i in range(3)], contigs, width=0)
+    synth.write_fasta(os.path.join(work, "dummy.fa"), ["q0"], [contigs[0][:5000]])
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    subprocess.run([os.path.join(REF_BIN, "qx2map"), "-db_dir", "db", "-keep_db", "-num_threads", "1", "dummy.fa", "ref.fa"], cwd=work,
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    per = synth.consensus_reads(contigs, 60, np.random.default_rng(4), max_len=52000)      # up to 52 kb: band 0.2 x len > one CTA
+    for d in ("grp_ref", "grp_gpu"):
+        os.makedirs(os.path.join(work, d))
+        for sid, lst in enumerate(per):
+            synth.write_fasta(os.path.join(work, d, f"subject_{sid:08d}.normal.cns.fasta"), [n for n, _ in lst], [c for _, c in lst], width=0)
+    subprocess.run([os.path.join(REF_BIN, "qx2asvr"), "db", "grp_ref", str(os.cpu_count() or 4)], cwd=work, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+    subprocess.run([os.path.join(BIN, "qx2asvr"), "db", "grp_gpu", "4"], cwd=work, check=True, stderr=subprocess.DEVNULL,
+                   env=dict(os.environ, LESV_ASVR_BATCH="9"))
+    n_rec = 0
+    for sid in range(3):
+        name = f"subject_{sid:08d}.normal.cns.fasta"
+        a, b = _lines(os.path.join(work, "grp_ref", name + ".sam")), _lines(os.path.join(work, "grp_gpu", name + ".sam"))
+        head = lambda x: [l for l in x if l.startswith("@") and not l.startswith("@PG")]
+        body = lambda x: sorted(l for l in x if not l.startswith("@"))
+        assert head(a) == head(b) and len(head(a)) == 5
+        assert body(a) == body(b), name
+        n_rec += len(body(a))
+        assert os.path.exists(os.path.join(work, "grp_gpu", name + ".mapped"))
+        for f in ("query.pac", "query.seq_info", "query.hdr"):                      # the packed consensus reads, byte for byte
+            pa, pb = (os.path.join(work, d, f"s{sid:08d}_svr_pdb", f) for d in ("grp_ref", "grp_gpu"))
+            assert open(pa, "rb").read() == open(pb, "rb").read(), f
+    assert 30 <= n_rec < 60            # the reads at 10-22 % error fall below 85 % effective identity and are dropped
