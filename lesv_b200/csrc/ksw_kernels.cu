@@ -434,49 +434,54 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                 __syncthreads();
             }
         } else {
-            // ring endpoints of this thread (only lane 0 / lane 31 use them): my warp's inbox and where
-            // my consumed-rows counter lives; the inbox I publish into and the counter I watch
-            uint32_t in_addr = map_rank(smem_addr(&ps.inbox[warp][0]), rank);
-            uint32_t cons_addr = map_rank(smem_addr(&ps.consumed[warp]), rank);
-            uint32_t out_addr = map_rank(smem_addr(&ps.inbox[warp + 1 < NW ? warp + 1 : 0][0]), rank);
-            uint32_t watch_addr = map_rank(smem_addr(&ps.consumed[warp + 1 < NW ? warp + 1 : 0]), rank);
-            if (warp == 0) cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
-            if (warp == NW - 1) {
-                out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
-                watch_addr = map_rank(smem_addr(&ps.right_consumed), rank);
-            }
-            const int nrow = warp < NW ? nrow_all : 0;       // warps beyond NT sit this alignment out
-            for (int r = 0; r < nrow; ++r) {
-                Carry cin;
-                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                bool fetched = false;
-                auto consume = [&]() -> Carry {        // lane 0: take row r-1 out of the inbox
-                    Carry v = carry_init();
-                    fetched = true;
-                    if (r == 0) return v;
-                    const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                    while (ld_slot<true>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
-                    st_word<true>(cons_addr, (uint32_t)r);
-                    return v;
-                };
-                Carry cout;
-                uint32_t tb[4];
-                const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                                 [&]() -> Carry { return lane == 0 ? consume() : cin; }, cout, tb);
-                if (did) {
-                    *reinterpret_cast<uint4*>(arena + (size_t)r * prow + (size_t)c.tb_off) =
-                        make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                    prev_out = cout;
+            // Cluster: inside a CTA the same lean barrier loop as above (the polled ring between warps of one SM costs
+            // issue slots of the schedulers that are the bottleneck: 3.5 instead of 5.5 GCUPS per SM); only the carry INTO
+            // warp 0 and OUT OF the last warp crosses CTAs, through the tagged DSMEM slots.  Lane 0 of warp 0 fetches it
+            // as late as possible (just before pair 0, the last pair of the row), so the CTA to the left may lag by most of
+            // a row before anybody waits; a consumed-rows counter flowing back keeps it from lapping the ring.
+            const uint32_t in_addr = smem_addr(&ps.inbox[0][0]);                                   // written by the CTA to the left
+            const uint32_t cons_addr = map_rank(smem_addr(&ps.right_consumed), (rank + ncta - 1) % ncta);
+            const uint32_t out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
+            const uint32_t watch_addr = smem_addr(&ps.right_consumed);
+            const bool first_lane = warp == 0 && lane == 0, last_lane = warp == NW - 1 && lane == 31;
+            uint8_t* rowp = arena;
+            for (int r = 0; r < nrow_all; ++r, rowp += prow) {
+                if (warp < NW) {
+                    const uint2 nb = carry_sh[(r + 1) & 1][warp];
+                    Carry cin;
+                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                    if (lane == 0 && warp > 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    bool fetched = false;
+                    auto consume = [&]() -> Carry {        // first lane of the CTA: take row r-1 out of the inbox
+                        Carry v = carry_init();
+                        fetched = true;
+                        if (r == 0) return v;
+                        const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                        while (ld_slot<false>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
+                        st_word<true>(cons_addr, (uint32_t)r);
+                        return v;
+                    };
+                    Carry cout;
+                    uint32_t tb[4];
+                    const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                                     [&]() -> Carry { return first_lane ? consume() : cin; }, cout, tb);
+                    if (did) {
+                        *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                        prev_out = cout;
+                    }
+                    if (first_lane && !fetched) consume();                     // flow control only
+                    if (lane == 31) {
+                        if (last_lane) {                                       // publish row r to the CTA on the right
+                            if (r >= kRingD)
+                                while ((int)ld_word<false>(watch_addr) < r - kRingD + 1) { }
+                            const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                            st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
+                        } else carry_sh[r & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
+                    }
                 }
-                if (lane == 0 && !fetched) consume();                      // flow control only
-                if (lane == 31) {                                          // publish row r
-                    if (r >= kRingD)
-                        while ((int)ld_word<true>(watch_addr) < r - kRingD + 1) { }
-                    const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                    st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
-                }
-                __syncwarp();
+                __syncwarp();                  // the polling lanes are back before the aligned barrier
+                __syncthreads();
             }
         }
         __syncthreads();
@@ -488,6 +493,91 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         if (kCluster) cluster_sync_all();
     }
     if (tid == 0) stamp_end(counter);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Narrow bands: several alignments per warp
+// ---------------------------------------------------------------------------------------------
+// A band of 64 columns lives in 7 or 8 sixteen-column blocks, one of 128..192 in at most 16: with one block per thread a
+// warp that holds ONE such alignment computes with a quarter or half of its lanes (BASELINE configs[4]: 63-107 GCUPS at band
+// 64).  Here a warp is cut into 32 / G groups of G lanes and every group runs its own alignment: its own queue entry, row
+// counter, geometry and traceback arena.  The groups of a warp step through their anti-diagonals together; the carry of
+// a block comes from the lane to its left in the group (a rotation inside the group, so the ring wrap needs no shared
+// memory), nothing is synchronised beyond the warp, and the packed sequences are read straight from the pool (they are
+// tiny next to the traceback and stay in L1).  A group that has finished its last row is walked by the whole warp
+// (backtrack_warp, which keeps all 32 lanes busy with the row prefetch), the other groups wait for that walk.
+template <int G>
+__global__ void __launch_bounds__(32, 20)
+ksw_dp_group_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
+                    const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base,
+                    const size_t* __restrict__ arena_off, uint32_t* __restrict__ cigar_pool,
+                    KswGapRun* __restrict__ run_pool, KswOut* __restrict__ outs, int* counter)
+{
+    __shared__ BtShared bt;
+    constexpr int NG = 32 / G;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int lane = (int)threadIdx.x, gl = lane & (G - 1), grp = lane / G;
+    const unsigned gmask = (G == 32 ? kFull : ((1u << G) - 1u)) << (grp * G);
+    const int group_id = (int)blockIdx.x * NG + grp;
+    if (lane == 0) stamp_start(counter);
+    uint8_t* const arena = arena_base + arena_off[group_id];
+    const int left = grp * G + ((gl + G - 1) & (G - 1));           // the lane that holds the block to my left (ring inside the group)
+    bool have = false, first = true, exhausted = false;
+    int jid = 0, r = 0, nrow = 0, qlen = 0, tlen = 0, w = 0, tb_blocks = 1;
+    size_t prow = 16;
+    const uint32_t *tp = pool, *qrp = pool;
+    ThreadCtx c;
+    thread_ctx_reset(c, gl);
+    Carry prev_out = carry_init();
+    for (;;) {
+        if (!have && !exhausted) {                                  // uniform inside a group
+            int j = 0;
+            if (gl == 0) j = first ? group_id : atomicAdd(counter, 1);
+            j = __shfl_sync(gmask, j, grp * G);
+            first = false;
+            if (j < njobs) {
+                jid = order[j];
+                const KswJob job = jobs[jid];
+                qlen = job.qlen; tlen = job.tlen; w = job.w; tb_blocks = job.tb_blocks;
+                prow = (size_t)tb_blocks * 16;
+                nrow = qlen + tlen - 1;
+                tp = pool + job.tp_off; qrp = pool + job.qrp_off;
+                thread_ctx_reset(c, gl);
+                prev_out = carry_init();
+                r = 0;
+                have = true;
+            } else exhausted = true;
+        }
+        if (!__any_sync(kFull, have)) break;
+        if (have && r < nrow) {
+            Carry cin;
+            cin.xv = __shfl_sync(gmask, prev_out.xv, left);
+            cin.x2 = __shfl_sync(gmask, prev_out.x2, left);
+            Carry cout;
+            uint32_t tb[4];
+            if (thread_row_step<true, false>(c, G, r, qlen, tlen, w, tb_blocks, tp, qrp, [&]() -> Carry { return cin; }, cout, tb)) {
+                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                prev_out = cout;
+            }
+            ++r;
+        }
+        __syncwarp();
+        unsigned dm = __ballot_sync(kFull, have && r >= nrow && gl == 0);
+        if (dm) __threadfence_block();                              // the rows were written by other lanes of this warp
+        while (dm) {
+            const int leader = __ffs((int)dm) - 1;
+            dm &= dm - 1;
+            const int wj = __shfl_sync(kFull, jid, leader);
+            const KswJob job = jobs[wj];
+            uint8_t* const wa = arena_base + arena_off[(int)blockIdx.x * NG + leader / G];
+            backtrack_warp(job, wa, (size_t)job.tb_blocks * 16, pool + job.tp_off, pool + job.qrp_off, cigar_pool + job.cigar_off,
+                           run_pool + job.sig_off, outs + wj, bt, lane);
+            __syncwarp();
+            if (grp == leader / G) have = false;
+        }
+    }
+    if (lane == 0) stamp_end(counter);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,7 +986,12 @@ size_t ksw_smem_bytes(int max_qlen, int max_tlen)
 }
 
 // <= 96 registers per thread -> 680 threads per SM
-int ksw_ctas_per_sm(int nt) { int n = 680 / nt; return n < 1 ? 1 : n > 23 ? 23 : n; }
+int ksw_ctas_per_sm(int nt)
+{
+    if (nt <= kGroupTierMax) return 20 * (32 / nt);    // groups per SM: 20 one-warp CTAs (ksw_dp_group_kernel's launch bounds)
+    const int n = 680 / nt;
+    return n < 1 ? 1 : n > 21 ? 21 : n;
+}
 
 using KswKernelFn = void (*)(const KswJob*, const int*, int, const uint32_t*, uint8_t*, const size_t*, uint32_t*,
                              KswGapRun*, KswOut*, int*);
@@ -912,6 +1007,15 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
     at[0].val.programmaticStreamSerializationAllowed = after_resident ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
+    if (ncta <= 1 && nt <= kGroupTierMax) {             // several alignments per warp: n_clusters counts GROUPS (a multiple of 32 / nt)
+        cfg.gridDim = dim3((unsigned)(n_clusters / (32 / nt)));
+        cfg.blockDim = dim3(32u); cfg.dynamicSmemBytes = 0;
+        if (nt == 8)
+            return cudaLaunchKernelEx(&cfg, ksw_dp_group_kernel<8>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs,
+                                      d_out, d_counter);
+        return cudaLaunchKernelEx(&cfg, ksw_dp_group_kernel<16>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride, d_cigar, d_runs,
+                                  d_out, d_counter);
+    }
     if (ncta <= 1) {
         cfg.gridDim = dim3((unsigned)n_clusters);
         if (nt >= kTierLow && 2 * smem <= 200 * 1024) {

@@ -172,6 +172,9 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
         static const int tiers[] = {32, 64, 96, 128, 160, kTierLow, kTierMid, kTierTop};
+        static const bool groups = getenv("LESV_KSW_NO_GROUPS") == nullptr;
+        if (groups && wb <= 8) return {1, 8, 8};             // several alignments per warp (ksw_dp_group_kernel)
+        if (groups && wb <= 16) return {1, 16, 16};
         if (wb <= kTierTop) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};
@@ -306,6 +309,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         const int whole = std::max(1, std::min(std::min(ctx->n_sm * per_sm / sms_per_job, L.count), cap));
         L.fair = std::max(1, std::min((int)(share * per_sm / sms_per_job + 0.5), whole));
         int n = &L == major ? whole : std::min(whole, (5 * L.fair + 3) / 4);
+        if (L.ncta == 1 && L.nt <= kGroupTierMax) n = (n + 32 / L.nt - 1) / (32 / L.nt) * (32 / L.nt);   // whole warps of lane groups
         L.n_clusters = n;
     }
     // fit the arenas.  Cluster i of a launch starts with job i of its (size-sorted) queue and only
@@ -314,7 +318,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     auto footprint = [&](const Launch& L) {
         if (L.ncta == 0) return L.stride * (size_t)L.n_clusters;
         size_t b = 0;
-        for (int i = 0; i < L.n_clusters; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
+        for (int i = 0; i < L.n_clusters && i < L.count; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
         return b;
     };
     if (strip_arena > arena_limit) { ctx->err = "traceback arena too small for the full-matrix alignments"; return LESVGPU_E_NOMEM; }
@@ -329,9 +333,10 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big)
             for (Launch& L : launches)
-                if (L.n_clusters > 1 && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+                if (L.n_clusters > ((L.ncta == 1 && L.nt <= kGroupTierMax) ? 32 / L.nt : 1) && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
-        --big->n_clusters;
+        big->n_clusters -= (big->ncta == 1 && big->nt <= kGroupTierMax) ? 32 / big->nt : 1;
+        if (big->n_clusters < 1) { ctx->err = "traceback arena too small for this batch"; return LESVGPU_E_NOMEM; }
     }
     std::vector<size_t> arena_offs;                 // per launch: n_clusters offsets relative to its arena_off
     std::vector<KswLaunchSlot> counters(launches.size());
@@ -342,7 +347,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         size_t b = 0;
         for (int i = 0; i < L.n_clusters; ++i) {
             arena_offs.push_back(b);
-            b += L.ncta == 0 ? L.stride : ((tb_bytes[L.ids[i]] + 255) & ~(size_t)255);
+            b += L.ncta == 0 ? L.stride : i < L.count ? ((tb_bytes[L.ids[i]] + 255) & ~(size_t)255) : 0;   // lane groups beyond the queue: no job
         }
         arena_offs.push_back(b);                         // end of the last arena (ksw_dp_overlap_kernel needs the sizes)
         counters[li] = KswLaunchSlot{L.ncta == 0 ? 0 : L.n_clusters, 0, ~0ull, 0ull};       // clusters start with jobs 0..n-1
