@@ -357,12 +357,19 @@ def c5_block(ctx, capi, cores: int, seed: int, n_sm: int, f_mhz: float):
     nw_ksw2_extd2 of oracle/_ref/libhbn_ref.so called from one Python thread per host core (ctypes releases the GIL)."""
     import ctypes as C
     rng = np.random.default_rng(seed + 5)
-    n_pairs = int(os.environ.get("LESV_C5_PAIRS", "3072"))
-    base = []
-    for _ in range(n_pairs):
-        L = int(np.exp(rng.uniform(np.log(1000), np.log(50000))))
-        q = rng.integers(0, 4, L, dtype=np.uint8)
-        base.append((q, np.ascontiguousarray(synth.mutate(q, 0.12, rng))))
+    n_pairs = int(os.environ.get("LESV_C5_PAIRS", "32768"))
+    # the pairs are slices of one long random sequence and of its noisy copy (no per-pair generation, no copies): enough of
+    # them that the batch is several waves of alignments deep, as BASELINE's 1 M pairs are -- with a few thousand pairs the time
+    # is the critical path of the longest alignment (100 k anti-diagonals one after the other), not throughput
+    lens = np.exp(rng.uniform(np.log(1000), np.log(50000), n_pairs)).astype(np.int64)
+    big = synth.random_codes(int(min(lens.sum() + 50000, 96_000_000)), rng)
+    noisy, pos = synth.mutate_with_map(big, 0.12, rng)
+    base, a = [], 0
+    for L in lens:
+        if a + L > len(big):
+            a = int(rng.integers(0, len(big) - 50000))
+        base.append((big[a:a + L], noisy[pos[a]:pos[a + L]]))
+        a += int(L)
     peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9
     so = os.path.join(ROOT, "oracle", "_ref", "libhbn_ref.so")
     lib = None
@@ -417,8 +424,8 @@ def c5_block(ctx, capi, cores: int, seed: int, n_sm: int, f_mhz: float):
             row["reference_gcups"] = cpu_gcups(good[:n_cpu], w)
             row["reference_pairs"] = n_cpu
         rows.append(row)
-    return {"workload": f"C5 sample: {n_pairs} pairs, lengths log-uniform 1-50 kb, target = query at 12 % error; of BASELINE's 1 M pairs "
-                        "(same length and band distribution)", "reference_threads": cores if lib is not None else 0, "bands": rows}
+    return {"workload": f"C5 sample: {n_pairs} of BASELINE's 1 M pairs (lengths log-uniform 1-50 kb, target = query at 12 % error), every band "
+                        "over all pairs whose length difference fits it", "reference_threads": cores if lib is not None else 0, "bands": rows}
 
 
 def main():
@@ -452,7 +459,8 @@ def main():
                           "; mapping + SvRead selection + SV signatures (-max_target_seqs 5 -max_hsps 10, SVR 3000/70.0/300, min indel 40)",
               "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN,
               "ref_len": int(sum(HG19_MBP) * 1e6 * args.c3_scale) if c3 else args.ref_len,
-              "batches": f"{args.batches} distinct read batches per GPU, cycled step by step (warm-up included)",
+              "batches": (f"one read set of {args.batches} batches for the whole job; steps x n_gpus sub-batches pulled by all ranks from a shared queue"
+                          if args.scaling == "strong" else f"{args.batches} distinct read batches per GPU, cycled step by step (warm-up included)"),
               "l2": "every step maps another batch and writes > 100 GB of traceback: far beyond the 126 MB L2",
               "seed": args.seed}
 
@@ -511,7 +519,7 @@ def main():
     def reads_of(seed, n):
         return make_reads_c3(contigs, n, seed) if c3 else make_reads(sample, n, seed)
     if strong:      # one read set for the whole job (every rank holds it; ranks pull sub-batches from the shared queue)
-        batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches * world)]
+        batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches)]
     else:           # this rank's own batches
         batches = [Batch(reads_of(shard.read_seed_of_rank(args.seed, rank) + b, args.reads_per_step), capi) for b in range(n_batches)]
     if c3:

@@ -82,6 +82,27 @@ def mutate(seq: np.ndarray, err: float, rng: np.random.Generator,
     return res
 
 
+def mutate_with_map(seq: np.ndarray, err: float, rng: np.random.Generator, mix=(0.4, 0.3, 0.3)):
+    """mutate() that also returns where every source position starts in the result (len(seq) + 1 entries), so that
+    a slice seq[a:b] and its noisy copy result[pos[a]:pos[b]] can be cut out of one long sequence without copying."""
+    n = len(seq)
+    u = rng.random(n)
+    sub = u < err * mix[0]
+    ins = (u >= err * mix[0]) & (u < err * (mix[0] + mix[1]))
+    dele = (u >= err * (mix[0] + mix[1])) & (u < err)
+    out = seq.copy()
+    out[sub] = (out[sub] + rng.integers(1, 4, size=int(sub.sum()), dtype=np.uint8)) & 3
+    reps = (~dele).astype(np.int64) + ins.astype(np.int64)
+    pos = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(reps, out=pos[1:])
+    idx = np.repeat(np.arange(n), reps)
+    res = out[idx]
+    second = np.zeros(len(idx), dtype=bool)
+    second[1:] = idx[1:] == idx[:-1]
+    res[second] = rng.integers(0, 4, size=int(second.sum()), dtype=np.uint8)
+    return res, pos
+
+
 def simulate_reads(sample: np.ndarray, n_reads: int, read_len: int, rng: np.random.Generator,
                    err_lo: float = 0.12, err_hi: float = 0.12):
     """Draw `n_reads` windows of `read_len` sample bases, mutate, random strand."""
