@@ -50,6 +50,7 @@ MIN_INDEL = 40
 OPS_PER_CELL = 46            # scalar formulation of ksw2_extd2_sse.c:31-58,227-265,318-349
 LANES_PACKED = 2             # two DP cells per 32-bit integer instruction (16-bit lanes)
 METRIC = "aligned bases/s (qx2map + qx2svr + qx2svsig stages, C2)"
+METRIC_C3 = "aligned bases/s (qx2map + qx2svr + qx2svsig stages, C3)"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -611,7 +612,7 @@ def main():
                           "gcups_over_done_ms": e["cells"] / max(e["done_ms"], 1e-9) / 1e6}
                    for name, e in acc["class_sum"].items()}
         line = {
-            "metric": METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
+            "metric": METRIC_C3 if c3 else METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": config,
