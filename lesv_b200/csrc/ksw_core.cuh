@@ -35,20 +35,20 @@
 // second pipe sees as few instructions as possible and both pipes carry about the same load.
 // State per column (lane), all arithmetic mod 2^16:
 //     UC = 256(u - (q+e))   VC = 256(v - (q+e))                      (low byte 0)
-//     PX = 256 max(a',0) + 3    with x = PX/256 - (q+e);  PY = .. + 2,  PX2 = .. + 1,  PY2 = .. + 0
-//     S  = 256 s + 4                                                  (tag = 4 - winner index)
+//     PX = 256 max(a',0) + 4    with x = PX/256 - (q+e);  PY = .. + 3,  PX2 = .. + 2,  PY2 = .. + 1
+//     S  = 256 s + 5                                                  (tag = 5 - winner index)
 // so that the five candidates of a row need no constants:
-//     ka  = PX[t-1] + VC[t-1]        = 256a  + 3        kb  = PY  + UC        = 256b  + 2
-//     ka2 = PX2[t-1] + (VC[t-1] + D) = 256a2 + 1        kb2 = PY2 + (UC + D)  = 256b2 + 0
+//     ka  = PX[t-1] + VC[t-1]        = 256a  + 4        kb  = PY  + UC        = 256b  + 3
+//     ka2 = PX2[t-1] + (VC[t-1] + D) = 256a2 + 2        kb2 = PY2 + (UC + D)  = 256b2 + 1
 //     (D = 256((q+e) - (q2+e2)))
 //     k   = max3(max3(S, ka, kb), ka2, kb2)             tag = k & 7
 //     W   = min((k | 0xFF) + K, C)   = 256(z - 2(q+e)) + 1            (one VIADDMNMX: clamp z <= 2)
 //     UC' = W + ~VC[t-1]    VC' = W + ~UC                              (~w = -w-1 per lane)
 //     N   = ~W + 256(q - 2(q+e)) + 2 = 256(q - z),   N2 = N + 256(q2 - q)
-//     PX' = max(ka + N, 3)   PY' = max(kb + N, 2)   PX2' = max(ka2 + N2, 1)   PY2' = max(kb2 + N2, 0)
+//     PX' = max(ka + N, 4)   PY' = max(kb + N, 3)   PX2' = max(ka2 + N2, 2)   PY2' = max(kb2 + N2, 1)
 // The relu thresholds are the tags, so a clamped and an unclamped lane carry the same low byte and
 // no lane sum ever carries out of its low byte into the value.  The flag "x' > -(q+e)" is
-// min(PX', 256 + 3) = 256 flag + 3; the four flags and the tag are summed into the high byte of the
+// min(PX', 256 + 4) = 256 flag + 4; the four flags and the tag are summed into the high byte of the
 // lane with multiply-adds (the other pipe) and one PRMT per four columns gathers the bytes.
 #pragma once
 #include <stdint.h>
@@ -73,7 +73,7 @@ static_assert(!(kQ2 + kE2 + kLongThres * kE2 > kQ + kE + kLongThres * kE), "long
 
 // ---- lane representation: 256*value + tag ---------------------------------------------------
 constexpr int kQE = kQ + kE, kQE2 = kQ2 + kE2;
-constexpr int kTagS = 4, kTagA = 3, kTagB = 2, kTagA2 = 1, kTagB2 = 0;
+constexpr int kTagS = 5, kTagA = 4, kTagB = 3, kTagA2 = 2, kTagB2 = 1;     // none is 0: ptxas builds a zero operand of VIADDMNMX with a PRMT per use
 KSW_HDC uint32_t dup(int v) { return (uint32_t)(v & 0xFFFF) | ((uint32_t)(v & 0xFFFF) << 16); }
 constexpr uint32_t kD2 = dup(256 * (kQE - kQE2));           // VC/UC -> the long-gap candidates
 constexpr uint32_t kWK = dup(256 * (-2 * kQE) - 254);       // (k | 0xFF) + kWK = 256(z - 2(q+e)) + 1
@@ -91,7 +91,7 @@ static_assert((kSStep & 0xFF) == 0, "score step is a multiple of 256: it can be 
 constexpr uint32_t kSatA = dup(256 + kTagA), kSatB = dup(256 + kTagB), kSatA2 = dup(256 + kTagA2), kSatB2 = dup(256 + kTagB2);
 constexpr int kFlagJunk = 128 * kTagA + 64 * kTagB + 32 * kTagA2 + 16 * kTagB2;   // what the tags add up to
 constexpr uint32_t kFlagFix = (uint32_t)(0u - (uint32_t)kFlagJunk * 0x00010001u); // 32-bit add: both lanes at once
-static_assert(kFlagJunk == 544, "flag sum");
+static_assert(kFlagJunk == 784 && kTagS < 8, "flag sum");
 
 // value the reference writes into u[r] (top row) and uses as v1 at column 0 (:150, :154)
 KSW_HD int first_gap_diff(int r)
@@ -155,22 +155,12 @@ KSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
 }
 #endif
 
-// A constant the compiler must keep in a register: ptxas otherwise re-materialises the register operands of
-// VIADDMNMX (it takes one immediate only) with a MOV / PRMT per use inside the block update.
-KSW_HD uint32_t reg_const(uint32_t v)
-{
-#if defined(__CUDA_ARCH__) && defined(KSW_REG_CONST)
-    asm volatile("" : "+r"(v));
-#endif
-    return v;
-}
-
 // ---- internal traceback byte -------------------------------------------------------------------
-// bits 0-2: 4 - winner (winner 0 H, 1 E, 2 F, 3 E~, 4 F~); bit 7: E continues; bit 6: F continues;
+// bits 0-2: 5 - winner (winner 0 H, 1 E, 2 F, 3 E~, 4 F~); bit 7: E continues; bit 6: F continues;
 // bit 5: E~ continues; bit 4: F~ continues; bit 3: 0.  (The reference's own layout, ksw2.h:117-120,
 // is winner | flags at bits 3..6; only our backtrack kernel reads this one.)
 KSW_HD int tb_cont_bit(int state) { return 8 - state; }
-KSW_HD int tb_winner(uint32_t byte) { return 4 - (int)(byte & 7); }
+KSW_HD int tb_winner(uint32_t byte) { return kTagS - (int)(byte & 7); }
 // byte position of column c (0..15) inside the 16-byte block written per thread per row
 KSW_HD int tb_byte_pos(int c) { return 4 * ((c & 7) >> 1) + 2 * (c & 1) + (c >> 3); }
 
@@ -182,10 +172,8 @@ struct BlockState {
     // 2c+1: never written) and rebuilds the S lanes of a row from them.  Stale bytes (columns of the
     // 16-aligned band outside [st0, wr]) are simply bits that were not refreshed.
     uint32_t sbits;
-    uint32_t kwk, kzero;                                    // kWK and kReluB2 held in registers (reg_const)
     KSW_HD void init()
     {
-        kwk = reg_const(kWK); kzero = reg_const(kReluB2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             U[j] = kInitUV; V[j] = kInitUV; X[j] = kReluA; Y[j] = kReluB;
@@ -248,12 +236,12 @@ KSW_HD uint32_t pair_row(BlockState& b, int j, uint32_t s, uint32_t x1, uint32_t
     const uint32_t ka = vadd2(x1, v1), kb = vadd2(b.Y[j], u0);
     const uint32_t ka2 = vadd2(x21, vadd2(v1, kD2)), kb2 = vadd2(b.Y2[j], vadd2(u0, kD2));
     const uint32_t k = vmax3(vmax3(s, ka, kb), ka2, kb2);
-    const uint32_t w = vaddmin(k | 0x00FF00FFu, b.kwk, kWClamp);
+    const uint32_t w = vaddmin(k | 0x00FF00FFu, kWK, kWClamp);
     const uint32_t n = vadd2(~w, kNQ), n2 = vadd2(n, kNQ2);
     b.U[j] = vadd2(w, ~v1);
     b.V[j] = vadd2(w, ~u0);
     const uint32_t px = vaddmax(ka, n, kReluA), py = vaddmax(kb, n, kReluB);
-    const uint32_t px2 = vaddmax(ka2, n2, kReluA2), py2 = vaddmax(kb2, n2, b.kzero);
+    const uint32_t px2 = vaddmax(ka2, n2, kReluA2), py2 = vaddmax(kb2, n2, kReluB2);
     b.X[j] = px; b.Y[j] = py; b.X2[j] = px2; b.Y2[j] = py2;
     // high byte of a lane: E continues | F continues | E~ continues | F~ continues | 0 | tag (k's low byte; the
     // value byte of k lands in the neighbouring lane's low byte, which nobody reads)

@@ -595,6 +595,7 @@ ksw_dp_group_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ ord
 #define KSW_WALK_SLEEP_NS 4000      // the walker's poll for the next alignment shares a scheduler with DP warps: poll rarely
 #endif
 __device__ __forceinline__ void bar_dp(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bar_rows(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
 
 template <int kTier>                                    // CTA = kTier DP threads + the walker warp: fixes the register budget
 __global__ void __launch_bounds__(kTier + 32, kTier <= kTierLow ? 2 : 1)
@@ -684,41 +685,46 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         // row r lives at rowp; consecutive rows are prow apart, upwards or downwards
         uint8_t* rowp = arena + (reversed ? asize - prow : (size_t)0);
         const long long rstep = reversed ? -(long long)prow : (long long)prow;
-        for (int r = 0; r < nrow_all; ++r, rowp += rstep) {
-            if ((r & 255) == 0 && m > 0) {
-                // rows r .. r+255 of this alignment must not touch what walk m-1 still needs (rows <= wk_row of it)
-                if (warp == 0) {
-                    const unsigned long long mine = (unsigned long long)(r + 256 < nrow_all ? r + 256 : nrow_all) * sh_prow;
-                    for (;;) {
-                        int ok = 0;
-                        if (lane == 0) {
-                            const int need = wk_done >= m ? -1 : wk_row;
-                            ok = (need < 0 && wk_done >= m) ||
-                                 (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize);
+        // Only the warps that hold blocks of this alignment run the row loop, on a named barrier of their own (2) sized for
+        // them; the others wait at the all-warps barrier (1) behind it.  Rows come in chunks of 256: before a chunk the
+        // first logical warp checks that its rows do not reach into what walk m-1 still needs (rows <= wk_row of it).
+        if (lwarp < NW) {
+            for (int r0 = 0; r0 < nrow_all; r0 += 256) {
+                const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
+                if (m > 0) {
+                    if (lwarp == 0) {
+                        const unsigned long long mine = (unsigned long long)r1 * sh_prow;
+                        for (;;) {                          // (whole-warp poll: no divergence in front of the aligned barrier)
+                            int ok = 0;
+                            if (lane == 0) {
+                                const int need = wk_done >= m ? -1 : wk_row;
+                                ok = (need < 0 && wk_done >= m) ||
+                                     (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize);
+                            }
+                            ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+                            if (ok) break;
+                            __nanosleep(500);
                         }
-                        ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
-                        if (ok) break;
-                        __nanosleep(500);
                     }
+                    bar_rows(NT);
                 }
-                bar_dp(ndp);
-            }
-            if (lwarp < NW) {
-                const uint2 nb = carry_sh[(r + 1) & 1][lwarp];
-                Carry cin;
-                cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
-                Carry cout;
-                uint32_t tb[4];
-                if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                          [&]() -> Carry { return cin; }, cout, tb)) {
-                    *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                    prev_out = cout;
+                for (int r = r0; r < r1; ++r, rowp += rstep) {
+                    const uint2 nb = carry_sh[(r + 1) & 1][lwarp];
+                    Carry cin;
+                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
+                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
+                    if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    Carry cout;
+                    uint32_t tb[4];
+                    if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                              [&]() -> Carry { return cin; }, cout, tb)) {
+                        *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                        prev_out = cout;
+                    }
+                    if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
+                    bar_rows(NT);
                 }
-                if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
             }
-            bar_dp(ndp);
         }
         __threadfence();                                 // the traceback is read by the walker through L2
         bar_dp(ndp);
@@ -747,7 +753,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
 // Strips are handed out in (strip, alignment) order, so the predecessor of a strip is always running or done -- no
 // CTA ever waits for work that has not been started.  A CTA that finishes a strip goes on to the next one of any
 // alignment; whoever finishes the last strip of an alignment walks its traceback.
-constexpr int kStripNT = 640;
+constexpr int kStripNT = kStripBlocks;
 struct StripJob {
     int jid;                 // alignment (index into jobs)
     int s, n_strips;
@@ -756,7 +762,7 @@ struct StripJob {
     unsigned long long edge_off;    // edges[edge_off + s * nrow + r]: column-15 values of strip s in row r
 };
 
-__global__ void __launch_bounds__(kStripNT)
+__global__ void __launch_bounds__(kStripNT, kStripCtasPerSm)
 ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict__ sjobs, int n_sjobs,
                     const uint32_t* __restrict__ pool, uint8_t* __restrict__ arena_base, uint2* __restrict__ edges,
                     int* __restrict__ progress, uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,

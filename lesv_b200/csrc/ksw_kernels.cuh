@@ -97,7 +97,11 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 int ksw_max_clusters(int nt, int ncta, size_t smem);
 
 // Full-matrix alignments cut into column strips of kStripBlocks blocks (ksw_kernels.cu: ksw_dp_strip_kernel).
-constexpr int kStripBlocks = 640;
+#ifndef KSW_STRIP_BLOCKS
+#define KSW_STRIP_BLOCKS 256
+#endif
+constexpr int kStripBlocks = KSW_STRIP_BLOCKS;                  // threads per strip CTA
+constexpr int kStripCtasPerSm = kStripBlocks <= 320 ? 2 : 1;    // 2 x 8 warps: four per scheduler, like the banded kernel
 struct KswStripJob {
     int jid, s, n_strips, prog_off;
     unsigned long long arena_off, edge_off;

@@ -214,7 +214,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         std::vector<int> cand;
         for (int k = 0; k < nj; ++k) {
             const KswJob& J = jobs[k];
-            if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > 640) cand.push_back(k);
+            if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > kTierTop) cand.push_back(k);
         }
         // They are processed in groups whose arenas fit into three quarters of the budget, one launch per group.  A group
         // costs the critical path of one alignment (~110 k rows) however few alignments it holds, so a short last group
@@ -392,8 +392,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                         sjobs.push_back(KswStripJob{strip_ids[x], st, p.n_strips, p.prog_off, p.arena_off, p.edge_off});
                     }
             g.count = (int)sjobs.size() - g.first;
-            g.n_ctas = (int)std::min<size_t>((size_t)g.count, (size_t)ctx->n_sm);
-            if (getenv("LESV_KSW_STRIP_CTAS")) g.n_ctas = std::max(1, std::min(g.n_ctas, atoi(getenv("LESV_KSW_STRIP_CTAS"))));
+            g.n_ctas = (int)std::min<size_t>((size_t)g.count, (size_t)ctx->n_sm * kStripCtasPerSm);
             sgroups.push_back(g);
             x0 = x1;
         }

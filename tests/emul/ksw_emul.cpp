@@ -220,7 +220,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
             for (int b = 0; b < nb; ++b)
                 for (int c = 0; c < 16; ++c) {
                     const uint8_t x = p[r * prow + (size_t)tb_block_slot((g.st0 >> 4) + b, prow_blocks) * 16 + tb_byte_pos(c)];
-                    t[r * prow + (size_t)b * 16 + c] = (uint8_t)((4 - (x & 7)) | ((x >> 7) & 1) << 3 | ((x >> 6) & 1) << 4 |
+                    t[r * prow + (size_t)b * 16 + c] = (uint8_t)((lesvksw::kTagS - (x & 7)) | ((x >> 7) & 1) << 3 | ((x >> 6) & 1) << 4 |
                                                              ((x >> 5) & 1) << 5 | ((x >> 4) & 1) << 6);
                 }
         }

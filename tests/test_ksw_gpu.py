@@ -125,3 +125,36 @@ def test_full_matrix_alignments_as_column_strips(ctx):
     for q, t, r, cg in zip(qs, ts, res, cigs):
         exp, _ = H.oracle_ksw(q, t, -1)
         assert r.ok and [int(x) for x in cg] == exp
+
+
+@pytest.mark.parametrize("switch", ["LESV_KSW_NO_GROUPS", "LESV_KSW_NO_STRIPS"])
+def test_environment_switches_select_tested_paths(switch):
+    """The two environment switches of the scheduler (lesvgpu.cu: narrow bands without lane groups, full-matrix
+    alignments on clusters instead of column strips) select kernels that stay bit-exact: a fresh process per switch
+    (they are read once), narrow-band pairs and full-matrix pairs wider than one CTA against the oracle."""
+    import os, subprocess, sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import helpers as H
+from lesv_b200 import capi
+from lesv_b200.synth import mutate
+rng = np.random.default_rng(5)
+cases = []
+for it in range(60):                                   # bands 8 .. 200: lane groups (or the 32-thread tier)
+    q = rng.integers(0, 4, int(rng.integers(200, 3000)), dtype=np.uint8)
+    t = np.ascontiguousarray(mutate(q, 0.08, rng))
+    cases.append((q, t, abs(len(q) - len(t)) + int(rng.integers(8, 200))))
+for it in range(3):                                    # no band, 11-12 kb: wider than one CTA (strips, or a cluster)
+    q = rng.integers(0, 4, 11000 + 300 * it, dtype=np.uint8)
+    t = np.ascontiguousarray(mutate(q, 0.12, rng))
+    cases.append((q, t, -1))
+ctx = capi.Context(0)
+res, cigs = ctx.ksw_batch([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases])
+for (q, t, w), r, c in zip(cases, res, cigs):
+    exp, _ = H.oracle_ksw(q, t, w)
+    assert r.ok and [int(x) for x in c] == exp, (len(q), len(t), w)
+print("ok", len(cases))
+'''
+    out = subprocess.run([sys.executable, "-c", code], cwd=H.ROOT, env=dict(os.environ, **{switch: "1"}), capture_output=True, text=True)
+    assert out.returncode == 0 and "ok 63" in out.stdout, out.stderr[-2000:]
