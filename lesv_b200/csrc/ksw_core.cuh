@@ -61,6 +61,18 @@
 #define KSW_HDC constexpr
 #endif
 
+// kWK as a constant-bank operand: VIADDMNMX takes one immediate, and ptxas rebuilds a second constant with a MOV per use
+// (8 per block row) rather than keeping it in a register; a __constant__ it cannot fold is read straight from the bank.
+#define KSW_WK_VALUE 0xED02ED02u
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+static __constant__ uint32_t ksw_wk_bank = KSW_WK_VALUE;
+#endif
+#if defined(__CUDA_ARCH__)
+#define KSW_WK ksw_wk_bank
+#else
+#define KSW_WK KSW_WK_VALUE
+#endif
+
 namespace lesvksw {
 
 // ---- scoring in force (ksw2_wrapper.c:83-94) and what ksw_extd2_sse derives from it ----------
@@ -155,6 +167,8 @@ KSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
 }
 #endif
 
+static_assert(kWK == KSW_WK_VALUE, "ksw_wk_bank holds kWK");
+
 // ---- internal traceback byte -------------------------------------------------------------------
 // bits 0-2: 5 - winner (winner 0 H, 1 E, 2 F, 3 E~, 4 F~); bit 7: E continues; bit 6: F continues;
 // bit 5: E~ continues; bit 4: F~ continues; bit 3: 0.  (The reference's own layout, ksw2.h:117-120,
@@ -236,7 +250,7 @@ KSW_HD uint32_t pair_row(BlockState& b, int j, uint32_t s, uint32_t x1, uint32_t
     const uint32_t ka = vadd2(x1, v1), kb = vadd2(b.Y[j], u0);
     const uint32_t ka2 = vadd2(x21, vadd2(v1, kD2)), kb2 = vadd2(b.Y2[j], vadd2(u0, kD2));
     const uint32_t k = vmax3(vmax3(s, ka, kb), ka2, kb2);
-    const uint32_t w = vaddmin(k | 0x00FF00FFu, kWK, kWClamp);
+    const uint32_t w = vaddmin(k | 0x00FF00FFu, KSW_WK, kWClamp);
     const uint32_t n = vadd2(~w, kNQ), n2 = vadd2(n, kNQ2);
     b.U[j] = vadd2(w, ~v1);
     b.V[j] = vadd2(w, ~u0);

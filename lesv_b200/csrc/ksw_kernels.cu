@@ -595,6 +595,13 @@ ksw_dp_group_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ ord
 #define KSW_WALK_SLEEP_NS 4000      // the walker's poll for the next alignment shares a scheduler with DP warps: poll rarely
 #endif
 __device__ __forceinline__ void bar_dp(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+#define KSW_PRAGMA_(x) _Pragma(#x)
+#define KSW_PRAGMA(x) KSW_PRAGMA_(x)
+#ifdef KSW_ROW_UNROLL
+#define KSW_ROW_LOOP_PRAGMA KSW_PRAGMA(unroll KSW_ROW_UNROLL)
+#else
+#define KSW_ROW_LOOP_PRAGMA KSW_PRAGMA(unroll 1)
+#endif
 __device__ __forceinline__ void bar_rows(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }
 
 template <int kTier>                                    // CTA = kTier DP threads + the walker warp: fixes the register budget
@@ -708,6 +715,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                     }
                     bar_rows(NT);
                 }
+                KSW_ROW_LOOP_PRAGMA
                 for (int r = r0; r < r1; ++r, rowp += rstep) {
                     const uint2 nb = carry_sh[(r + 1) & 1][lwarp];
                     Carry cin;
