@@ -281,6 +281,46 @@ def make_reads_c3(contigs, n_reads: int, seed: int, read_len: int = READ_LEN):
     return reads
 
 
+def make_reads_c4(contigs, n_subreads: int, seed: int):
+    """BASELINE.json configs[3]: ultra-long source reads (log-normal, clipped to 150 kb-2.4 Mbp) cut like `qx2splitseq 50000 0
+    20000` cuts them (reference src/app/split_seq/main.c:28-45: 50 kb pieces, a rest below 20 kb stays with the last piece);
+    35 % of the source reads carry 20-30 % error, the others 8-15 % (README.md:90-95); an INS/DEL of 40 bp-10 kb about every
+    250 kb.  Returns exactly n_subreads subreads."""
+    rng = np.random.default_rng(seed)
+    sizes = np.array([len(c) for c in contigs], dtype=np.float64)
+    out = []
+    while len(out) < n_subreads:
+        c = contigs[int(rng.choice(len(contigs), p=sizes / sizes.sum()))]
+        L = int(min(2_400_000, max(150_000, np.exp(rng.normal(np.log(200_000), 0.6)))))
+        L = min(L, len(c) - 20_000)
+        p0 = int(rng.integers(0, len(c) - L - 10_000))
+        pieces, prev = [], p0
+        for _ in range(max(1, L // 250_000)):
+            pos = int(rng.integers(prev + 1000, p0 + L - 1000)) if prev + 1000 < p0 + L - 1000 else None
+            if pos is None:
+                break
+            size = int(np.exp(rng.uniform(np.log(40), np.log(10000))))
+            pieces.append(c[prev:pos])
+            if rng.random() < 0.5:
+                pieces.append(synth.random_codes(size, rng))
+                prev = pos
+            else:
+                prev = min(pos + size, p0 + L)
+        pieces.append(c[prev:p0 + L])
+        err = float(rng.uniform(0.20, 0.30)) if rng.random() < 0.35 else float(rng.uniform(0.08, 0.15))
+        long_read = synth.mutate(np.concatenate(pieces), err, rng)
+        if rng.integers(0, 2):
+            long_read = synth.revcomp_codes(long_read)
+        n, a = len(long_read), 0
+        while a < n:
+            b = min(a + 50_000, n)
+            if n - b < 20_000:
+                b = n
+            out.append(np.ascontiguousarray(long_read[a:b]))
+            a = b
+    return out[:n_subreads]
+
+
 class Batch:
     """One query batch as the drop-in tools hand it to the library: packed reads (.pac layout) in HOST memory."""
 
@@ -293,7 +333,7 @@ class Batch:
         self.nq = len(reads)
 
 
-def run_path(ctx, capi, B: Batch, subj, collect: bool = False):
+def run_path(ctx, capi, B: Batch, subj, collect: bool = False, svr_ident: float = 70.0):
     """One batch through the path: qx2map -> (m4 text round trip) -> qx2svr -> qx2svsig, all through the C ABI with host
     buffers.  Returns per-stage device ms, byte counts and work counts (collect: also the records themselves)."""
     w0 = time.perf_counter()
@@ -302,7 +342,7 @@ def run_path(ctx, capi, B: Batch, subj, collect: bool = False):
     mt, et = capi.map_last_timing(ctx), capi.map_last_extend_timing(ctx)
     m4 = capi.hsps_to_m4(h)
     w2 = time.perf_counter()
-    svr, st = capi.svr_batch(ctx, B.query_pac, B.read_offset, subj["offsets"], subj["sizes"], m4, 3000, 70.0, 300)
+    svr, st = capi.svr_batch(ctx, B.query_pac, B.read_offset, subj["offsets"], subj["sizes"], m4, 3000, svr_ident, 300)
     w3 = time.perf_counter()
     t_svr = ctx.timing() if (st.n_refine_jobs or st.n_chain_jobs) else capi.Timing()
     svr_classes = ctx.class_timing() if (st.n_refine_jobs or st.n_chain_jobs) else []
@@ -441,8 +481,10 @@ def main():
     ap.add_argument("--ref-len", type=int, default=REF_LEN)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 = BASELINE configs[1] (headline); c3 = configs[2]: 24 contigs / 3.1 Gbp (x --c3-scale), index replicated per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 = BASELINE configs[1] (headline); c3 = configs[2]: 24 contigs / 3.1 Gbp (x --c3-scale), index replicated per GPU; "
+                         "c4 = configs[3]: the c3 reference, ultra-long reads split into 50 kb subreads, 35 %% of them at 20-30 %% error, "
+                         "-kmer_size 19 -kmer_window 20, SVR identity 80.0")
     ap.add_argument("--c3-scale", type=float, default=1.0)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank has its own batches; strong: one fixed read set, sub-batches pulled by all ranks from a shared queue")
@@ -453,11 +495,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    c3 = args.workload == "c3"
-    what = ("C3: 24 contigs with hg19's length profile, %.2f Gbp" % (3.098 * args.c3_scale)) if c3 else "C2: 50 Mbp synthetic contig"
-    config = {"workload": what + ", 50 kb subreads at 10-15 % error with planted 40 bp-10 kb INS/DEL"
-                          + (" (every 4th read)" if c3 else " (~1 per 250 kb of the sample genome)") +
-                          "; mapping + SvRead selection + SV signatures (-max_target_seqs 5 -max_hsps 10, SVR 3000/70.0/300, min indel 40)",
+    c4 = args.workload == "c4"
+    c3 = args.workload == "c3" or c4                    # the 24-contig reference
+    kmer, window, svr_ident = (19, 20, 80.0) if c4 else (15, 10, 70.0)
+    if c4:
+        what = ("C4: 24 contigs with hg19's length profile, %.2f Gbp; ultra-long reads (150 kb-2.4 Mbp) cut into 50 kb subreads, 35 %% of "
+                "the source reads at 20-30 %% error, the others at 8-15 %%, INS/DEL of 40 bp-10 kb about every 250 kb" % (3.098 * args.c3_scale))
+    elif c3:
+        what = ("C3: 24 contigs with hg19's length profile, %.2f Gbp, 50 kb subreads at 10-15 %% error with planted 40 bp-10 kb INS/DEL "
+                "(every 4th read)" % (3.098 * args.c3_scale))
+    else:
+        what = ("C2: 50 Mbp synthetic contig, 50 kb subreads at 10-15 % error with planted 40 bp-10 kb INS/DEL (~1 per 250 kb of the "
+                "sample genome)")
+    config = {"workload": what + f"; mapping + SvRead selection + SV signatures (-max_target_seqs 5 -max_hsps 10 -kmer_size {kmer} "
+                                 f"-kmer_window {window}, SVR 3000/{svr_ident}/300, min indel 40)",
               "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN,
               "ref_len": int(sum(HG19_MBP) * 1e6 * args.c3_scale) if c3 else args.ref_len,
               "batches": (f"one read set of {args.batches} batches for the whole job; steps x n_gpus sub-batches pulled by all ranks from a shared queue"
@@ -518,7 +569,7 @@ def main():
     subj["seq_arr"] = capi._seq_array(subj["offsets"], subj["sizes"])
 
     def reads_of(seed, n):
-        return make_reads_c3(contigs, n, seed) if c3 else make_reads(sample, n, seed)
+        return make_reads_c4(contigs, n, seed) if c4 else make_reads_c3(contigs, n, seed) if c3 else make_reads(sample, n, seed)
     if strong:      # one read set for the whole job (every rank holds it; ranks pull sub-batches from the shared queue)
         batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches)]
     else:           # this rank's own batches
@@ -532,7 +583,7 @@ def main():
     lib.lesvgpu_launch_count.restype = C.c_uint64
     capi.subject_load(ctx, subject_pac)
     t0 = time.perf_counter()
-    capi.index_build(ctx, subj["offsets"], subj["sizes"], 15, 10, 200)
+    capi.index_build(ctx, subj["offsets"], subj["sizes"], kmer, window, 200)
     index_ms = (time.perf_counter() - t0) * 1e3
 
     def barrier():
@@ -541,7 +592,7 @@ def main():
         torch.cuda.synchronize()
 
     for k in range(args.warmup):
-        run_path(ctx, capi, batches[k % len(batches)], subj)
+        run_path(ctx, capi, batches[k % len(batches)], subj, svr_ident=svr_ident)
     barrier()
     acc = None
     n_done = 0
@@ -561,7 +612,7 @@ def main():
                     break
                 B = batches[(args.warmup + k) % len(batches)]
             k += 1
-            r = run_path(ctx, capi, B, subj)
+            r = run_path(ctx, capi, B, subj, svr_ident=svr_ident)
             n_done += 1
             if acc is None:
                 acc = {key: (dict(v) if isinstance(v, dict) and key in ("dev", "wall") else v) for key, v in r.items()}
@@ -612,7 +663,7 @@ def main():
                           "gcups_over_done_ms": e["cells"] / max(e["done_ms"], 1e-9) / 1e6}
                    for name, e in acc["class_sum"].items()}
         line = {
-            "metric": METRIC_C3 if c3 else METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
+            "metric": METRIC.replace("C2", "C4") if c4 else METRIC_C3 if c3 else METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": config,
