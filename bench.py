@@ -657,7 +657,7 @@ def main():
             n_done += 1
             if acc is None:
                 acc = {key: (dict(v) if isinstance(v, dict) and key in ("dev", "wall") else v) for key, v in r.items()}
-                acc["class_sum"] = {}
+                acc["class_sum"], acc["class_sum_svr"] = {}, {}
             else:
                 for key in ("dp_ms", "sig_dp_ms", "sig_cells", "svr_dp_ms", "svr_cells", "cells", "dp_launches", "sig_launches", "bases",
                             "n_unsupported"):
@@ -666,11 +666,13 @@ def main():
                     acc["dev"][key] += r["dev"][key]
                 for key in acc["wall"]:
                     acc["wall"][key] += r["wall"][key]
-            for c in r["classes"]["svsig"]:
-                name = ("strips" if c["ctas_per_alignment"] < 0 else "global-memory fallback" if c["ctas_per_alignment"] == 0 else
-                        f"{c['ctas_per_alignment']}-CTA cluster" if c["ctas_per_alignment"] > 1 else f"single CTA, {c['threads']} threads")
-                e = acc["class_sum"].setdefault(name, {"alignments": 0, "cells": 0, "done_ms": 0.0, "ctas": c["n_ctas"]})
-                e["alignments"] += c["n_alignments"]; e["cells"] += c["cells"]; e["done_ms"] += c["done_ms"]
+            for stage, key in (("svsig", "class_sum"), ("svr_last_round", "class_sum_svr")):
+                for c in r["classes"][stage]:
+                    name = ("strips" if c["ctas_per_alignment"] < 0 else "global-memory fallback" if c["ctas_per_alignment"] == 0 else
+                            f"{c['ctas_per_alignment']}-CTA cluster" if c["ctas_per_alignment"] > 1 else
+                            f"{32 // c['threads']} alignments per warp" if c["threads"] <= 16 else f"single CTA, {c['threads']} threads")
+                    e = acc.setdefault(key, {}).setdefault(name, {"alignments": 0, "cells": 0, "done_ms": 0.0, "ctas": c["n_ctas"]})
+                    e["alignments"] += c["n_alignments"]; e["cells"] += c["cells"]; e["done_ms"] += c["done_ms"]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
     launches = lib.lesvgpu_launch_count() - launches0
@@ -699,10 +701,11 @@ def main():
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
         int_peak = n_sm * 128 * f_mhz * 1e6 / OPS_PER_CELL * LANES_PACKED / 1e9      # GCUPS, SURVEY.md 8d
         kern_gcups = acc["sig_cells"] / (max(acc["sig_dp_ms"], 1e-9) / 1e3) / 1e9    # rank 0's qx2svsig DP launches
-        classes = {name: {"alignments_per_step": e["alignments"] / max(1, n_done), "gcells_per_step": e["cells"] / max(1, n_done) / 1e9,
-                          "ctas": e["ctas"], "done_ms_per_step": e["done_ms"] / max(1, n_done),
-                          "gcups_over_done_ms": e["cells"] / max(e["done_ms"], 1e-9) / 1e6}
-                   for name, e in acc["class_sum"].items()}
+        def class_table(cs):
+            return {name: {"alignments_per_step": e["alignments"] / max(1, n_done), "gcells_per_step": e["cells"] / max(1, n_done) / 1e9,
+                           "ctas": e["ctas"], "done_ms_per_step": e["done_ms"] / max(1, n_done),
+                           "gcups_over_done_ms": e["cells"] / max(e["done_ms"], 1e-9) / 1e6} for name, e in cs.items()}
+        classes = class_table(acc.get("class_sum", {}))
         line = {
             "metric": METRIC.replace("C2", "C4") if c4 else METRIC_C3 if c3 else METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
@@ -722,6 +725,7 @@ def main():
                                  "svsig_gcups": kern_gcups,
                                  "svr_svsig_gcups": acc["cells"] / (max(acc["dp_ms"], 1e-9) / 1e3) / 1e9},
             "svsig_launch_classes": classes,
+            "svr_launch_classes": class_table(acc.get("class_sum_svr", {})),
             "roofline": {"bound": "int-issue", "kernel": "ksw_dp_overlap_kernel (single-CTA classes; ksw_dp_kernel for cluster classes)", "achieved": kern_gcups, "peak": int_peak,
                          "unit": "GCUPS", "frac": kern_gcups / int_peak,
                          "peak_def": f"{n_sm} SMs x 128 lanes x {f_mhz:.0f} MHz (median under load) / {OPS_PER_CELL} ops per cell x "

@@ -52,7 +52,7 @@ typedef struct {
 } lesvgpu_timing;
 void lesvgpu_last_timing(const lesvgpu_ctx* ctx, lesvgpu_timing* t);
 /* Launch classes of the last K-ksw batch (lesvgpu_ksw_batch, lesvgpu_align_refine_batch, lesvgpu_svsig_batch; for
- * lesvgpu_svr_batch: of its last alignment round).  The classes of a batch run concurrently on one GPU, so
+ * lesvgpu_svr_batch: of its two alignment rounds, one after the other).  The classes of a batch run concurrently on one GPU, so
  * done_ms is the time from the start of the first launch to the moment this class had finished. */
 typedef struct {
     int ctas_per_alignment;  /* 1 = single CTA, 2..16 = thread-block cluster, 0 = global-memory fallback, -1 = column strips */

@@ -142,7 +142,9 @@ extern "C" int lesvgpu_svr_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
     std::vector<SvRead>& out = ctx->svreads;
     out.clear();
     lesvgpu_timing acc = {};
+    std::vector<lesvgpu_class_timing> classes;          // launch classes of both alignment rounds
     auto add_timing = [&]() {
+        classes.insert(classes.end(), ctx->classes.begin(), ctx->classes.end());
         const lesvgpu_timing& t = ctx->timing;
         acc.h2d_ms += t.h2d_ms; acc.pack_ms += t.pack_ms; acc.dp_ms += t.dp_ms; acc.scan_ms += t.scan_ms; acc.d2h_ms += t.d2h_ms;
         acc.dp_launches += t.dp_launches; acc.kernel_launches += t.kernel_launches;
@@ -316,6 +318,7 @@ extern "C" int lesvgpu_svr_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
     // input (query id) order so the result is reproducible.
     std::stable_sort(out.begin(), out.end(), [](const SvRead& a, const SvRead& b) { return a.query_id < b.query_id; });
     ctx->timing = acc;
+    ctx->classes = classes;
     if (stats) { stats->n_m4 = m4c; stats->n_refine_jobs = jobs.size(); stats->n_chain_jobs = chain_jobs.size(); }
     *out_reads = out.data();
     *n_out = (int)out.size();
