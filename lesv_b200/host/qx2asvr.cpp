@@ -143,7 +143,10 @@ void sam_record(const CnsRead& R, const char* read_name, const char* subject_nam
     sam_cigar_md(q, s, cigar_s, md);
     char buf[256];
     out += read_name;
-    snprintf(buf, sizeof buf, "\t%d\t%s\t%d\t%d\t", R.read_dir != 0 ? 0x10 : 0, subject_name, R.sfrom + sif + 1, 60);
+    snprintf(buf, sizeof buf, "\t%d\t", R.read_dir != 0 ? 0x10 : 0);
+    out += buf;
+    out += subject_name;                                        // names are not bounded: no %s into the fixed buffer
+    snprintf(buf, sizeof buf, "\t%d\t%d\t", R.sfrom + sif + 1, 60);
     out += buf;
     out += cigar_s;                                             // qoff 0, qend == qsize: no soft clips (:151)
     out += "\t*\t*\t0\t";
@@ -211,6 +214,7 @@ int main(int argc, char* argv[])
                     r.length = reads.size(id);
                     if (r.sid != sid) die("consensus read of another contig in " + fasta + ": " + name);
                     if (r.sfrom < 0 || r.sto > subj.size(sid) || r.sfrom >= r.sto) die("reference window outside the contig: " + name);
+                    if (r.cns_from < 0 || r.cns_to > r.length || r.cns_from >= r.cns_to) die("consensus range outside the read: " + name);
                     r.read.resize((size_t)r.length);
                     const size_t qoff = reads.seqs[id].seq_offset, soff = subj.seqs[sid].seq_offset;
                     for (int x = 0; x < r.length; ++x)                                     // RawReadReader_ExtractRead on strand read_dir

@@ -150,7 +150,10 @@ void format_hsp(const Options& o, const lesvgpu_hsp& h, const uint8_t* ops, cons
         return;
     }
     char buf[512];
-    snprintf(buf, sizeof buf, "%s\t%s\t%g\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lld", qv.name(qid_l), sv.name(sid_l), ident, score, h.qdir,
+    out += qv.name(qid_l);                              // names are not bounded: appended, not formatted into the fixed buffer
+    out.push_back('\t');
+    out += sv.name(sid_l);
+    snprintf(buf, sizeof buf, "\t%g\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%lld", ident, score, h.qdir,
              qoff, qend, h.qsize, 0, h.soff, h.send, (long long)h.ssize);
     out += buf;
     if (o.cigar) {                                      // print_paf_cigar / print_cigar_core :27-62 (roles swapped there)
