@@ -96,3 +96,23 @@ def test_qx2splitseq_equals_reference(tmp_path):
             assert a == b, (inp, args)
             n += a.count(b">")
     assert n > 100
+
+
+def test_trf_loader_rejects_what_the_reference_asserts(tmp_path):
+    """TrfArrayBuild (app/necat2sv/trf_array.cpp:31-46) asserts three tab-separated columns, from < to and to <= contig size;
+    the shared loader of qx2svr / qx2svsig (host/lesv_db.hpp) dies on the same lines instead of writing past the mask.
+    The mask is loaded before any GPU is touched, so this runs without one."""
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(H.ROOT, "lesv_b200", "csrc"), "../bin/qx2svsig"], check=True)
+    gold = os.path.join(H.ROOT, "tests", "golden", "svsig_small")
+    S = H.LesvDb(os.path.join(gold, "db"), "subject")
+    name, size = S.name(0), int(S.seq_size[0])
+    tool = os.path.join(H.ROOT, "lesv_b200", "bin", "qx2svsig")
+    for bad, msg in ((f"{name}\t10\t20\textra\n", "3 tab-separated columns"), (f"{name}\t30\t30\n", "from >= to"),
+                     (f"{name}\t5\t{size + 1}\n", "behind the contig"), (f"{name} 10 20\n", "3 tab-separated columns"),
+                     (f"{name}\tx\t20\n", "bad interval")):
+        bed = tmp_path / "bad.bed"
+        bed.write_text(f"{name}\t0\t100\nunknown_contig\t5\t50\n" + bad)
+        r = subprocess.run([tool, str(tmp_path / "out"), os.path.join(gold, "svr"), os.path.join(gold, "db"), "40", "1", str(bed)],
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and msg in r.stderr, (bad, r.stderr[-300:])
