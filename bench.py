@@ -552,8 +552,9 @@ def main():
                                  f"-kmer_window {window}, SVR 3000/{svr_ident}/300, min indel 40)",
               "reads_per_step_per_gpu": args.reads_per_step, "read_len": READ_LEN,
               "ref_len": int(sum(HG19_MBP) * 1e6 * args.c3_scale) if c3 else args.ref_len,
-              "batches": (f"one read set of {args.batches} batches for the whole job; steps x n_gpus sub-batches pulled by all ranks from a shared queue"
-                          if args.scaling == "strong" else f"{args.batches} distinct read batches per GPU, cycled step by step (warm-up included)"),
+              "batches": (f"a pool of {args.batches} distinct read batches; steps x {args.batches} sub-batches for the whole job, pulled by all ranks from a shared queue"
+                          if args.scaling == "strong" else f"a pool of {args.batches} distinct read batches, cycled step by step by every GPU from its own "
+                                                           "starting point (warm-up included): equal work per GPU when steps is a multiple of the pool size"),
               "l2": "every step maps another batch and writes > 100 GB of traceback: far beyond the 126 MB L2",
               "seed": args.seed}
 
@@ -611,10 +612,11 @@ def main():
 
     def reads_of(seed, n):
         return make_reads_c4(contigs, n, seed) if c4 else make_reads_c3(contigs, n, seed) if c3 else make_reads(sample, n, seed)
-    if strong:      # one read set for the whole job (every rank holds it; ranks pull sub-batches from the shared queue)
-        batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches)]
-    else:           # this rank's own batches
-        batches = [Batch(reads_of(shard.read_seed_of_rank(args.seed, rank) + b, args.reads_per_step), capi) for b in range(n_batches)]
+    # One pool of read batches, the same on every rank.  weak: every rank cycles through the whole pool, each from its own
+    # starting point, so all ranks do the same work (the slowest rank's time then shows the system, not its draw of reads: with
+    # a private read set per rank the spread between draws alone cost 4-5 % at 8 GPUs); strong: steps x batches sub-batches
+    # for the whole job, pulled by all ranks from a shared queue.
+    batches = [Batch(reads_of(args.seed + 500 + b, args.reads_per_step), capi) for b in range(n_batches)]
     if c3:
         subject_bases = sum(subj["sizes"])
         del contigs
@@ -633,12 +635,12 @@ def main():
         torch.cuda.synchronize()
 
     for k in range(args.warmup):
-        run_path(ctx, capi, batches[k % len(batches)], subj, svr_ident=svr_ident)
+        run_path(ctx, capi, batches[(rank + k) % len(batches)], subj, svr_ident=svr_ident)
     barrier()
     acc = None
     n_done = 0
     launches0 = lib.lesvgpu_launch_count()
-    queue = shard.WorkQueue(args.steps * world, world) if strong else None
+    queue = shard.WorkQueue(args.steps * n_batches, world) if strong else None
     with ClockSampler(local_rank, active=(rank == 0)) as clk:
         t0 = time.perf_counter()
         k = 0
@@ -651,7 +653,7 @@ def main():
             else:
                 if k >= args.steps:
                     break
-                B = batches[(args.warmup + k) % len(batches)]
+                B = batches[(rank + args.warmup + k) % len(batches)]
             k += 1
             r = run_path(ctx, capi, B, subj, svr_ident=svr_ident)
             n_done += 1
@@ -689,7 +691,7 @@ def main():
     dev_hi, dev_mean, dev_lo = shard.spread(dev_ms, world, device="cuda")
 
     if rank == 0:
-        K = args.steps
+        K = args.steps * n_batches / world if strong else args.steps       # steps per rank
         clocks = clk.summary()
         peaks = {}
         try:
@@ -708,7 +710,7 @@ def main():
         classes = class_table(acc.get("class_sum", {}))
         line = {
             "metric": METRIC.replace("C2", "C4") if c4 else METRIC_C3 if c3 else METRIC, "value": all_bases / (dev_ms_max / 1e3), "unit": "bases/s",
-            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int8",
             "data": "synthetic", "config": config,
             "gcups": all_cells / (acc["dp_ms"] / 1e3) / 1e9 if world == 1 else None,
