@@ -209,31 +209,39 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
             arena_limit = std::min(arena_limit, (size_t)((free_b + ctx->d_arena.cap) * 0.90));
     }
-    const size_t strip_cap = arena_limit / 4 * 3;
+    std::vector<std::pair<size_t, size_t>> strip_groups;            // [first, last) into strip_ids, one launch each
     if (use_strips) {
         std::vector<int> cand;
         for (int k = 0; k < nj; ++k) {
             const KswJob& J = jobs[k];
             if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > kTierTop) cand.push_back(k);
         }
-        // They are processed in groups whose arenas fit into three quarters of the budget, one launch per group.  A group
-        // costs the critical path of one alignment (~110 k rows) however few alignments it holds, so a short last group
-        // (<= 15 alignments: one round of 8-CTA clusters) takes the cluster route next to the strips instead.
-        const size_t cap = strip_cap;
-        size_t group = 0, group_first = 0;
-        for (int k : cand) {
+        // A full-matrix alignment of 50 kb x 60 kb is 3.3 GB of traceback, and every alignment of a strip launch needs its
+        // own arena: they are processed in groups that fit the budget -- all of it when the batch holds nothing else (the
+        // chaining round of qx2svr), three quarters next to other launch classes -- one launch per group, the groups about
+        // equally large (a launch costs the critical path of one alignment however few alignments it holds).
+        const size_t cap = (int)cand.size() == nj ? arena_limit / 20 * 19 : arena_limit / 4 * 3;
+        auto tb_of = [&](int k) {
             const KswJob& J = jobs[k];
-            const size_t tb = ((size_t)(J.qlen + J.tlen - 1) * (size_t)tb_row_blocks(J.qlen, J.tlen, J.w) * 16 + 255) & ~(size_t)255;
+            return ((size_t)(J.qlen + J.tlen - 1) * (size_t)tb_row_blocks(J.qlen, J.tlen, J.w) * 16 + 255) & ~(size_t)255;
+        };
+        size_t total = 0;
+        for (int k : cand) if (tb_of(k) <= cap) total += tb_of(k);
+        const size_t n_groups = std::max<size_t>(1, (total + cap - 1) / cap);
+        const size_t target = (total + n_groups - 1) / n_groups;
+        size_t group = 0, first = 0;
+        for (int k : cand) {
+            const size_t tb = tb_of(k);
             if (tb > cap) continue;                         // a single alignment that large takes the cluster / wide route
-            if (group + tb > cap) { group = 0; group_first = strip_ids.size(); }
+            if (group > 0 && (group + tb > cap || group >= target)) {
+                strip_groups.emplace_back(first, strip_ids.size());
+                first = strip_ids.size(); group = 0;
+            }
             group += tb;
             strip_arena = std::max(strip_arena, group);
             strip_ids.push_back(k); is_strip[k] = 1;
         }
-        if (group_first > 0 && strip_ids.size() - group_first <= 15) {
-            for (size_t x = group_first; x < strip_ids.size(); ++x) is_strip[strip_ids[x]] = 0;
-            strip_ids.resize(group_first);
-        }
+        if (strip_ids.size() > first) strip_groups.emplace_back(first, strip_ids.size());
     }
     for (int k = 0; k < nj; ++k) {
         KswJob& J = jobs[k];
@@ -363,16 +371,14 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     int prog_ints = 0, strip_smem_q = 0, strip_smem_t = 0;
     if (!strip_ids.empty()) {
         struct Per { int n_strips, prog_off; size_t arena_off, edge_off; };
-        const size_t cap = strip_cap;
-        size_t x0 = 0;
-        while (x0 < strip_ids.size()) {                  // a group = consecutive alignments (input order) whose arenas fit
-            size_t x1 = x0, aoff = arena_need;
+        for (const auto& range : strip_groups) {
+            const size_t x0 = range.first, x1 = range.second;
+            size_t aoff = arena_need;
             std::vector<Per> per;
             int max_strips = 0;
-            while (x1 < strip_ids.size()) {
-                const size_t tb = (tb_bytes[strip_ids[x1]] + 255) & ~(size_t)255;
-                if (x1 > x0 && aoff - arena_need + tb > cap) break;
-                const KswJob& J = jobs[strip_ids[x1]];
+            for (size_t x = x0; x < x1; ++x) {
+                const size_t tb = (tb_bytes[strip_ids[x]] + 255) & ~(size_t)255;
+                const KswJob& J = jobs[strip_ids[x]];
                 const int max_b = ((J.tlen - 1) >> 4) + 1;
                 Per p;
                 p.n_strips = (max_b + 1 + kStripBlocks - 1) / kStripBlocks;
@@ -382,7 +388,6 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
                 max_strips = std::max(max_strips, p.n_strips);
                 strip_smem_q = std::max(strip_smem_q, J.qlen); strip_smem_t = std::max(strip_smem_t, J.tlen);
                 per.push_back(p);
-                ++x1;
             }
             StripGroup g{(int)sjobs.size(), 0, 0};
             for (int st = 0; st < max_strips; ++st)        // (strip, alignment) order: a strip's predecessor is always handed out first
@@ -394,7 +399,6 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             g.count = (int)sjobs.size() - g.first;
             g.n_ctas = (int)std::min<size_t>((size_t)g.count, (size_t)ctx->n_sm * kStripCtasPerSm);
             sgroups.push_back(g);
-            x0 = x1;
         }
         arena_need += strip_arena;
         CK(ctx->d_sjobs.reserve(sjobs.size()));
