@@ -397,12 +397,12 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
 {
     Carry eager = carry_init();
     if (kEager) eager = carry();
+    const bool fast = row_is_fast(c, r);
     // carry policy of this row: 0 = take what the left neighbour published, 1 = matrix edge
     // (column 0), 2 = the left block was not computed one row earlier (initial values)
     int policy = 0;
     uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
     bool pre_block = false;
-    const bool fast = row_is_fast(c, r);
     if (!(kVote ? warp_all(fast) : fast)) {
         const RowGeom g = row_geom(r, qlen, tlen, w);
         if (!fast) {

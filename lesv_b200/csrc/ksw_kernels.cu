@@ -614,7 +614,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
 {
     extern __shared__ uint32_t seq_s[];                 // two halves of half_words words
     __shared__ BtShared bt;
-    __shared__ uint2 carry_sh[2][kMaxWarps];
+    __shared__ __align__(512) uint2 carry_sh[2][32];   // 256 bytes per row parity: the two parities differ in one address bit
     __shared__ int sh_job;
     __shared__ int wk_jid[2];
     __shared__ volatile int wk_posted, wk_done, wk_finished, wk_row;
@@ -696,6 +696,8 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         // them; the others wait at the all-warps barrier (1) behind it.  Rows come in chunks of 256: before a chunk the
         // first logical warp checks that its rows do not reach into what walk m-1 still needs (rows <= wk_row of it).
         if (lwarp < NW) {
+            // column-15 values by row parity and consumer warp; both addresses flip one bit per row
+            uint32_t carry_rd = smem_addr(&carry_sh[1][lwarp]), carry_wr = smem_addr(&carry_sh[0][wnext]);
             for (int r0 = 0; r0 < nrow_all; r0 += 256) {
                 const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
                 if (m > 0) {
@@ -717,7 +719,8 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                 }
                 KSW_ROW_LOOP_PRAGMA
                 for (int r = r0; r < r1; ++r, rowp += rstep) {
-                    const uint2 nb = carry_sh[(r + 1) & 1][lwarp];
+                    uint2 nb;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nb.x), "=r"(nb.y) : "r"(carry_rd) : "memory");
                     Carry cin;
                     cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
                     cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
@@ -729,7 +732,9 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                         *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
                         prev_out = cout;
                     }
-                    if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
+                    if (lane == 31)
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                    carry_rd ^= 256u; carry_wr ^= 256u;
                     bar_rows(NT);
                 }
             }
