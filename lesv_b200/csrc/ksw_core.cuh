@@ -410,7 +410,18 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
             // leaving the fast stretch: the score bits were not tracked there (every column was fresh every row)
             if (c.fast_n > 0 && r == c.fast_lo + c.fast_n)
                 c.b.sbits = mismatch_bits(c.tword, query_window(c, qrp, qlen, r - 1, c.myB));
-            while (c.cand < bst) c.cand += nt;  // the band left this thread's block behind: take the next one
+            // the band left this thread's block behind: take the next one.  One step is the rule (the band moves by at most one
+            // block per row); the loop behind it serves the kernels that visit a slot only now and then, and the empty asm
+            // keeps the compiler from turning it into a division inside every row.
+            if (c.cand < bst) {
+                c.cand += nt;
+                while (c.cand < bst) {
+#if defined(__CUDA_ARCH__)
+                    asm volatile("" : "+r"(c.cand));
+#endif
+                    c.cand += nt;
+                }
+            }
             const int B = c.cand;
             if (B > bwr) return false;
             if (B != c.myB) {                   // take ownership of a new block
