@@ -3,6 +3,26 @@
 
 std::atomic<unsigned long long> g_lesv_launches{0};   // several feeder threads (one per GPU) count here
 
+#include <mutex>
+#include <set>
+#include <utility>
+cudaError_t lesv_allow_max_smem(const void* func)
+{
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, func})) return cudaSuccess;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) done.insert({dev, func});
+    return e;
+}
+
 namespace lesvmap {
 
 // ---------------------------------------------------------------------------------------------

@@ -13,6 +13,13 @@
 #include <atomic>
 extern std::atomic<unsigned long long> g_lesv_launches;
 
+// The dynamic-shared-memory ceiling of a kernel is a property of the FUNCTION, shared by every context and feeder thread of
+// the process (one per device): a launch that raises it to what it needs can see another thread lower it again before
+// the kernel is issued ("invalid argument", one run in ten with three feeders).  It is raised once per device, to the
+// device's opt-in maximum, and never touched again; what a launch really uses is still its own dynamicSmemBytes.
+cudaError_t lesv_allow_max_smem(const void* func);
+template <class F> inline cudaError_t lesv_allow_max_smem(F* func) { return lesv_allow_max_smem(reinterpret_cast<const void*>(func)); }
+
 namespace lesvmap {
 
 // out[i] = sum_{j<i} in[j]; returns nothing, the grand total lands in *d_total (may be null).

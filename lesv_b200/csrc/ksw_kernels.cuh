@@ -61,7 +61,10 @@ __host__ __device__ static inline uint32_t qrp_words(int qlen) { return (uint32_
 #define KSW_TIER_MID 480
 #define KSW_TIER_TOP 608
 #endif
-constexpr int kTierLow = 320, kTierMid = KSW_TIER_MID, kTierTop = KSW_TIER_TOP;
+#ifndef KSW_TIER_LOW
+#define KSW_TIER_LOW 320
+#endif
+constexpr int kTierLow = KSW_TIER_LOW, kTierMid = KSW_TIER_MID, kTierTop = KSW_TIER_TOP;
 // Band windows of <= 8 / <= 16 blocks (bands up to 64 / 192 columns): 4 / 2 alignments per warp (ksw_dp_group_kernel).
 // For these classes the "clusters" of a launch are lane groups and `nt` is the group size.
 constexpr int kGroupTierMax = 16;

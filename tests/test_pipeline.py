@@ -218,11 +218,14 @@ def test_tools_write_the_same_files_for_any_number_of_feeders(tmp_path):
         env = dict(os.environ, LESV_GPUS=gl, LESV_SVSIG_BATCH="7", LESV_SVR_CHUNK="5")
         env.pop("LESV_GPU", None)
         with open(os.path.join(work, "gpu.map.m4"), "wb") as f, open(os.path.join(work, "gpu.log"), "ab") as log:
-            subprocess.run([os.path.join(BIN, "qx2map"), "-max_target_seqs", "5", "-max_hsps", "10", "-query_batch_size", "20k",
-                            "-db_dir", "db_gpu", "-keep_db", "split.fa", "ref.fa"], cwd=work, check=True, stdout=f, stderr=log, env=env)
-            subprocess.run([os.path.join(BIN, "qx2m4x"), "db_gpu"], cwd=work, check=True, stderr=log)
-            subprocess.run([os.path.join(BIN, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", "4"], cwd=work, check=True, stderr=log, env=env)
-            subprocess.run([os.path.join(BIN, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", "4"], cwd=work, check=True, stderr=log, env=env)
+            for cmd, out in (([os.path.join(BIN, "qx2map"), "-max_target_seqs", "5", "-max_hsps", "10", "-query_batch_size", "20k",
+                               "-db_dir", "db_gpu", "-keep_db", "split.fa", "ref.fa"], f),
+                             ([os.path.join(BIN, "qx2m4x"), "db_gpu"], None),
+                             ([os.path.join(BIN, "qx2svr"), "svr_gpu", "db_gpu", "3000", "70.0", "300", "4"], None),
+                             ([os.path.join(BIN, "qx2svsig"), "svsig_gpu", "svr_gpu", "db_gpu", "40", "4"], None)):
+                rc = subprocess.run(cmd, cwd=work, stdout=out, stderr=log, env=env).returncode
+                log.flush()
+                assert rc == 0, (gl, cmd[0], rc, open(os.path.join(work, "gpu.log"), errors="replace").read()[-1500:])
         log = open(os.path.join(work, "gpu.log"), errors="replace").read()
         assert f"on {len(gl.split(','))} GPU(s)" in log, log
         t = _tree(work, ["svr_gpu", "svsig_gpu", "db_gpu/backup_results"])
