@@ -3,23 +3,21 @@
 
 std::atomic<unsigned long long> g_lesv_launches{0};   // several feeder threads (one per GPU) count here
 
+#include <map>
 #include <mutex>
-#include <set>
 #include <utility>
-cudaError_t lesv_allow_max_smem(const void* func)
+cudaError_t lesv_need_smem(const void* func, size_t bytes)
 {
     static std::mutex mu;
-    static std::set<std::pair<int, const void*>> done;
+    static std::map<std::pair<int, const void*>, size_t> ceiling;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lock(mu);
-    if (done.count({dev, func})) return cudaSuccess;
-    int optin = 0;
-    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) done.insert({dev, func});
+    size_t& have = ceiling[{dev, func}];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
     return e;
 }
 

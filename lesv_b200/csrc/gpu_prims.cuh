@@ -14,11 +14,13 @@
 extern std::atomic<unsigned long long> g_lesv_launches;
 
 // The dynamic-shared-memory ceiling of a kernel is a property of the FUNCTION, shared by every context and feeder thread of
-// the process (one per device): a launch that raises it to what it needs can see another thread lower it again before
-// the kernel is issued ("invalid argument", one run in ten with three feeders).  It is raised once per device, to the
-// device's opt-in maximum, and never touched again; what a launch really uses is still its own dynamicSmemBytes.
-cudaError_t lesv_allow_max_smem(const void* func);
-template <class F> inline cudaError_t lesv_allow_max_smem(F* func) { return lesv_allow_max_smem(reinterpret_cast<const void*>(func)); }
+// the process (one per device): a launch that sets it to what it needs can see another thread lower it again before the
+// kernel is issued ("invalid argument", one run in ten with three feeders on a device).  lesv_need_smem only ever RAISES
+// the ceiling of (device, function), under a lock, to the largest amount any launch has asked for so far -- not to the
+// device maximum: the driver sizes the shared-memory carve-out by this attribute, and the maximum costs the kernels
+// 1-2 % through the smaller L1.
+cudaError_t lesv_need_smem(const void* func, size_t bytes);
+template <class F> inline cudaError_t lesv_need_smem(F* func, size_t bytes) { return lesv_need_smem(reinterpret_cast<const void*>(func), bytes); }
 
 namespace lesvmap {
 

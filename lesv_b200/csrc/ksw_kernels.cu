@@ -994,7 +994,7 @@ void launch_ksw_wide(int n_ctas, size_t smem, const KswJob* d_jobs, const int* d
                      size_t scratch_stride_words, int max_slots, uint32_t* d_cigar, KswGapRun* d_runs,
                      KswOut* d_out, int* d_counter, cudaStream_t s)
 {
-    lesv_allow_max_smem(ksw_dp_wide_kernel);
+    lesv_need_smem(ksw_dp_wide_kernel, smem);
     ksw_dp_wide_kernel<<<n_ctas, kWideNT, smem, s>>>(d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                                      d_scratch, scratch_stride_words, max_slots, d_cigar,
                                                      d_runs, d_out, d_counter);
@@ -1045,17 +1045,17 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 #else
             auto kern = nt <= kTierLow ? ksw_dp_overlap_kernel<kTierLow> : nt <= kTierMid ? ksw_dp_overlap_kernel<kTierMid> : ksw_dp_overlap_kernel<kTierTop>;
 #endif
-            lesv_allow_max_smem(kern);
+            lesv_need_smem(kern, 2 * smem);
             cfg.blockDim = dim3((unsigned)nt + 32); cfg.dynamicSmemBytes = 2 * smem;
             return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                       (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
         }
-        lesv_allow_max_smem(ksw_dp_kernel<false>);
+        lesv_need_smem(ksw_dp_kernel<false>, smem);
         cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
         return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<false>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                   d_cigar, d_runs, d_out, d_counter);
     }
-    lesv_allow_max_smem(ksw_dp_kernel<true>);
+    lesv_need_smem(ksw_dp_kernel<true>, smem);
     if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
     cfg.blockDim = dim3((unsigned)nt);
@@ -1071,7 +1071,7 @@ cudaError_t launch_ksw_strips(int n_ctas, size_t smem, const KswJob* d_jobs, con
                               const uint32_t* d_pool, uint8_t* d_arena, uint2* d_edges, int* d_progress,
                               uint32_t* d_cigar, KswGapRun* d_runs, KswOut* d_out, int* d_counter, cudaStream_t s)
 {
-    lesv_allow_max_smem(ksw_dp_strip_kernel);
+    lesv_need_smem(ksw_dp_strip_kernel, smem);
     ksw_dp_strip_kernel<<<n_ctas, kStripNT, smem, s>>>(d_jobs, static_cast<const StripJob*>(d_sjobs), n_sjobs, d_pool, d_arena,
                                                        d_edges, d_progress, d_cigar, d_runs, d_out, d_counter);
     return cudaGetLastError();
@@ -1082,7 +1082,7 @@ int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
     KswKernelFn kern = ksw_dp_kernel<true>;
-    lesv_allow_max_smem(kern);
+    lesv_need_smem(kern, smem);
     if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;

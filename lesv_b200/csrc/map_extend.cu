@@ -830,7 +830,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
         if (seed_cap >= 0xFFFFFFF0ull) { ctx->err = "too many MEM-stage seeds in one batch"; return LESVGPU_E_NOMEM; }
         CK(E->d_keys0.reserve(seed_cap)); CK(E->d_keys1.reserve(seed_cap));
         CK(cudaMemsetAsync(E->d_counters.p, 0, sizeof(uint32_t) * 8, s));
-        CK(lesv_allow_max_smem(ihf_kernel));
+        CK(lesv_need_smem(ihf_kernel, smem_bytes));
         ihf_kernel<<<ctas, kIhfThreads, smem_bytes, s>>>(E->d_wins.p, n_win, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, word, stride,
                                                          smem_words, E->d_gscratch.p, gstride, E->d_keys0.p, (uint32_t)seed_cap,
                                                          E->d_counters.p, E->d_win_count.p, E->d_counters.p + 1); ++g_lesv_launches;

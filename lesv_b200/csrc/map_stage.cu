@@ -593,7 +593,7 @@ extern "C" int lesvgpu_map_candidates(lesvgpu_ctx* ctx, const uint8_t* query_pac
     ix.off = M->d_off.p; ix.dir_hash = M->d_dir_hash.p; ix.dir_start = M->d_dir_start.p; ix.bucket = M->d_bucket.p;
     ix.qcount = M->d_qcount.p; ix.n_dir = M->n_dir; ix.k = k; ix.bucket_shift = 2 * k - M->bucket_bits;
     int smem_cap = (int)std::min<uint32_t>(max_read_bytes, 160 * 1024);
-    CK(lesv_allow_max_smem(seed_kernel<0>));
+    CK(lesv_need_smem(seed_kernel<0>, (size_t)smem_cap));
     uint32_t n_match = 0;
     if (nkm) {
         seed_kernel<0><<<2 * nr, 256, smem_cap, s>>>(M->d_qpac.p, M->d_reads.p, ix, smem_cap, M->d_slot.p, nullptr,
