@@ -401,11 +401,19 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
     // carry policy of this row: 0 = take what the left neighbour published, 1 = matrix edge
     // (column 0), 2 = the left block was not computed one row earlier (initial values)
     int policy = 0;
-    uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
-    bool pre_block = false;
-    if (!(kVote ? warp_all(fast) : fast)) {
-        const RowGeom g = row_geom(r, qlen, tlen, w);
+    uint32_t S[8];
+    if (kVote ? warp_all(fast) : fast) {
+        // every column of the block is rewritten this row and the block was held one row ago: no geometry, no score-bit
+        // bookkeeping, and the query window moves by one base (a new word every 16 rows)
+        const int qrel = qlen - 1 - r;
+        if ((qrel & 15) == 15) { c.qhi = c.qlo; c.qwi = (qrel >> 4) + 1 + c.myB; c.qlo = qrp[c.qwi]; }
+        const uint32_t x = c.tword ^ funnel_r(c.qlo, c.qhi, 2 * qrel);     // the shift amount is taken mod 32
+        score_lanes(x | (x >> 1), true, S);                                 // odd bits: don't care
+    } else {
+        uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
+        bool pre_block = false;
         if (!fast) {
+            const RowGeom g = row_geom(r, qlen, tlen, w);
             const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
             // leaving the fast stretch: the score bits were not tracked there (every column was fresh every row)
             if (c.fast_n > 0 && r == c.fast_lo + c.fast_n)
@@ -468,16 +476,15 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                 if (kEager && policy) eager = policy == 1 ? carry_left_boundary(r) : carry_init();
             }
         }
+        const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
+        const uint32_t x = c.tword ^ qword;
+        uint32_t sb = x | (x >> 1);                // mismatch of column c at bit 2c (odd bits: don't care)
+        if (!fast) {
+            sb = c.b.sbits = (sb & 0x55555555u & fm) | (c.b.sbits & ~fm);
+            if (pre_block) return false;
+        }
+        score_lanes(sb, fast, S);
     }
-    const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
-    const uint32_t x = c.tword ^ qword;
-    uint32_t sb = x | (x >> 1);                // mismatch of column c at bit 2c (odd bits: don't care)
-    if (!fast) {
-        sb = c.b.sbits = (sb & 0x55555555u & fm) | (c.b.sbits & ~fm);
-        if (pre_block) return false;
-    }
-    uint32_t S[8];
-    score_lanes(sb, fast, S);
     if (kEager) block_row(c.b, S, [&]() -> Carry { return eager; }, cout, tb);
     else
         block_row(c.b, S, [&]() -> Carry {

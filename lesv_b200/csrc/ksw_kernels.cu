@@ -615,7 +615,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
 {
     extern __shared__ uint32_t seq_s[];                 // two halves of half_words words
     __shared__ BtShared bt;
-    __shared__ __align__(512) uint2 carry_sh[2][32];   // 256 bytes per row parity: the two parities differ in one address bit
+    __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // per thread and row parity: the two parities differ in one address bit
     __shared__ int sh_job;
     __shared__ int wk_jid[2];
     __shared__ volatile int wk_posted, wk_done, wk_finished, wk_row;
@@ -687,7 +687,6 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         ThreadCtx c;
         thread_ctx_reset(c, ltid);
         Carry prev_out = carry_init();
-        const int wnext = lwarp + 1 < NW ? lwarp + 1 : 0;
         const int nrow_all = qlen + tlen - 1;
         if (tid == 0) { sh_prow = (unsigned long long)prow; sh_asize = (unsigned long long)asize; }
         // row r lives at rowp; consecutive rows are prow apart, upwards or downwards
@@ -697,8 +696,9 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
         // them; the others wait at the all-warps barrier (1) behind it.  Rows come in chunks of 256: before a chunk the
         // first logical warp checks that its rows do not reach into what walk m-1 still needs (rows <= wk_row of it).
         if (lwarp < NW) {
-            // column-15 values by row parity and consumer warp; both addresses flip one bit per row
-            uint32_t carry_rd = smem_addr(&carry_sh[1][lwarp]), carry_wr = smem_addr(&carry_sh[0][wnext]);
+            // column-15 values of every thread by row parity: a thread stores its own and loads its left neighbour's of the
+            // row before (no shuffle, no lane-0 / lane-31 special cases); both addresses flip one bit per row
+            uint32_t carry_rd = smem_addr(&carry_all[ltid ? ltid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[ltid][0]);
             for (int r0 = 0; r0 < nrow_all; r0 += 256) {
                 const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
                 if (m > 0) {
@@ -720,12 +720,8 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                 }
                 KSW_ROW_LOOP_PRAGMA
                 for (int r = r0; r < r1; ++r, rowp += rstep) {
-                    uint2 nb;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nb.x), "=r"(nb.y) : "r"(carry_rd) : "memory");
                     Carry cin;
-                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                    if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
                     Carry cout;
                     uint32_t tb[4];
                     if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
@@ -733,9 +729,8 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                         *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
                         prev_out = cout;
                     }
-                    if (lane == 31)
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
-                    carry_rd ^= 256u; carry_wr ^= 256u;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                    carry_rd ^= 8u; carry_wr ^= 8u;
                     bar_rows(NT);
                 }
             }
