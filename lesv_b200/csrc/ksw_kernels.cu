@@ -359,7 +359,7 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     extern __shared__ uint32_t seq_s[];
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
-    __shared__ uint2 carry_sh[2][kMaxWarps];      // barrier mode: column-15 values by row parity and consumer warp
+    __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // column-15 values per thread and row parity (one address bit apart)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Programmatic dependent launch: the launch classes of a batch are chained in one stream, each allowed to start
     // as soon as every CTA of the class before it is resident (lesvgpu.cu: run_jobs).  Nothing is waited for.
@@ -411,18 +411,14 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
         const size_t prow = (size_t)tb_blocks * 16;
         const int nrow_all = qlen + tlen - 1;
         if (!kCluster) {
-            // Lean barrier loop: lane 31 leaves its column-15 values in carry_sh[row parity][next warp],
-            // every lane of the next warp reads them back (one broadcast LDS) at the top of the next
-            // row and lane 0 keeps them -- no divergent single-lane fetch in front of pair 0.
-            const int wnext = warp + 1 < NW ? warp + 1 : 0;
+            // Lean barrier loop: every thread leaves its column-15 values in carry_all[thread][row parity] and loads its left
+            // neighbour's of the row before at the top of the next row (no shuffle, no lane-0 / lane-31 special cases).
+            uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
             for (int r = 0; r < nrow_all; ++r, rowp += prow) {
                 if (warp < NW) {
-                    const uint2 nb = carry_sh[(r + 1) & 1][warp];
                     Carry cin;
-                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                    if (lane == 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
                     Carry cout;
                     uint32_t tb[4];
                     if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
@@ -430,7 +426,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                         *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
                         prev_out = cout;
                     }
-                    if (lane == 31) carry_sh[r & 1][wnext] = make_uint2(prev_out.xv, prev_out.x2);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                    carry_rd ^= 8u; carry_wr ^= 8u;
                 }
                 __syncthreads();
             }
@@ -445,14 +442,12 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             const uint32_t out_addr = map_rank(smem_addr(&ps.inbox[0][0]), (rank + 1) % ncta);
             const uint32_t watch_addr = smem_addr(&ps.right_consumed);
             const bool first_lane = warp == 0 && lane == 0, last_lane = warp == NW - 1 && lane == 31;
+            uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
             for (int r = 0; r < nrow_all; ++r, rowp += prow) {
                 if (warp < NW) {
-                    const uint2 nb = carry_sh[(r + 1) & 1][warp];
-                    Carry cin;
-                    cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-                    cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-                    if (lane == 0 && warp > 0) { cin.xv = nb.x; cin.x2 = nb.y; }
+                    Carry cin;                             // thread 0 reads a slot nobody writes and takes consume() instead
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
                     bool fetched = false;
                     auto consume = [&]() -> Carry {        // first lane of the CTA: take row r-1 out of the inbox
                         Carry v = carry_init();
@@ -472,13 +467,13 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
                         prev_out = cout;
                     }
                     if (first_lane && !fetched) consume();                     // flow control only
-                    if (lane == 31) {
-                        if (last_lane) {                                       // publish row r to the CTA on the right
-                            if (r >= kRingD)
-                                while ((int)ld_word<false>(watch_addr) < r - kRingD + 1) { }
-                            const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                            st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
-                        } else carry_sh[r & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                    carry_rd ^= 8u; carry_wr ^= 8u;
+                    if (last_lane) {                                           // publish row r to the CTA on the right
+                        if (r >= kRingD)
+                            while ((int)ld_word<false>(watch_addr) < r - kRingD + 1) { }
+                        const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                        st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
                     }
                 }
                 __syncwarp();                  // the polling lanes are back before the aligned barrier
@@ -779,7 +774,7 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
 {
     extern __shared__ uint32_t seq_s[];
     __shared__ BtShared bt;
-    __shared__ uint2 carry_sh[2][kMaxWarps];
+    __shared__ __align__(16) uint2 carry_all[kStripNT][2];   // column-15 values per thread and row parity
     __shared__ int sh_job, sh_last;
     __shared__ int bt_dummy;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -819,6 +814,7 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
         thread_ctx_reset(c, B0 + tid);
         Carry prev_out = carry_init();
         uint2 edge_next = make_uint2(0u, 0u);          // value for the NEXT row, loaded one row ahead (thread 0)
+        uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : 0][1]), carry_wr = smem_addr(&carry_all[tid][0]);
         for (int r = r_lo; r <= r_hi; ++r) {
             if (((r - r_lo) & 63) == 0) {
                 if (sj.s > 0 && warp == 0) {            // rows r .. r+63 read rows r-1 .. r+62 of the strip to the left
@@ -844,14 +840,9 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
             }
             const uint2 edge_now = edge_next;
             if (sj.s > 0 && tid == 0 && r + 1 <= r_hi) edge_next = __ldcv(edge_in + r);   // for row r+1
-            const uint2 nb = carry_sh[(r + 1) & 1][warp];
-            Carry cin;
-            cin.xv = __shfl_up_sync(0xFFFFFFFFu, prev_out.xv, 1);
-            cin.x2 = __shfl_up_sync(0xFFFFFFFFu, prev_out.x2, 1);
-            if (lane == 0) {
-                if (warp == 0) { cin.xv = edge_now.x; cin.x2 = edge_now.y; }
-                else { cin.xv = nb.x; cin.x2 = nb.y; }
-            }
+            Carry cin;                                  // left neighbour's column-15 values of the row before (thread 0: the edge buffer)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
+            if (tid == 0) { cin.xv = edge_now.x; cin.x2 = edge_now.y; }
             Carry cout;
             uint32_t tb[4];
             if (thread_row_step<true>(c, 1 << 24, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
@@ -860,7 +851,8 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
                 prev_out = cout;
                 if (tid == kStripNT - 1) edge_out[r] = make_uint2(cout.xv, cout.x2);
             }
-            if (lane == 31 && warp + 1 < NW) carry_sh[r & 1][warp + 1] = make_uint2(prev_out.xv, prev_out.x2);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+            carry_rd ^= 8u; carry_wr ^= 8u;
             __syncthreads();
         }
         __threadfence();
