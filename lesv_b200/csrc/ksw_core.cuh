@@ -333,6 +333,28 @@ KSW_HD int tb_row_blocks(int qlen, int tlen, int w)
     return (n + 15) / 16 + 1;
 }
 
+// What a block at an edge of the band has to know about row r.  The numbers are the same for every thread, so a
+// kernel may compute them once per row for the whole CTA (a table in shared memory, filled a chunk of rows ahead)
+// and hand thread_row_step a lookup instead of the arithmetic.
+struct RowEdges {
+    int st0;        // first column of the band proper; its block st0 >> 4 is the left-most block of the row
+    int wr;         // last column whose score byte is rewritten; wr >> 4 is the right-most block that exists
+    int ben;        // en0 >> 4: blocks beyond it only keep score bytes (pre-blocks)
+    int bst_prev;   // left-most block of row r-1 (INT_MAX for r = 0): block B-1 was computed there iff B-1 >= bst_prev
+};
+KSW_HD RowEdges row_edges(int r, int qlen, int tlen, int w)
+{
+    const RowGeom g = row_geom(r, qlen, tlen, w);
+    RowEdges e;
+    e.st0 = g.st0; e.wr = g.wr; e.ben = g.en0 >> 4;
+    e.bst_prev = r > 0 ? row_geom(r - 1, qlen, tlen, w).st0 >> 4 : 0x7fffffff;
+    return e;
+}
+struct ComputeEdges {
+    int qlen, tlen, w;
+    KSW_HD RowEdges operator()(int r) const { return row_edges(r, qlen, tlen, w); }
+};
+
 // ---- the per-thread row step shared by the kernel and the host emulation ----------------------
 // A thread (slot) owns, at any row, the unique block B == slot (mod nt) of the live window.
 struct ThreadCtx {
@@ -390,10 +412,10 @@ KSW_HD bool warp_all(bool p) { return p; }
 // but the one or two warps at the band edges -- then skips everything that concerns the edges with ONE uniform
 // branch; the edge warps are the critical path of a row (every warp of the CTA waits for them at the row barrier),
 // so their extra work is kept short as well: geometry once per warp, the rare cases behind their own branches.
-template <bool kEager = false, bool kVote = true, class CarryFn>
+template <bool kEager = false, bool kVote = true, class CarryFn, class EdgeFn>
 KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w, int tb_blocks,
                             const uint32_t* tp, const uint32_t* qrp,
-                            CarryFn&& carry, Carry& cout, uint32_t tb[4])
+                            CarryFn&& carry, Carry& cout, uint32_t tb[4], EdgeFn&& edges)
 {
     Carry eager = carry_init();
     if (kEager) eager = carry();
@@ -408,16 +430,14 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
         const int qrel = qlen - 1 - r;
         if ((qrel & 15) == 15) { c.qhi = c.qlo; c.qwi = (qrel >> 4) + 1 + c.myB; c.qlo = qrp[c.qwi]; }
         const uint32_t x = c.tword ^ funnel_r(c.qlo, c.qhi, 2 * qrel);     // the shift amount is taken mod 32
-        score_lanes(x | (x >> 1), true, S);                                 // odd bits: don't care
+        c.b.sbits = (x | (x >> 1)) & 0x55555555u;                           // every column fresh: the row's mismatch bits
+        score_lanes(c.b.sbits, true, S);
     } else {
         uint32_t fm = 0xFFFFFFFFu;                 // score bits refreshed this row (2 per column)
         bool pre_block = false;
         if (!fast) {
-            const RowGeom g = row_geom(r, qlen, tlen, w);
-            const int bst = g.st0 >> 4, ben = g.en0 >> 4, bwr = g.wr >> 4;
-            // leaving the fast stretch: the score bits were not tracked there (every column was fresh every row)
-            if (c.fast_n > 0 && r == c.fast_lo + c.fast_n)
-                c.b.sbits = mismatch_bits(c.tword, query_window(c, qrp, qlen, r - 1, c.myB));
+            const RowEdges g = edges(r);
+            const int bst = g.st0 >> 4, bwr = g.wr >> 4;
             // the band left this thread's block behind: take the next one.  One step is the rule (the band moves by at most one
             // block per row); the loop behind it serves the kernels that visit a slot only now and then, and the empty asm
             // keeps the compiler from turning it into a division inside every row.
@@ -451,12 +471,11 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                     c.fast_lo = lo; c.fast_n = hi >= lo ? hi - lo + 1 : 0;
                 }
             }
-            const int c0 = 16 * B;
-            // fresh columns: st0 <= c0 + col <= wr
-            int lo = g.st0 - c0, hi = g.wr - c0;
-            lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
-            fm = lo <= hi ? (0xFFFFFFFFu >> (30 - 2 * hi)) & (0xFFFFFFFFu << (2 * lo)) : 0u;
-            pre_block = B > ben;                // pre-block: only its score bytes exist so far
+            // fresh columns st0 <= 16B + col <= wr: only the left-most and the right-most block of the row are cut
+            // (bst <= B <= bwr here)
+            if (B == bst) fm = 0xFFFFFFFFu << (2 * (g.st0 & 15));
+            if (B == bwr) fm &= 0xFFFFFFFFu >> (30 - 2 * (g.wr & 15));
+            pre_block = B > g.ben;              // pre-block: only its score bytes exist so far
             if (!pre_block) {
                 if ((r >> 4) == B) {            // top row of the matrix reaches column r: :152-155
                     const int col = r & 15, j = col & 7;
@@ -472,18 +491,16 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
                 }
                 // block B-1 was computed in row r-1 iff it was inside that row's aligned band (:142-147)
                 if (B == 0) policy = 1;
-                else if (r == 0 || B - 1 < (row_geom(r - 1, qlen, tlen, w).st0 >> 4)) policy = 2;
+                else if (B - 1 < g.bst_prev) policy = 2;
                 if (kEager && policy) eager = policy == 1 ? carry_left_boundary(r) : carry_init();
             }
         }
         const uint32_t qword = query_window(c, qrp, qlen, r, c.myB);
         const uint32_t x = c.tword ^ qword;
-        uint32_t sb = x | (x >> 1);                // mismatch of column c at bit 2c (odd bits: don't care)
-        if (!fast) {
-            sb = c.b.sbits = (sb & 0x55555555u & fm) | (c.b.sbits & ~fm);
-            if (pre_block) return false;
-        }
-        score_lanes(sb, fast, S);
+        // mismatch of column c at bit 2c, fresh columns only (a block strictly inside the band has fm = all ones)
+        const uint32_t sb = c.b.sbits = ((x | (x >> 1)) & 0x55555555u & fm) | (c.b.sbits & ~fm);
+        if (pre_block) return false;
+        score_lanes(sb, false, S);
     }
     if (kEager) block_row(c.b, S, [&]() -> Carry { return eager; }, cout, tb);
     else
@@ -492,6 +509,14 @@ KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int
             return policy == 1 ? carry_left_boundary(r) : carry_init();
         }, cout, tb);
     return true;
+}
+
+template <bool kEager = false, bool kVote = true, class CarryFn>
+KSW_HD bool thread_row_step(ThreadCtx& c, int nt, int r, int qlen, int tlen, int w, int tb_blocks,
+                            const uint32_t* tp, const uint32_t* qrp,
+                            CarryFn&& carry, Carry& cout, uint32_t tb[4])
+{
+    return thread_row_step<kEager, kVote>(c, nt, r, qlen, tlen, w, tb_blocks, tp, qrp, carry, cout, tb, ComputeEdges{qlen, tlen, w});
 }
 
 }  // namespace lesvksw

@@ -611,6 +611,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
     extern __shared__ uint32_t seq_s[];                 // two halves of half_words words
     __shared__ BtShared bt;
     __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // per thread and row parity: the two parities differ in one address bit
+    __shared__ int4 edge_tab[256];                          // RowEdges of the current chunk of 256 rows
     __shared__ int sh_job;
     __shared__ int wk_jid[2];
     __shared__ volatile int wk_posted, wk_done, wk_finished, wk_row;
@@ -696,23 +697,27 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
             uint32_t carry_rd = smem_addr(&carry_all[ltid ? ltid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[ltid][0]);
             for (int r0 = 0; r0 < nrow_all; r0 += 256) {
                 const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
-                if (m > 0) {
-                    if (lwarp == 0) {
-                        const unsigned long long mine = (unsigned long long)r1 * sh_prow;
-                        for (;;) {                          // (whole-warp poll: no divergence in front of the aligned barrier)
-                            int ok = 0;
-                            if (lane == 0) {
-                                const int need = wk_done >= m ? -1 : wk_row;
-                                ok = (need < 0 && wk_done >= m) ||
-                                     (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize);
-                            }
-                            ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
-                            if (ok) break;
-                            __nanosleep(500);
+                if (m > 0 && lwarp == 0) {
+                    const unsigned long long mine = (unsigned long long)r1 * sh_prow;
+                    for (;;) {                          // (whole-warp poll: no divergence in front of the aligned barrier)
+                        int ok = 0;
+                        if (lane == 0) {
+                            const int need = wk_done >= m ? -1 : wk_row;
+                            ok = (need < 0 && wk_done >= m) ||
+                                 (need >= 0 && mine + (unsigned long long)(need + 1) * sh_prev_prow <= sh_asize);
                         }
+                        ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+                        if (ok) break;
+                        __nanosleep(500);
                     }
-                    bar_rows(NT);
                 }
+                // the band edges of the chunk's rows, once for the CTA: the warps that hold edge blocks are the last to
+                // arrive at every row barrier, so what they do per row is kept to a table look-up
+                for (int x = ltid; x < r1 - r0; x += NT) {
+                    const RowEdges e = row_edges(r0 + x, qlen, tlen, w);
+                    edge_tab[x] = make_int4(e.st0, e.wr, e.ben, e.bst_prev);
+                }
+                bar_rows(NT);
                 KSW_ROW_LOOP_PRAGMA
                 for (int r = r0; r < r1; ++r, rowp += rstep) {
                     Carry cin;
@@ -720,7 +725,12 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
                     Carry cout;
                     uint32_t tb[4];
                     if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                              [&]() -> Carry { return cin; }, cout, tb)) {
+                                              [&]() -> Carry { return cin; }, cout, tb,
+                                              [&](int rr) -> RowEdges {
+                                                  const int4 v = edge_tab[rr & 255];
+                                                  RowEdges e; e.st0 = v.x; e.wr = v.y; e.ben = v.z; e.bst_prev = v.w;
+                                                  return e;
+                                              })) {
                         *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
                         prev_out = cout;
                     }
