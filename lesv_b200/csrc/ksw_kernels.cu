@@ -301,6 +301,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 // Slot protocol without fences: a slot is ONE 16-byte shared-memory word {xv, x2, tag, -}, written
 // with a single 128-bit store and polled with a single 128-bit load, so data and tag can never be
 // seen torn; the consumed-rows counter is a single word.  volatile = re-read on every poll.
+__device__ __forceinline__ void bar_active(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 template <bool kCluster> __device__ __forceinline__ void st_slot(uint32_t addr, uint32_t a, uint32_t b, uint32_t tag)
 {
     if (kCluster) asm volatile("st.volatile.shared::cluster.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(a), "r"(b), "r"(tag) : "memory");
@@ -360,7 +361,13 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
     __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // column-15 values per thread and row parity (one address bit apart)
+    __shared__ int4 edge_tab[256];                          // RowEdges of the current chunk of 256 rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto edges_from_table = [&](int rr) -> RowEdges {
+        const int4 v = edge_tab[rr & 255];
+        RowEdges e; e.st0 = v.x; e.wr = v.y; e.ben = v.z; e.bst_prev = v.w;
+        return e;
+    };
     // Programmatic dependent launch: the launch classes of a batch are chained in one stream, each allowed to start
     // as soon as every CTA of the class before it is resident (lesvgpu.cu: run_jobs).  Nothing is waited for.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -415,22 +422,29 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             // neighbour's of the row before at the top of the next row (no shuffle, no lane-0 / lane-31 special cases).
             uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
-            for (int r = 0; r < nrow_all; ++r, rowp += prow) {
-                if (warp < NW) {
-                    Carry cin;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
-                    Carry cout;
-                    uint32_t tb[4];
-                    if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                              [&]() -> Carry { return cin; }, cout, tb)) {
-                        *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                        prev_out = cout;
+            if (warp < NW)                          // the warps that hold blocks, on a named barrier of their own
+                for (int r0 = 0; r0 < nrow_all; r0 += 256) {
+                    const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
+                    for (int x = tid; x < r1 - r0; x += NT) {          // band edges of the chunk's rows, once for the CTA
+                        const RowEdges e = row_edges(r0 + x, qlen, tlen, w);
+                        edge_tab[x] = make_int4(e.st0, e.wr, e.ben, e.bst_prev);
                     }
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
-                    carry_rd ^= 8u; carry_wr ^= 8u;
+                    bar_active(NT);
+                    for (int r = r0; r < r1; ++r, rowp += prow) {
+                        Carry cin;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
+                        Carry cout;
+                        uint32_t tb[4];
+                        if (thread_row_step<true>(c, NT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                                  [&]() -> Carry { return cin; }, cout, tb, edges_from_table)) {
+                            *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                            prev_out = cout;
+                        }
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                        carry_rd ^= 8u; carry_wr ^= 8u;
+                        bar_active(NT);
+                    }
                 }
-                __syncthreads();
-            }
         } else {
             // Cluster: inside a CTA the same lean barrier loop as above (the polled ring between warps of one SM costs
             // issue slots of the schedulers that are the bottleneck: 3.5 instead of 5.5 GCUPS per SM); only the carry INTO
@@ -444,41 +458,49 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             const bool first_lane = warp == 0 && lane == 0, last_lane = warp == NW - 1 && lane == 31;
             uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
-            for (int r = 0; r < nrow_all; ++r, rowp += prow) {
-                if (warp < NW) {
-                    Carry cin;                             // thread 0 reads a slot nobody writes and takes consume() instead
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
-                    bool fetched = false;
-                    auto consume = [&]() -> Carry {        // first lane of the CTA: take row r-1 out of the inbox
-                        Carry v = carry_init();
-                        fetched = true;
-                        if (r == 0) return v;
-                        const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                        while (ld_slot<false>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
-                        st_word<true>(cons_addr, (uint32_t)r);
-                        return v;
-                    };
-                    Carry cout;
-                    uint32_t tb[4];
-                    const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
-                                                     [&]() -> Carry { return first_lane ? consume() : cin; }, cout, tb);
-                    if (did) {
-                        *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
-                        prev_out = cout;
+            if (warp < NW)
+                for (int r0 = 0; r0 < nrow_all; r0 += 256) {
+                    const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
+                    for (int x = tid; x < r1 - r0; x += NT) {
+                        const RowEdges e = row_edges(r0 + x, qlen, tlen, w);
+                        edge_tab[x] = make_int4(e.st0, e.wr, e.ben, e.bst_prev);
                     }
-                    if (first_lane && !fetched) consume();                     // flow control only
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
-                    carry_rd ^= 8u; carry_wr ^= 8u;
-                    if (last_lane) {                                           // publish row r to the CTA on the right
-                        if (r >= kRingD)
-                            while ((int)ld_word<false>(watch_addr) < r - kRingD + 1) { }
-                        const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
-                        st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
+                    bar_active(NT);
+                    for (int r = r0; r < r1; ++r, rowp += prow) {
+                        Carry cin;                             // thread 0 reads a slot nobody writes and takes consume() instead
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cin.xv), "=r"(cin.x2) : "r"(carry_rd) : "memory");
+                        bool fetched = false;
+                        auto consume = [&]() -> Carry {        // first lane of the CTA: take row r-1 out of the inbox
+                            Carry v = carry_init();
+                            fetched = true;
+                            if (r == 0) return v;
+                            const uint32_t slot = in_addr + (uint32_t)((r - 1) & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                            while (ld_slot<false>(slot, v.xv, v.x2) != (uint32_t)(r - 1)) { }
+                            st_word<true>(cons_addr, (uint32_t)r);
+                            return v;
+                        };
+                        Carry cout;
+                        uint32_t tb[4];
+                        const bool did = thread_row_step(c, NTT, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
+                                                         [&]() -> Carry { return first_lane ? consume() : cin; }, cout, tb,
+                                                         edges_from_table);
+                        if (did) {
+                            *reinterpret_cast<uint4*>(rowp + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                            prev_out = cout;
+                        }
+                        if (first_lane && !fetched) consume();                     // flow control only
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
+                        carry_rd ^= 8u; carry_wr ^= 8u;
+                        if (last_lane) {                                           // publish row r to the CTA on the right
+                            if (r >= kRingD)
+                                while ((int)ld_word<false>(watch_addr) < r - kRingD + 1) { }
+                            const uint32_t slot = out_addr + (uint32_t)(r & (kRingD - 1)) * (uint32_t)sizeof(CarrySlot);
+                            st_slot<true>(slot, prev_out.xv, prev_out.x2, (uint32_t)r);
+                        }
+                        __syncwarp();              // the polling lanes are back before the aligned barrier
+                        bar_active(NT);
                     }
                 }
-                __syncwarp();                  // the polling lanes are back before the aligned barrier
-                __syncthreads();
-            }
         }
         __syncthreads();
         if (kCluster) { __threadfence(); cluster_sync_all(); }
