@@ -281,7 +281,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     size_t arena_need = 0, scratch_need = 0;
     // SM budget: every launch gets SMs in proportion to its share of the work (traceback bytes ~ cells)
     const double budget = ctx->n_sm * 1.0;
-    auto shape_weight = [](int ncta) { return ncta <= 1 ? 1.0 : ncta == 2 ? 1.4 : ncta == 4 ? 1.7 : 2.2; };
+    auto shape_weight = [](int ncta) { return ncta <= 1 ? 1.0 : ncta == 2 ? 1.75 : ncta == 4 ? 2.0 : 2.4; };
     double weighted_work = 0;
     const Launch* major = launches.empty() ? nullptr : &launches[0];
     for (const Launch& L : launches) { weighted_work += L.work * shape_weight(L.ncta); if (L.work > major->work) major = &L; }
@@ -302,7 +302,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         const int sms_per_job = L.ncta > 0 ? L.ncta : 1;
         const int per_sm = (L.ncta == 1 || L.nt <= 320) ? ksw_ctas_per_sm(L.nt) : 1;
         // `fair` = the SMs the class needs to finish together with the others: its share of the work, weighted by
-        // what an SM achieves in that shape (measured: 2-CTA clusters run at ~0.7x the single-CTA rate per SM,
+        // what an SM achieves in that shape (measured: 2-CTA clusters run at ~0.57x the single-CTA rate per SM,
         // full-band 8-CTA clusters at ~0.45x because an anti-diagonal of the whole matrix is a triangle).
         // The class with the most work is additionally launched wide enough to fill the machine on its own
         // (persistent CTAs pulling from the class queue), the others 25 % above fair: when a class runs dry its SMs
@@ -335,10 +335,15 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         arena_need = 0;
         for (Launch& L : launches) { L.arena_off = arena_need; L.arena_bytes = footprint(L); arena_need += L.arena_bytes; }
         if (arena_need <= arena_limit) break;
-        // Take memory from the surplus first (largest footprint first), then from below the fair share.
+        // Take memory from the surplus first -- that of the smaller classes before that of the class with the most work:
+        // their SMs go to its pending CTAs when they run dry, but only as many of those can ever run as have an arena --
+        // then from below the fair share.
         Launch* big = nullptr;
         for (Launch& L : launches)
-            if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+            if (&L != major && L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+        if (!big)
+            for (Launch& L : launches)
+                if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big)
             for (Launch& L : launches)
                 if (L.n_clusters > ((L.ncta == 1 && L.nt <= kGroupTierMax) ? 32 / L.nt : 1) && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
