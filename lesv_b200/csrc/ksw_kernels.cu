@@ -357,14 +357,19 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
               uint32_t* __restrict__ cigar_pool, KswGapRun* __restrict__ run_pool,
               KswOut* __restrict__ outs, int* counter)
 {
-    extern __shared__ uint32_t seq_s[];
+    // dynamic shared memory: 16 bytes per thread of the launch (column-15 values by row parity, one address bit apart),
+    // then the packed sequences.  One-warp CTAs of the narrow tiers share an SM by the dozen: nothing here is sized for
+    // the widest launch.
+    extern __shared__ __align__(16) uint32_t dyn_s[];
+    uint2 (*carry_all)[2] = reinterpret_cast<uint2 (*)[2]>(dyn_s);
+    uint32_t* const seq_s = dyn_s + 4 * blockDim.x;
     __shared__ PipeShared ps;
     __shared__ BtShared bt;
-    __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // column-15 values per thread and row parity (one address bit apart)
-    __shared__ int4 edge_tab[256];                          // RowEdges of the current chunk of 256 rows
+    constexpr int kChunk = kCluster ? 256 : 64;             // rows per band-edge table
+    __shared__ int4 edge_tab[kChunk];                       // RowEdges of the current chunk of rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto edges_from_table = [&](int rr) -> RowEdges {
-        const int4 v = edge_tab[rr & 255];
+        const int4 v = edge_tab[rr & (kChunk - 1)];
         RowEdges e; e.st0 = v.x; e.wr = v.y; e.ben = v.z; e.bst_prev = v.w;
         return e;
     };
@@ -423,8 +428,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
             if (warp < NW)                          // the warps that hold blocks, on a named barrier of their own
-                for (int r0 = 0; r0 < nrow_all; r0 += 256) {
-                    const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
+                for (int r0 = 0; r0 < nrow_all; r0 += kChunk) {
+                    const int r1 = r0 + kChunk < nrow_all ? r0 + kChunk : nrow_all;
                     for (int x = tid; x < r1 - r0; x += NT) {          // band edges of the chunk's rows, once for the CTA
                         const RowEdges e = row_edges(r0 + x, qlen, tlen, w);
                         edge_tab[x] = make_int4(e.st0, e.wr, e.ben, e.bst_prev);
@@ -459,8 +464,8 @@ ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, in
             uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : NT - 1][1]), carry_wr = smem_addr(&carry_all[tid][0]);
             uint8_t* rowp = arena;
             if (warp < NW)
-                for (int r0 = 0; r0 < nrow_all; r0 += 256) {
-                    const int r1 = r0 + 256 < nrow_all ? r0 + 256 : nrow_all;
+                for (int r0 = 0; r0 < nrow_all; r0 += kChunk) {
+                    const int r1 = r0 + kChunk < nrow_all ? r0 + kChunk : nrow_all;
                     for (int x = tid; x < r1 - r0; x += NT) {
                         const RowEdges e = row_edges(r0 + x, qlen, tlen, w);
                         edge_tab[x] = make_int4(e.st0, e.wr, e.ben, e.bst_prev);
@@ -1069,11 +1074,12 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
             return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                       (uint32_t)(smem / 4), d_cigar, d_runs, d_out, d_counter);
         }
-        lesv_need_smem(ksw_dp_kernel<false>, smem);
-        cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem;
+        lesv_need_smem(ksw_dp_kernel<false>, smem + (size_t)nt * 16);
+        cfg.blockDim = dim3((unsigned)nt); cfg.dynamicSmemBytes = smem + (size_t)nt * 16;
         return cudaLaunchKernelEx(&cfg, ksw_dp_kernel<false>, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
                                   d_cigar, d_runs, d_out, d_counter);
     }
+    smem += (size_t)nt * 16;
     lesv_need_smem(ksw_dp_kernel<true>, smem);
     if (ncta > 8) cudaFuncSetAttribute(ksw_dp_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cfg.gridDim = dim3((unsigned)(n_clusters * ncta));
@@ -1101,6 +1107,7 @@ int ksw_max_clusters(int nt, int ncta, size_t smem)
 {
     if (ncta <= 1) return 1 << 20;
     KswKernelFn kern = ksw_dp_kernel<true>;
+    smem += (size_t)nt * 16;
     lesv_need_smem(kern, smem);
     if (ncta > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};

@@ -27,7 +27,7 @@ for path in a.libs:
             res, _ = ctx.ksw_batch(qs, ts, ws, want_cigars=False)
             ok = sum(r.ok for r in res)
         except RuntimeError as e:
-            ok = -1
+            print('   ', e, flush=True); ok = -1; out.append('failed'); continue
         tm = ctx.timing()
         out.append(f"{cells / tm.dp_ms / 1e6:.1f}")
     print(f"{os.path.basename(path):24s} n={a.n} len={a.len} err={a.err} band={ws[0]} ok={ok} GCUPS " + " ".join(out), flush=True)
