@@ -637,7 +637,7 @@ ksw_dp_overlap_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ o
 {
     extern __shared__ uint32_t seq_s[];                 // two halves of half_words words
     __shared__ BtShared bt;
-    __shared__ __align__(16) uint2 carry_all[kMaxNT][2];   // per thread and row parity: the two parities differ in one address bit
+    __shared__ __align__(16) uint2 carry_all[kTier][2];    // per thread and row parity: the two parities differ in one address bit
     __shared__ int4 edge_tab[256];                          // RowEdges of the current chunk of 256 rows
     __shared__ int sh_job;
     __shared__ int wk_jid[2];
@@ -1067,7 +1067,8 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
 #ifdef KSW_ONE_TIER
             auto kern = ksw_dp_overlap_kernel<kTierTop>;
 #else
-            auto kern = nt <= kTierLow ? ksw_dp_overlap_kernel<kTierLow> : nt <= kTierMid ? ksw_dp_overlap_kernel<kTierMid> : ksw_dp_overlap_kernel<kTierTop>;
+            auto kern = nt <= kTierLow ? ksw_dp_overlap_kernel<kTierLow> : nt <= kTierMid ? ksw_dp_overlap_kernel<kTierMid>
+                      : nt <= kTierTop ? ksw_dp_overlap_kernel<kTierTop> : ksw_dp_overlap_kernel<kTierXL>;
 #endif
             lesv_need_smem(kern, 2 * smem);
             cfg.blockDim = dim3((unsigned)nt + 32); cfg.dynamicSmemBytes = 2 * smem;

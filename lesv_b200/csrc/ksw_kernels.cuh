@@ -65,6 +65,12 @@ __host__ __device__ static inline uint32_t qrp_words(int qlen) { return (uint32_
 #define KSW_TIER_LOW 320
 #endif
 constexpr int kTierLow = KSW_TIER_LOW, kTierMid = KSW_TIER_MID, kTierTop = KSW_TIER_TOP;
+// One more single-CTA tier above them: 736 DP threads + the walker = 24 warps, six per scheduler at 80 registers (a few
+// spills).  Bands of 9.7-11.8 k columns run here at about twice the rate per SM of the 2-CTA cluster that held them before.
+#ifndef KSW_TIER_XL
+#define KSW_TIER_XL 736
+#endif
+constexpr int kTierXL = KSW_TIER_XL;
 // Band windows of <= 8 / <= 16 blocks (bands up to 64 / 192 columns): 4 / 2 alignments per warp (ksw_dp_group_kernel).
 // For these classes the "clusters" of a launch are lane groups and `nt` is the group size.
 constexpr int kGroupTierMax = 16;

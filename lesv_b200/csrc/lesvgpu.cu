@@ -171,11 +171,11 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     // alignment actually uses of it.
     struct Shape { int ncta, tier, nt; };
     auto shape_of = [](int wb) -> Shape {
-        static const int tiers[] = {32, 64, 96, 128, 160, kTierLow, kTierMid, kTierTop};
+        static const int tiers[] = {32, 64, 96, 128, 160, kTierLow, kTierMid, kTierTop, kTierXL};
         static const bool groups = getenv("LESV_KSW_NO_GROUPS") == nullptr;
         if (groups && wb <= 8) return {1, 8, 8};             // several alignments per warp (ksw_dp_group_kernel)
         if (groups && wb <= 16) return {1, 16, 16};
-        if (wb <= kTierTop) {
+        if (wb <= kTierXL) {
             const int nt = (wb + 31) / 32 * 32;
             for (int t : tiers) if (nt <= t) return {1, t, nt};
         }
@@ -214,7 +214,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         std::vector<int> cand;
         for (int k = 0; k < nj; ++k) {
             const KswJob& J = jobs[k];
-            if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > kTierTop) cand.push_back(k);
+            if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > kTierXL) cand.push_back(k);
         }
         // A full-matrix alignment of 50 kb x 60 kb is 3.3 GB of traceback, and every alignment of a strip launch needs its
         // own arena: they are processed in groups that fit the budget -- all of it when the batch holds nothing else (the
@@ -339,8 +339,10 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         // their SMs go to its pending CTAs when they run dry, but only as many of those can ever run as have an arena --
         // then from below the fair share.
         Launch* big = nullptr;
+        // (a small class keeps one CTA above its share: with a handful of CTAs and alignments of 150 ms each, the exact
+        // share ends a whole alignment later than the rest)
         for (Launch& L : launches)
-            if (&L != major && L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
+            if (&L != major && L.n_clusters > std::max(L.fair + 1, (11 * L.fair + 9) / 10) && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
         if (!big)
             for (Launch& L : launches)
                 if (L.n_clusters > L.fair && (!big || L.arena_bytes > big->arena_bytes)) big = &L;
