@@ -181,7 +181,7 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
                                const uint32_t* tp_s, const uint32_t* qrp_s,
                                uint32_t* __restrict__ cigar, KswGapRun* __restrict__ runs, KswOut* out,
                                BtShared& sh, int lane, size_t arena_size = 0, bool reversed = false,
-                               volatile int* progress = nullptr)
+                               volatile int* progress = nullptr, int fold_q = 0)
 {
     const int qlen = job.qlen, tlen = job.tlen, w = job.w, min_indel = job.min_indel;
     const bool wr_cigar = job.cigar_cap != 0 && lane == 0, wr_runs = lane == 0;
@@ -207,12 +207,18 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
                 b1 = b0 + ((ic & 15) >= 8 ? 1 : -1);
                 if (b1 < bst || b1 > ben) b1 = -1;
                 const uint8_t* row = arena + ((kOverlap && reversed) ? arena_size - (size_t)(r + 1) * prow : (size_t)r * prow);
+                size_t o0 = (size_t)tb_block_slot(b0, job.tb_blocks) * 16, o1 = b1 >= 0 ? (size_t)tb_block_slot(b1, job.tb_blocks) * 16 : 0;
+                if (fold_q) {                           // column strips: rows folded modulo qlen (ksw_kernels.cuh)
+                    const int pass = r / fold_q;
+                    row = arena + (size_t)(r - pass * fold_q) * prow + (size_t)pass * 16;
+                    o0 = (size_t)b0 * 16; o1 = b1 >= 0 ? (size_t)b1 * 16 : 0;
+                }
                 if (kOverlap) {
-                    sh.cache[k][0] = __ldcg(reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16));
-                    if (b1 >= 0) sh.cache[k][1] = __ldcg(reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16));
+                    sh.cache[k][0] = __ldcg(reinterpret_cast<const uint4*>(row + o0));
+                    if (b1 >= 0) sh.cache[k][1] = __ldcg(reinterpret_cast<const uint4*>(row + o1));
                 } else {
-                    sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b0, job.tb_blocks) * 16);
-                    if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + (size_t)tb_block_slot(b1, job.tb_blocks) * 16);
+                    sh.cache[k][0] = *reinterpret_cast<const uint4*>(row + o0);
+                    if (b1 >= 0) sh.cache[k][1] = *reinterpret_cast<const uint4*>(row + o1);
                 }
             }
             sh.blk[k][0] = b0; sh.blk[k][1] = b1;
@@ -843,7 +849,7 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
         hi = hi < hi2 ? hi : hi2;
         const int r_hi = hi < nrow_all - 1 ? (int)hi : nrow_all - 1;
         uint8_t* const arena = arena_base + sj.arena_off;
-        const size_t prow = (size_t)tb_blocks * 16;
+        const size_t prow = fold_row_bytes(qlen, tlen);  // rows folded modulo qlen: row r at physical row r % qlen, block B at slot B + r / qlen
         const uint2* edge_in = edges + sj.edge_off + (size_t)(sj.s - 1) * nrow_all;      // strip s-1 (s > 0)
         uint2* edge_out = edges + sj.edge_off + (size_t)sj.s * nrow_all;
         int* prog = progress + sj.prog_off;
@@ -852,6 +858,8 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
         Carry prev_out = carry_init();
         uint2 edge_next = make_uint2(0u, 0u);          // value for the NEXT row, loaded one row ahead (thread 0)
         uint32_t carry_rd = smem_addr(&carry_all[tid ? tid - 1 : 0][1]), carry_wr = smem_addr(&carry_all[tid][0]);
+        int frow = r_lo % qlen;                         // physical row of r
+        uint8_t* rowp = arena + (size_t)frow * prow + (size_t)(B0 + tid + r_lo / qlen) * 16;     // this thread's 16 bytes of row r
         for (int r = r_lo; r <= r_hi; ++r) {
             if (((r - r_lo) & 63) == 0) {
                 if (sj.s > 0 && warp == 0) {            // rows r .. r+63 read rows r-1 .. r+62 of the strip to the left
@@ -884,10 +892,12 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
             uint32_t tb[4];
             if (thread_row_step<true>(c, 1 << 24, r, qlen, tlen, w, tb_blocks, tp_s, qrp_s,
                                       [&]() -> Carry { return cin; }, cout, tb)) {
-                *reinterpret_cast<uint4*>(arena + (size_t)r * prow + c.tb_off) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+                *reinterpret_cast<uint4*>(rowp) = make_uint4(tb[0], tb[1], tb[2], tb[3]);
                 prev_out = cout;
                 if (tid == kStripNT - 1) edge_out[r] = make_uint2(cout.xv, cout.x2);
             }
+            rowp += prow;
+            if (++frow == qlen) { frow = 0; rowp += 16 - (ptrdiff_t)((size_t)qlen * prow); }     // next pass: back to physical row 0, one slot to the right
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(carry_wr), "r"(prev_out.xv), "r"(prev_out.x2) : "memory");
             carry_rd ^= 8u; carry_wr ^= 8u;
             __syncthreads();
@@ -904,7 +914,7 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
             __threadfence();
             if (warp == 0)
                 backtrack_warp<true>(job, arena, prow, tp_s, qrp_s, cigar_pool + job.cigar_off, run_pool + job.sig_off,
-                                     outs + sj.jid, bt, lane, 0, false, (volatile int*)&bt_dummy);
+                                     outs + sj.jid, bt, lane, 0, false, (volatile int*)&bt_dummy, qlen);
         }
         __syncthreads();
     }

@@ -216,14 +216,14 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
             const KswJob& J = jobs[k];
             if (J.w >= J.qlen && J.w >= J.tlen && window_blocks(J.tlen, J.w) > kTierXL) cand.push_back(k);
         }
-        // A full-matrix alignment of 50 kb x 60 kb is 3.3 GB of traceback, and every alignment of a strip launch needs its
+        // A full-matrix alignment of 50 kb x 60 kb is 3 GB of traceback, and every alignment of a strip launch needs its
         // own arena: they are processed in groups that fit the budget -- all of it when the batch holds nothing else (the
         // chaining round of qx2svr), three quarters next to other launch classes -- one launch per group, the groups about
         // equally large (a launch costs the critical path of one alignment however few alignments it holds).
         const size_t cap = (int)cand.size() == nj ? arena_limit / 20 * 19 : arena_limit / 4 * 3;
-        auto tb_of = [&](int k) {
+        auto tb_of = [&](int k) {                        // rows folded modulo qlen (ksw_kernels.cuh: fold_tb_bytes)
             const KswJob& J = jobs[k];
-            return ((size_t)(J.qlen + J.tlen - 1) * (size_t)tb_row_blocks(J.qlen, J.tlen, J.w) * 16 + 255) & ~(size_t)255;
+            return (fold_tb_bytes(J.qlen, J.tlen) + 255) & ~(size_t)255;
         };
         size_t total = 0;
         for (int k : cand) if (tb_of(k) <= cap) total += tb_of(k);
@@ -254,7 +254,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         cigar_words += J.cigar_cap;
         J.sig_off = (uint32_t)k * kSigCap;
         if (pool_words > 0xFFFFFFF0ull) { ctx->err = "batch too large (packed pool offsets are 32-bit)"; return LESVGPU_E_ARG; }
-        tb_bytes[k] = (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
+        tb_bytes[k] = is_strip[k] ? fold_tb_bytes(J.qlen, J.tlen) : (size_t)(J.qlen + J.tlen - 1) * (size_t)J.tb_blocks * 16;
         if (tb_bytes[k] > arena_limit) { ctx->err = "one alignment's traceback does not fit the arena"; return LESVGPU_E_NOMEM; }
         if (is_strip[k]) { J.nt = kStripBlocks; continue; }
         size_t li = 0;
