@@ -329,6 +329,7 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
         for (int i = 0; i < L.n_clusters && i < L.count; ++i) b += (tb_bytes[L.ids[i]] + 255) & ~(size_t)255;
         return b;
     };
+    const size_t arena_budget = arena_limit;             // what the arena may be right now, strips included
     if (strip_arena > arena_limit) { ctx->err = "traceback arena too small for the full-matrix alignments"; return LESVGPU_E_NOMEM; }
     arena_limit -= strip_arena;                          // the strips' per-alignment arenas sit behind the classes' ones
     for (;;) {
@@ -423,7 +424,11 @@ static int run_jobs(lesvgpu_ctx* ctx, std::vector<KswJob>& jobs, size_t raw_byte
     CK(ctx->d_order.reserve(nj));
     CK(ctx->d_counter.reserve((launches.size() + sgroups.size() + 1) * kLaunchSlotInts));
     CK(ctx->d_aoff.reserve(arena_offs.size()));
-    CK(ctx->d_arena.reserve_exact(arena_need));
+    // A batch that needs more than half of the budget is memory-bound and the next one will want a little more or less:
+    // take the whole budget at once instead of freeing and allocating 100+ GB whenever a batch exceeds the last maximum
+    // (cudaMalloc of that size costs 0.1 s and showed up as jitter of the end-to-end time).
+    if (arena_need > ctx->d_arena.cap)
+        CK(ctx->d_arena.reserve_exact(arena_need > arena_budget / 2 ? std::max(arena_need, arena_budget) : arena_need));
     CK(ctx->d_scratch.reserve(scratch_need));
     CK(ctx->h_outs.reserve(nj));
     if (want_cigar) CK(ctx->h_cigar.reserve(cigar_words));

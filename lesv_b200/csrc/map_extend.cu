@@ -914,6 +914,19 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
                                                                            E->d_cand_list.p, n_cand, E->d_cand_info.p, E->d_hs_w.p, E->d_hs_r.p,
                                                                            word, E->d_f.p, E->d_p.p, pb, E->d_preps.p); ++g_lesv_launches;
         CK(cudaEventRecord(E->ev[0], s));
+        CK(cudaEventRecord(E->ev[2], s));               // the side stream of the giant gaps starts here
+        SlabBufs sb;
+        sb.P = E->d_P.p; sb.M = E->d_M.p; sb.score = E->d_score.p; sb.peq = E->d_peq.p; sb.cells = cells; sb.peq_words = peq_words;
+        const size_t carry_stride = ((size_t)max_wlen + 64 + 15) & ~(size_t)15;
+        CK(E->d_carry.reserve(carry_stride * n_big_warps));
+        // the few giant gaps (one warp each, latency-bound: 25 ms for a handful of them) run beside the three small-gap
+        // launches on a side stream: disjoint job queues, disjoint result slots
+        cudaStream_t bs = ctx->side[0];
+        CK(cudaStreamWaitEvent(bs, E->ev[2], 0));
+        gap_big_kernel<<<n_big_warps / kBigWarps, kBigWarps * 32, 0, bs>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
+                                                       pb.queue[3], pb.queue[4], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
+                                                       E->d_counters.p + 3); ++g_lesv_launches;
+        CK(cudaEventRecord(E->ev[3], bs));
         const unsigned small_grid = (unsigned)dev_sms * 8;
         gap_small_kernel<kSmallCells0, 0><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,
                                                                      E->d_jobs.p, pb.queue[0], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
@@ -921,13 +934,7 @@ extern "C" int lesvgpu_map_batch(lesvgpu_ctx* ctx, const uint8_t* query_pac, con
                                                                      E->d_jobs.p, pb.queue[1], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
         gap_small_kernel<kSmallCells2, 2><<<small_grid, 128, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p,
                                                                      E->d_jobs.p, pb.queue[2], pb.queue_count, E->d_slots.p); ++g_lesv_launches;
-        SlabBufs sb;
-        sb.P = E->d_P.p; sb.M = E->d_M.p; sb.score = E->d_score.p; sb.peq = E->d_peq.p; sb.cells = cells; sb.peq_words = peq_words;
-        const size_t carry_stride = ((size_t)max_wlen + 64 + 15) & ~(size_t)15;
-        CK(E->d_carry.reserve(carry_stride * n_big_warps));
-        gap_big_kernel<<<n_big_warps / kBigWarps, kBigWarps * 32, 0, s>>>(E->d_wins.p, M->d_reads.p, M->d_qpac.p, ctx->d_subject.p, E->d_cand_list.p, E->d_jobs.p,
-                                                       pb.queue[3], pb.queue[4], pb.queue_count, E->d_slots.p, sb, E->d_carry.p, carry_stride,
-                                                       E->d_counters.p + 3); ++g_lesv_launches;
+        CK(cudaStreamWaitEvent(s, E->ev[3], 0));
         CK(cudaEventRecord(E->ev[1], s));
         TraceBufs tb;
         tb.sb = sb;
