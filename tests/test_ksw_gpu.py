@@ -127,6 +127,44 @@ def test_full_matrix_alignments_as_column_strips(ctx):
         assert r.ok and [int(x) for x in cg] == exp
 
 
+def test_column_strips_fold_rows_for_any_length_ratio(ctx):
+    """The strips store row r at physical row r % qlen, block B at slot B + r / qlen (ksw_kernels.cuh: fold_tb_bytes).
+    Lengths far apart exercise one to five passes over the physical rows, in both directions; the unrelated pair makes
+    the walk leave the diagonal early (long leading / trailing gaps)."""
+    from lesv_b200.synth import mutate
+    rng = np.random.default_rng(77)
+    qs, ts = [], []
+    t = rng.integers(0, 4, 13000, dtype=np.uint8)
+    qs.append(np.ascontiguousarray(mutate(t, 0.1, rng)[4000:8200])); ts.append(t)           # qlen 4.2 k, tlen 13 k: 5 passes
+    t = rng.integers(0, 4, 12500, dtype=np.uint8)
+    q = np.ascontiguousarray(np.concatenate([rng.integers(0, 4, 9000, dtype=np.uint8), mutate(t, 0.12, rng),
+                                             rng.integers(0, 4, 8000, dtype=np.uint8)]))    # qlen ~29.5 k, tlen 12.5 k: 2 passes
+    qs.append(q); ts.append(t)
+    t = rng.integers(0, 4, 16001, dtype=np.uint8)
+    qs.append(np.ascontiguousarray(mutate(t, 0.15, rng))); ts.append(t)                     # about equal lengths
+    qs.append(rng.integers(0, 4, 6000, dtype=np.uint8)); ts.append(rng.integers(0, 4, 12000, dtype=np.uint8))   # unrelated
+    res, cigs = ctx.ksw_batch(qs, ts, [-1] * len(qs))
+    for q, t, r, cg in zip(qs, ts, res, cigs):
+        exp, _ = H.oracle_ksw(q, t, -1)
+        assert r.ok and [int(x) for x in cg] == exp, (len(q), len(t))
+
+
+def test_band_classes_around_the_single_cta_limit(ctx):
+    """Banded (not full-matrix) alignments whose band window is just below and above what one CTA holds: tier 608, tier 736
+    (24 warps, 80 registers) and the 2-CTA cluster."""
+    from lesv_b200.synth import mutate
+    rng = np.random.default_rng(31)
+    cases = []
+    for w in (9500, 10400, 11700, 11900, 13000):
+        q = rng.integers(0, 4, 16000, dtype=np.uint8)
+        t = np.ascontiguousarray(mutate(q, 0.12, rng))
+        cases.append((q, t, w))
+    q = rng.integers(0, 4, 17000, dtype=np.uint8)
+    t = np.ascontiguousarray(np.concatenate([q[:6000], q[9000:]]))                          # 3 kb deletion inside a 11 k band
+    cases.append((q, mutate(t, 0.1, rng), 11000))
+    _check(ctx, [(q, np.ascontiguousarray(t), w) for q, t, w in cases])
+
+
 @pytest.mark.parametrize("switch", ["LESV_KSW_NO_GROUPS", "LESV_KSW_NO_STRIPS"])
 def test_environment_switches_select_tested_paths(switch):
     """The two environment switches of the scheduler (lesvgpu.cu: narrow bands without lane groups, full-matrix
