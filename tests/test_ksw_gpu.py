@@ -75,18 +75,20 @@ def test_identity_counts(ctx):
 
 
 def test_wide_bands_run_on_clusters(ctx):
-    """Bands wider than 640 blocks run on thread-block clusters (carries through DSMEM)."""
+    """Band windows wider than the single-CTA tiers: without a band (w = -1) these run as column strips or, up to 736
+    blocks, in one CTA of 24 warps; with LESV_KSW_NO_STRIPS they take thread-block clusters (carries through DSMEM, see
+    test_environment_switches_select_tested_paths); banded windows of that width: test_band_classes_around_the_single_cta_limit."""
     from lesv_b200.synth import mutate
     rng = np.random.default_rng(21)
     cases = []
-    for n in (9100, 11000, 15000):                     # 1 CTA x 576 threads, then clusters of 2
+    for n in (9100, 11000, 15000):                     # 1 CTA x 576 / 704 threads, then 4 strips
         q = rng.integers(0, 4, n, dtype=np.uint8)
         t = np.ascontiguousarray(mutate(q, 0.12, rng))
         cases.append((q, t, -1))                       # no band: max(qlen, tlen)
     q = rng.integers(0, 4, 9000, dtype=np.uint8)
     t = np.ascontiguousarray(np.concatenate([q[:4000], q[5500:]]))      # 1.5 kb deletion
     cases.append((q, t, max(len(q), len(t))))
-    q = rng.integers(0, 4, 24000, dtype=np.uint8)       # cluster of 4
+    q = rng.integers(0, 4, 24000, dtype=np.uint8)       # 6 strips
     cases.append((q, np.ascontiguousarray(mutate(q, 0.1, rng)), -1))
     _check(ctx, cases)
 
