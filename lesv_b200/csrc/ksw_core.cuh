@@ -52,6 +52,7 @@
 // lane with multiply-adds (the other pipe) and one PRMT per four columns gathers the bytes.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define KSW_HD __host__ __device__ __forceinline__
@@ -332,6 +333,15 @@ KSW_HD int tb_row_blocks(int qlen, int tlen, int w)
     n = n < w + 1 ? n : w + 1;
     return (n + 15) / 16 + 1;
 }
+
+// Traceback of a full-matrix alignment (column strips): without a band every column t is live in exactly the qlen rows
+// t .. t+qlen-1, so rows r and r +- qlen never share a column and the row-major layout of the banded kernels (one slot per
+// anti-diagonal, sized for the widest one) would leave half of the arena empty.  The strips fold the rows modulo qlen: row
+// r lies in physical row r % qlen, block B at slot B + r / qlen -- the shift keeps the 16-aligned blocks of two passes,
+// which may share a boundary block, apart.
+KSW_HD int fold_passes(int qlen, int tlen) { return (qlen + tlen - 2) / qlen + 1; }
+KSW_HD size_t fold_row_bytes(int qlen, int tlen) { return ((size_t)((tlen - 1) >> 4) + 1 + (size_t)fold_passes(qlen, tlen)) * 16; }
+KSW_HD size_t fold_tb_bytes(int qlen, int tlen) { return (size_t)qlen * fold_row_bytes(qlen, tlen); }
 
 // What a block at an edge of the band has to know about row r.  The numbers are the same for every thread, so a
 // kernel may compute them once per row for the whole CTA (a table in shared memory, filled a chunk of rows ahead)

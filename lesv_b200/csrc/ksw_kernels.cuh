@@ -75,15 +75,6 @@ constexpr int kTierXL = KSW_TIER_XL;
 // For these classes the "clusters" of a launch are lane groups and `nt` is the group size.
 constexpr int kGroupTierMax = 16;
 
-// Traceback of a full-matrix alignment (column strips): without a band every column t is live in exactly the qlen rows
-// t .. t+qlen-1, so rows r and r +- qlen never share a column and the row-major layout of the banded kernels (one slot per
-// anti-diagonal, sized for the widest one) would leave half of the arena empty.  The strips fold the rows modulo qlen: row
-// r lies in physical row r % qlen, block B at slot B + r / qlen -- the shift keeps the 16-aligned blocks of two passes,
-// which may share a boundary block, apart.
-__host__ __device__ static inline int fold_passes(int qlen, int tlen) { return (qlen + tlen - 2) / qlen + 1; }
-__host__ __device__ static inline size_t fold_row_bytes(int qlen, int tlen) { return ((size_t)((tlen - 1) >> 4) + 1 + (size_t)fold_passes(qlen, tlen)) * 16; }
-__host__ __device__ static inline size_t fold_tb_bytes(int qlen, int tlen) { return (size_t)qlen * fold_row_bytes(qlen, tlen); }
-
 // largest band window (in 16-column blocks) the register-resident kernel with NT threads holds
 __host__ __device__ static inline int window_blocks(int tlen, int w)
 {

@@ -228,3 +228,26 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
     }
     return n;
 }
+
+// Folded traceback of the column strips (ksw_core.cuh: fold_row_bytes): every block the kernel stores for a full-matrix
+// alignment -- blocks st0 >> 4 .. en0 >> 4 of every row -- must get a slot of its own inside qlen x fold_row_bytes bytes.
+// Returns the number of collisions plus out-of-range slots (0 = the layout holds).
+extern "C" long lesv_emul_fold_check(int qlen, int tlen)
+{
+    using namespace lesvksw;
+    const int w = qlen > tlen ? qlen : tlen;
+    const size_t row_blocks = fold_row_bytes(qlen, tlen) / 16;
+    std::vector<uint8_t> used((size_t)qlen * row_blocks, 0);
+    long bad = 0;
+    for (int r = 0; r < qlen + tlen - 1; ++r) {
+        const RowGeom g = row_geom(r, qlen, tlen, w);
+        const int pass = r / qlen;
+        for (int B = g.st0 >> 4; B <= (g.en0 >> 4); ++B) {
+            const size_t slot = (size_t)B + (size_t)pass;
+            if (slot >= row_blocks) { ++bad; continue; }
+            uint8_t& u = used[(size_t)(r % qlen) * row_blocks + slot];
+            bad += u; u = 1;
+        }
+    }
+    return bad + (fold_tb_bytes(qlen, tlen) != (size_t)qlen * row_blocks * 16);
+}

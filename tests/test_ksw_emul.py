@@ -106,3 +106,16 @@ def test_strip_schedule_equals_oracle():
             assert got == exp, (it, len(q), len(t), w, sw)
             n += 1
     assert n == 72
+
+
+def test_folded_strip_traceback_has_a_slot_for_every_block():
+    """Column strips store row r of a full-matrix alignment at physical row r % qlen, block B at slot B + r / qlen
+    (ksw_core.cuh: fold_row_bytes): no two stored blocks may share a slot, for any ratio of the lengths."""
+    import ctypes
+    lib = H.emul()
+    lib.lesv_emul_fold_check.restype = ctypes.c_long
+    rng = np.random.default_rng(9)
+    shapes = [(1, 1), (1, 500), (500, 1), (16, 16), (17, 33), (1000, 1000), (999, 4001), (4001, 999), (50, 3000), (3000, 50)]
+    shapes += [(int(rng.integers(1, 2500)), int(rng.integers(1, 2500))) for _ in range(150)]
+    for qlen, tlen in shapes:
+        assert lib.lesv_emul_fold_check(qlen, tlen) == 0, (qlen, tlen)
