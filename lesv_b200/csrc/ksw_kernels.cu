@@ -7,13 +7,14 @@
 // entirely in registers (ksw_core.cuh).  Thread tid owns the block B == tid (mod NT) of the live
 // window; as the band slides right along the anti-diagonals a thread drops the block that left
 // on the left and picks up the one NT blocks further right.  Per anti-diagonal each thread does
-// one block update (~300 integer instructions for 16 cells), hands its column-15 values to its
-// right neighbour (warp shuffle; shared memory across warps) and stores 16 traceback bytes with
-// one coalesced 128-bit store.  One __syncthreads per anti-diagonal.  The packed target and the
+// one block update (~310 integer instructions for 16 cells), leaves its column-15 values in shared
+// memory for its right neighbour and stores 16 traceback bytes with one coalesced 128-bit store.
+// One named barrier per anti-diagonal among the warps that hold blocks.  The packed target and the
 // packed reversed query (2 bits per base) are staged in shared memory once per alignment.
 // CTAs are persistent and pull alignments from a queue sorted by decreasing cost; each CTA owns
-// one traceback arena in HBM that is reused from alignment to alignment.  After the last
-// anti-diagonal warp 0 walks the traceback (64 rows prefetched per round trip to HBM).
+// one traceback arena in HBM that is reused from alignment to alignment.  The traceback of an
+// alignment is walked by one warp (64 rows prefetched per round trip to HBM) -- in the kernel of the
+// wide single-CTA tiers by an extra warp, while the other warps already fill the next alignment.
 #include "ksw_kernels.cuh"
 #include "ksw_core.cuh"
 #include "gpu_prims.cuh"
@@ -283,13 +284,12 @@ __device__ void backtrack_warp(const KswJob& job, const uint8_t* __restrict__ ar
 // ---------------------------------------------------------------------------------------------
 // DP kernel
 // ---------------------------------------------------------------------------------------------
-// No CTA-wide barrier inside the anti-diagonal loop.  The only cross-thread dependency of a row is
-// "column 15 of the block to my left, one row earlier": inside a warp that is a shuffle of a value
-// the neighbour lane already holds; across warps (and, for clusters, across CTAs) it goes through a
-// small ring of tagged slots in (distributed) shared memory.  Lane 31 of a warp publishes after its
-// row, lane 0 of the next warp picks the value up just before it needs it (pair 0 is processed
-// last), so warps drift apart by a row or two instead of all waiting for the slowest one.  A
-// consumed-rows counter flowing the other way keeps a producer from lapping its consumer.
+// The only cross-thread dependency of a row is "column 15 of the block to my left, one row earlier".  Inside a CTA every
+// thread leaves those values in shared memory and a barrier ends the row (a polled ring between the warps of one SM was
+// measured slower, twice: the warps of the busiest scheduler set the pace either way and polling costs them issue slots).
+// Across the CTAs of a cluster no barrier is cheap: the last lane of a CTA publishes into a small ring of tagged slots in
+// the next CTA's shared memory (DSMEM), the first lane of that CTA picks the value up just before it needs it (pair 0 is
+// processed last), and a consumed-rows counter flowing the other way keeps a producer from lapping its consumer.
 constexpr int kMaxNT = 640;
 constexpr int kMaxWarps = kMaxNT / 32;
 constexpr int kRingD = 4;
@@ -351,10 +351,10 @@ __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t
 __device__ __forceinline__ void stamp_start(int* counter) { atomicMin(reinterpret_cast<unsigned long long*>(counter + 2), global_ns()); }
 __device__ __forceinline__ void stamp_end(int* counter) { atomicMax(reinterpret_cast<unsigned long long*>(counter + 4), global_ns()); }
 
-// kCluster = false: one CTA per alignment, one CTA barrier per anti-diagonal (waiting warps sleep; a polled ring was
-//                   measured slower here: polling lanes burn issue slots of the SMSPs that are the bottleneck).
-// kCluster = true:  one alignment on a thread-block cluster; inside a CTA and across CTAs the carries go through the
-//                   tagged slots described above (no barrier spans CTAs cheaply).
+// kCluster = false: one CTA per alignment (tiers of 32..160 threads, and wider ones whose sequences do not fit the double
+//                   buffer of ksw_dp_overlap_kernel); warp 0 walks the traceback after the last row.
+// kCluster = true:  one alignment on a thread-block cluster; the carry into the first and out of the last thread of a
+//                   CTA crosses CTAs through the tagged slots described above.
 template <bool kCluster>
 __global__ void __launch_bounds__(kMaxNT)
 ksw_dp_kernel(const KswJob* __restrict__ jobs, const int* __restrict__ order, int njobs,
