@@ -1074,12 +1074,8 @@ cudaError_t launch_ksw(int nt, int ncta, int n_clusters, size_t smem, const KswJ
         cfg.gridDim = dim3((unsigned)n_clusters);
         if (nt >= kTierLow && 2 * smem <= 200 * 1024) {
             // DP of alignment m overlapped with the traceback walk of alignment m-1 (one extra warp)
-#ifdef KSW_ONE_TIER
-            auto kern = ksw_dp_overlap_kernel<kTierTop>;
-#else
             auto kern = nt <= kTierLow ? ksw_dp_overlap_kernel<kTierLow> : nt <= kTierMid ? ksw_dp_overlap_kernel<kTierMid>
                       : nt <= kTierTop ? ksw_dp_overlap_kernel<kTierTop> : ksw_dp_overlap_kernel<kTierXL>;
-#endif
             lesv_need_smem(kern, 2 * smem);
             cfg.blockDim = dim3((unsigned)nt + 32); cfg.dynamicSmemBytes = 2 * smem;
             return cudaLaunchKernelEx(&cfg, kern, d_jobs, d_order, njobs, d_pool, d_arena, arena_stride,
