@@ -407,7 +407,10 @@ KSW_HD uint32_t query_window(ThreadCtx& c, const uint32_t* qrp, int qlen, int r,
 #if defined(__CUDA_ARCH__)
 KSW_HD bool warp_all(bool p) { return __all_sync(0xFFFFFFFFu, p); }
 #else
-KSW_HD bool warp_all(bool p) { return p; }
+// Host emulation (tests/emul): one thread is its own warp.  With the switch off every row goes through the band-edge
+// path, which is what a block strictly inside the band executes on the GPU whenever another lane of its warp is not.
+static bool g_ksw_emul_lean = true;
+KSW_HD bool warp_all(bool p) { return p && g_ksw_emul_lean; }
 #endif
 
 // tp: packed target words (block B -> tp[B]); qrp: packed reversed query, word index offset by

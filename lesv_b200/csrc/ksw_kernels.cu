@@ -821,7 +821,6 @@ ksw_dp_strip_kernel(const KswJob* __restrict__ jobs, const StripJob* __restrict_
     __shared__ int sh_job, sh_last;
     __shared__ int bt_dummy;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kStripNT / 32;
     bool first = true;
     if (tid == 0) stamp_start(counter);
     for (;;) {

@@ -25,6 +25,7 @@ static int emul_impl(int qlen, const uint8_t* query, int tlen, const uint8_t* ta
                      int skew_k = 0, unsigned seed = 0);
 static int g_eager = 0;     // 1: step with thread_row_step<true> (carry resolved up front, barrier-mode kernel)
 extern "C" void lesv_emul_set_eager(int on) { g_eager = on; }
+extern "C" void lesv_emul_set_lean(int on) { lesvksw::g_ksw_emul_lean = on != 0; }
 static int g_strip = 0;     // > 0: column strips of g_strip blocks, one strip after the other (ksw_dp_strip_kernel)
 extern "C" void lesv_emul_set_strip(int blocks) { g_strip = blocks; }
 

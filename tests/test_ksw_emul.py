@@ -119,3 +119,25 @@ def test_folded_strip_traceback_has_a_slot_for_every_block():
     shapes += [(int(rng.integers(1, 2500)), int(rng.integers(1, 2500))) for _ in range(150)]
     for qlen, tlen in shapes:
         assert lib.lesv_emul_fold_check(qlen, tlen) == 0, (qlen, tlen)
+
+
+def test_inner_blocks_through_the_band_edge_path_equal_oracle():
+    """On the GPU a block strictly inside the band takes the lean path only if all 32 blocks of its warp do; in a warp
+    that holds a band edge it runs through the general path with an all-ones fresh-column mask.  The emulator forces
+    that for every row (lesv_emul_set_lean(0)): CIGARs must not change."""
+    lib = H.emul()
+    rng = np.random.default_rng(321)
+    lib.lesv_emul_set_lean(0)
+    try:
+        n = 0
+        for it in range(500):
+            q, t, w = H.random_pair(rng, it)
+            if not H.oracle_cells(len(q), len(t), w)[1]:
+                continue
+            need = H.min_threads(len(q), len(t), w)
+            a, _ = H.oracle_ksw(q, t, w)
+            assert a == H.emul_ksw(q, t, w, need + int(it % 3), eager=bool(it & 1)), (it, len(q), len(t), w)
+            n += 1
+        assert n > 250
+    finally:
+        lib.lesv_emul_set_lean(1)
